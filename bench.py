@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the NeRF render hot path on B200 (contract: see DESIGN.md "Measurement").
+
+Workload at every N: BASELINE.json configs[1], the volume-render composite micro-bench -
+2^20 rays x 64 samples per GPU, fp32, forward + backward of VolumeRenderer
+(reference: src/models/nerf_mlp.py:165-215).  One "step" = one forward (rgb, depth, weights
+out) + one backward (g_rgb, g_depth in; d_rgb, d_density out) over one batch of synthetic
+Blender-lego-shaped rays.  Rays are independent, so N GPUs each composite their own 2^20 rays
+(weak scaling, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path
+  python bench.py --impl reference ...                          the reference's CPU path (oracle
+                                                                port of it) on the host cores
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "nerf-few-shot-limitations_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+N_RAYS = 1 << 20
+N_SAMPLES = 64
+# algorithmic bytes per ray (SURVEY.md section 8d / DESIGN.md K1)
+FWD_BYTES = 24 * N_SAMPLES + 28          # read rgb 12S, density 4S, z 4S, rays_d 12; write rgb 12, depth 4, weights 4S
+BWD_BYTES = 36 * N_SAMPLES + 28          # read 20S + rays_d 12 + g_rgb 12 + g_depth 4; write d_rgb 12S + d_density 4S
+WORKLOAD = "composite_fwd_bwd_1Mrays_x64_fp32"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(n_rays, n_samples, seed, device):
+    """Synthetic lego-shaped batch (SURVEY.md section 8d cfg 2): rgb~U[0,1), density~10*N(0,1),
+    z = one stratified draw in [2,6], unnormalised rays_d from an 800x800 Blender camera."""
+    from oracle import nerf_oracle as O     # synthetic-ray generator only (inputs, not compute)
+    g = torch.Generator().manual_seed(seed)
+    _, rays_d = O.lego_rays(n_rays, seed=seed)
+    rgb = torch.rand(n_rays, n_samples, 3, generator=g)
+    density = torch.randn(n_rays, n_samples, 1, generator=g) * 10.0
+    t = torch.linspace(0.0, 1.0, n_samples)
+    zb = 2.0 * (1 - t) + 6.0 * t
+    mids = 0.5 * (zb[1:] + zb[:-1])
+    lower, upper = torch.cat([zb[:1], mids]), torch.cat([mids, zb[-1:]])
+    z = lower + (upper - lower) * torch.rand(n_rays, n_samples, generator=g)
+    target = torch.rand(n_rays, 3, generator=g)
+    depth_t = 2.0 + 4.0 * torch.rand(n_rays, generator=g)
+    outs = dict(rgb=rgb, density=density, z=z, rays_d=rays_d, target=target, depth_t=depth_t)
+    if device is not None:
+        outs = {k: v.to(device) for k, v in outs.items()}
+    return outs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.path = None, None
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_reference_rate(n_rays, reps, threads):
+    """The reference's CPU path for this workload (oracle port = the same ATen op sequence as
+    VolumeRenderer.forward + autograd backward) on `threads` host threads; returns rays/s and
+    seconds per pass on an n_rays sample of the bench workload."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(threads)
+    d = make_inputs(n_rays, N_SAMPLES, seed=0, device=None)
+    rgb, den = d["rgb"].requires_grad_(), d["density"].requires_grad_()
+    g_rgb = torch.randn(n_rays, 3) / n_rays
+    g_depth = torch.randn(n_rays) / n_rays
+    best, total = float("inf"), 0.0
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        o = O.render(rgb, den, d["z"], d["rays_d"])
+        torch.autograd.grad([o[0], o[1]], [rgb, den], [g_rgb, g_depth])
+        dt = time.perf_counter() - t0
+        if i:                      # first pass warms the allocator / thread pool
+            best = min(best, dt)
+            total += dt
+    return n_rays / (total / reps), total / reps, n_rays / best
+
+
+def run_reference(args):
+    """--impl reference: CPU arm.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 1 << 17                                    # 1/8 of the workload per step (~0.3 s on 8 cores)
+    torch.set_num_threads(threads)
+    rate_w, _, _ = cpu_reference_rate(sample, max(1, args.warmup), threads) if args.warmup else (0, 0, 0)
+    rate, sec, best = cpu_reference_rate(sample, max(1, args.steps), threads)
+    line = {
+        "impl": "reference", "metric": "rays/sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays": N_RAYS, "samples": N_SAMPLES,
+                   "note": "each step = a 131072-ray sample of the workload, fwd+autograd bwd, ATen CPU"},
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": "131072 of 1048576 rays x 64 samples per step, fwd + autograd bwd"},
+        "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from nfs_b200 import _lib, ops
+    from nfs_b200._lib import ptr
+    from models.nerf_mlp import VolumeRenderer
+    import ctypes
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    d = make_inputs(N_RAYS, N_SAMPLES, seed=rank, device=dev)
+    rgb, den, z, rays_d = d["rgb"], d["density"].reshape(N_RAYS, N_SAMPLES), d["z"], d["rays_d"]
+    out_rgb = torch.empty(N_RAYS, 3, device=dev)
+    out_depth = torch.empty(N_RAYS, device=dev)
+    out_w = torch.empty(N_RAYS, N_SAMPLES, device=dev)
+    d_rgb, d_den = torch.empty_like(rgb), torch.empty_like(den)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def fwd():
+        _lib.call("nfs_composite_fwd", ptr(rgb), ptr(den), ptr(z), ptr(rays_d), None, 0.0, N_RAYS, N_SAMPLES,
+                  0, 0, ptr(out_rgb), ptr(out_depth), ptr(out_w), stream)
+
+    # upstream gradients of loss = mse(rgb, target) + 0.1 * mean|depth - d*| at the first forward
+    fwd()
+    g_rgb = (2.0 / (3 * N_RAYS)) * (out_rgb - d["target"])
+    g_depth = (0.1 / N_RAYS) * torch.sign(out_depth - d["depth_t"])
+
+    def bwd():
+        _lib.call("nfs_composite_bwd", ptr(rgb), ptr(den), ptr(z), ptr(rays_d), None, 0.0, ptr(g_rgb),
+                  ptr(g_depth), None, N_RAYS, N_SAMPLES, 0, 0, ptr(d_rgb), ptr(d_den), stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        fwd(); bwd()
+    sync_all()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    launches0 = _lib.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # inputs (1.34 GB) + outputs (1.35 GB) per step far exceed the 126 MB L2: no flush needed
+    start.record()
+    for i in range(steps):
+        ev[i][0].record(); fwd(); ev[i][1].record(); bwd(); ev[i][2].record()
+    stop.record()
+    sync_all()
+    launches = _lib.launch_count() - launches0
+    elapsed_ms = start.elapsed_time(stop)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    clk = clocks.stop() if clocks is not None else None
+    value = world * N_RAYS * steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
+    vr = VolumeRenderer().eval()
+    host = {k: d[k].cpu().pin_memory() for k in ("rgb", "density", "z", "rays_d", "target", "depth_t")}
+    h_out = torch.empty(N_RAYS, 4, pin_memory=True)
+    h_loss = torch.empty(1, pin_memory=True)
+
+    def e2e_step():
+        r = host["rgb"].to(dev, non_blocking=True).requires_grad_()
+        s = host["density"].to(dev, non_blocking=True).requires_grad_()
+        zz = host["z"].to(dev, non_blocking=True)
+        dd = host["rays_d"].to(dev, non_blocking=True)
+        tg = host["target"].to(dev, non_blocking=True)
+        dt = host["depth_t"].to(dev, non_blocking=True)
+        o_rgb, o_depth, _ = vr(r, s, zz, dd)
+        loss = ((o_rgb - tg) ** 2).mean() + 0.1 * (o_depth - dt).abs().mean()
+        loss.backward()
+        h_out[:, :3].copy_(o_rgb.detach(), non_blocking=True)
+        h_out[:, 3].copy_(o_depth.detach(), non_blocking=True)
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        return r.grad, s.grad
+
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_RAYS * e2e_steps / (float(t.item()) * 1e-3)
+    h2d = sum(host[k].numel() * 4 for k in host)
+    d2h = h_out.numel() * 4 + 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    dom_ms, dom_bytes, dom = (bwd_ms, BWD_BYTES, "composite_bwd_kernel") if bwd_ms >= fwd_ms else \
+        (fwd_ms, FWD_BYTES, "composite_fwd_kernel")
+    achieved = dom_bytes * N_RAYS / (dom_ms * 1e-3) / 1e9
+    line = {
+        "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "samples": N_SAMPLES,
+                   "l2": "inputs+outputs 2.7 GB per step >> 126 MB L2, no flush needed",
+                   "upstream_grads": "d/d(rgb,depth) of mse(rgb,target)+0.1*mean|depth-d*|"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": dom_bytes * N_RAYS, "ms_per_launch": dom_ms,
+                     "fwd": {"ms": fwd_ms, "gbs": FWD_BYTES * N_RAYS / (fwd_ms * 1e-3) / 1e9},
+                     "bwd": {"ms": bwd_ms, "gbs": BWD_BYTES * N_RAYS / (bwd_ms * 1e-3) / 1e9},
+                     "step_gbs": (FWD_BYTES + BWD_BYTES) * N_RAYS * steps / (elapsed_ms * 1e-3) / 1e9},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "models.nerf_mlp.VolumeRenderer + autograd, pinned host buffers"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            line["roofline"]["traffic"] = json.load(open(traffic_file)).get(dom)
+        except Exception:
+            pass
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 1 << 17
+        rate, sec, best = cpu_reference_rate(sample, 8, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": "8 passes over 131072 of the 1048576 rays x 64 samples, fwd + autograd "
+                                          "bwd, %.2f s per pass" % sec}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

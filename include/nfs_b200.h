@@ -1,0 +1,142 @@
+/*
+ * nfs_b200.h — C ABI of the B200 (sm_100a) NeRF render hot path.
+ *
+ * This is the drop-in boundary below the reference's Python import surface
+ * (src/models/*.py + src/utils/ray_utils.py of ANKITSANJYAL/nerf-few-shot-limitations).
+ * The reference has no FFI layer of its own: its "operator API" is a set of
+ * Python functions / nn.Modules that run chains of ATen ops.  Each entry point
+ * below replaces one such chain and cites it (file:line, relative to the
+ * reference root).  The Python wrappers in nerf-few-shot-limitations_b200/
+ * bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless named
+ *     h_* ; all float tensors are fp32, row-major, contiguous;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success, a positive cudaError_t value when
+ *     the CUDA runtime reported an error, or a negative NFS_E_* code for an
+ *     argument error.  nfs_last_error_string() describes the last failure of
+ *     the calling thread.  Nothing here synchronises the device.
+ *   - no CPU fallback exists: without a CUDA device the functions return the
+ *     runtime's error.
+ */
+#ifndef NFS_B200_H_
+#define NFS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFS_B200_ABI_VERSION 1
+
+/* negative return codes (argument errors) */
+#define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
+#define NFS_E_TOOLARGE (-2)  /* size above what the kernel supports         */
+#define NFS_E_ALIGN    (-3)  /* pointer not aligned as the kernel requires  */
+#define NFS_E_UNSUPPORTED (-4)
+
+int         nfs_abi_version(void);
+const char *nfs_last_error_string(void);
+/* Number of kernels this library has launched since load (per process);
+ * bench.py reports the delta over its timed region as gpu_launches. */
+uint64_t    nfs_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * K1 — alpha compositing (volume rendering)
+ *   replaces VolumeRenderer.forward        src/models/nerf_mlp.py:165-215
+ *        and volume_render_radiance        src/models/volume_renderer.py:4-43
+ *
+ *   dists_i = (z_{i+1}-z_i) (last = 1e10) * ||rays_d||      nerf_mlp.py:181-185
+ *   alpha_i = 1 - exp(-relu(density_i [+ noise_i*noise_std]) * dists_i)   :188-193
+ *   T_i     = prod_{k<i} ((1-alpha_k) + 1e-10)              :196-199
+ *   w_i     = alpha_i * T_i                                 :202
+ *   rgb = sum w_i rgb_i ; depth = sum w_i z_i               :205-208
+ *   white_bkgd: rgb += 1 - sum w_i                          :211-213
+ *
+ * Layouts (packed == 0, the VolumeRenderer form):
+ *   rgb (N,S,3)  density (N,S)  z_vals (N,S)  rays_d (N,3)  noise (N,S)|NULL
+ * Layout (packed != 0, the volume_render_radiance form):
+ *   rgb = rgb_sigma (N,S,4) [R,G,B,sigma]; density is ignored (pass NULL).
+ * Outputs: out_rgb (N,3); out_depth (N)|NULL; out_weights (N,S)|NULL.
+ * One sub-warp (8/16/32 lanes) composites one ray; 128-bit loads when S%4==0.
+ * ------------------------------------------------------------------------- */
+int nfs_composite_fwd(const float *rgb, const float *density, const float *z_vals,
+                      const float *rays_d, const float *noise, float noise_std,
+                      int64_t n_rays, int32_t n_samples,
+                      int32_t white_bkgd, int32_t packed,
+                      float *out_rgb, float *out_depth, float *out_weights,
+                      void *stream);
+
+/* Backward of the above by recomputation from the inputs (nothing is saved by
+ * the forward).  Closed form of the autograd graph of nerf_mlp.py:181-215:
+ *   G_i       = g_rgb.rgb_i + g_depth z_i + g_w_i - white_bkgd * sum_c g_rgb_c
+ *   d rgb_i   = w_i g_rgb
+ *   d alpha_i = G_i T_i - (sum_{k>i} G_k w_k) / q_i ,  q_i = (1-alpha_i)+1e-10
+ *   d dens_i  = d alpha_i * dists_i * exp(-relu(dens_i) dists_i) * [dens_i > 0]
+ * g_rgb (N,3); g_depth (N)|NULL; g_weights (N,S)|NULL.
+ * d_rgb (N,S,3) and d_density (N,S)  — or, packed, d_rgb = d_rgb_sigma (N,S,4)
+ * and d_density NULL.  z_vals / rays_d never receive gradients (no reference
+ * caller asks for them). */
+int nfs_composite_bwd(const float *rgb, const float *density, const float *z_vals,
+                      const float *rays_d, const float *noise, float noise_std,
+                      const float *g_rgb, const float *g_depth, const float *g_weights,
+                      int64_t n_rays, int32_t n_samples,
+                      int32_t white_bkgd, int32_t packed,
+                      float *d_rgb, float *d_density,
+                      void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2 — positional encoding
+ *   replaces PositionalEncoding.forward   src/models/positional_encoding.py:20-33
+ *        and nerf_mlp.PositionalEncoding.forward  src/models/nerf_mlp.py:17-33
+ *   out[p] = [x (if include_input), sin(x f_0), cos(x f_0), ..., cos(x f_{L-1})]
+ *   x (P,D) -> out (P, D*(2L+include_input)); freqs: L floats (device).
+ * ------------------------------------------------------------------------- */
+int nfs_posenc_fwd(const float *x, const float *freqs, int64_t n_points,
+                   int32_t dim, int32_t n_freqs, int32_t include_input,
+                   float *out, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4a — stratified sampling along rays
+ *   replaces models.ray_sampler.sample_points_along_rays  src/models/ray_sampler.py:47-61
+ *        and utils.ray_utils.sample_points_along_rays     src/utils/ray_utils.py:55-84
+ *   The S-entry tables z_base / lower / upper are the reference's own
+ *   torch.linspace arithmetic (ray_utils.py:59-76) evaluated once on the host
+ *   and uploaded; the kernel does, with un-contracted fp32 mul/add,
+ *     z   = t_rand ? lower + (upper-lower)*t_rand : z_base      ray_utils.py:79
+ *     pts = rays_o + rays_d * z                                ray_utils.py:82
+ *   rays_o, rays_d (N,3); t_rand (N,S)|NULL; z_out (N,S); pts_out (N,S,3)|NULL.
+ * ------------------------------------------------------------------------- */
+int nfs_sample_stratified(const float *rays_o, const float *rays_d,
+                          const float *z_base, const float *lower, const float *upper,
+                          const float *t_rand, int64_t n_rays, int32_t n_samples,
+                          float *z_out, float *pts_out, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4b — hierarchical (inverse-CDF) sampling
+ *   replaces utils.ray_utils.hierarchical_sampling   src/utils/ray_utils.py:101-143
+ *   z_vals (N,M+1) coarse depths (bin edges), weights (N,M), u (N,Ni) with row
+ *   stride u_stride (0 = one row broadcast to all rays, the perturb=False
+ *   linspace table).  cdf_in (N,M+1)|NULL: when given it is used instead of
+ *   the kernel's own cdf (kernel-level parity against the oracle's cdf).
+ *   Outputs: z_out (N,M+1+Ni) sorted ascending; pts_out (N,M+1+Ni,3)|NULL;
+ *   debug (all optional): cdf_out (N,M+1), idx_out (N,Ni) int64 searchsorted
+ *   indices, samples_out (N,Ni) the un-merged fine samples.
+ *   One warp per ray; cdf = fp64-accumulated cumsum rounded per entry (ATen CPU
+ *   semantics), searchsorted(right=True), un-contracted interpolation, bitonic
+ *   merge-sort in shared memory.  M+1+Ni <= 4096.
+ * ------------------------------------------------------------------------- */
+int nfs_sample_hierarchical(const float *rays_o, const float *rays_d,
+                            const float *z_vals, const float *weights,
+                            const float *u, int64_t u_stride, const float *cdf_in,
+                            int64_t n_rays, int32_t n_bins, int32_t n_importance,
+                            float *z_out, float *pts_out,
+                            float *cdf_out, int64_t *idx_out, float *samples_out,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFS_B200_H_ */

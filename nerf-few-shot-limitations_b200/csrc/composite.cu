@@ -1,0 +1,467 @@
+// K1 — alpha compositing forward / backward for sm_100a.
+//
+// Replaces the ~20 (forward) + ~30 (autograd backward) full-tensor ATen passes of
+//   VolumeRenderer.forward          /root/reference/src/models/nerf_mlp.py:165-215
+//   volume_render_radiance          /root/reference/src/models/volume_renderer.py:4-43
+// with one pass over the inputs per direction.
+//
+// Mapping: a sub-warp ("group") of G lanes owns one ray; each lane owns 4
+// CONSECUTIVE samples per chunk, so z / density / weights move as one 128-bit
+// access per lane and rgb as three (the 48 contiguous bytes of 4 samples), and a
+// warp covers 32/G adjacent rays whose rows are contiguous in memory -> every
+// request is a fully used run of 128 B lines.  Transmittance is a lane-local
+// product followed by a log2(G)-step shuffle scan; the backward needs the
+// mirror-image suffix sum and runs the same scan with shfl_down.  Rays longer
+// than one chunk (S > 4G) carry T forward between chunks; the backward first
+// records the chunk-entry transmittances in shared memory (z/density only) and
+// then walks the chunks in reverse so the suffix sum is carried the other way.
+//
+// The kernel is HBM-bound: 24*S+28 B/ray forward, 36*S+28 (+4*S with g_weights)
+// backward (DESIGN.md "K1").
+#include "nfs_common.cuh"
+
+namespace nfs {
+namespace {
+
+struct CompositeArgs {
+  const float *rgb, *density, *z, *rays_d, *noise;
+  float noise_std;
+  long long n_rays;
+  int S;
+  int white;
+  // forward outputs
+  float *out_rgb, *out_depth, *out_w;
+  // backward inputs / outputs
+  const float *g_rgb, *g_depth, *g_w;
+  float *d_rgb, *d_density;
+};
+
+constexpr int kBlock = 256;
+
+// One lane's 4 consecutive samples of one ray.
+struct Lane4 {
+  float z[4], sg[4], col[12];
+};
+
+template <bool ALIGNED, bool PACKED, bool WITH_RGB>
+__device__ __forceinline__ void load_lane(const CompositeArgs &a, long long ray, int s0, bool ray_ok,
+                                          Lane4 &v) {
+  const int S = a.S;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v.z[j] = 0.f; v.sg[j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) v.col[j] = 0.f;
+  if (!ray_ok || s0 >= S) return;
+  const long long base = ray * (long long)S + s0;
+  if (ALIGNED) {
+    const float4 zz = ldg_stream4(a.z + base);
+    v.z[0] = zz.x; v.z[1] = zz.y; v.z[2] = zz.z; v.z[3] = zz.w;
+    if (PACKED) {
+      if (WITH_RGB) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = ldg_stream4(a.rgb + (base + j) * 4);
+          v.col[3 * j] = t.x; v.col[3 * j + 1] = t.y; v.col[3 * j + 2] = t.z; v.sg[j] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.sg[j] = ldg_stream1(a.rgb + (base + j) * 4 + 3);
+      }
+    } else {
+      const float4 dd = ldg_stream4(a.density + base);
+      v.sg[0] = dd.x; v.sg[1] = dd.y; v.sg[2] = dd.z; v.sg[3] = dd.w;
+      if (WITH_RGB) {
+        const float *cp = a.rgb + base * 3;
+        const float4 c0 = ldg_stream4(cp), c1 = ldg_stream4(cp + 4), c2 = ldg_stream4(cp + 8);
+        v.col[0] = c0.x; v.col[1] = c0.y; v.col[2] = c0.z; v.col[3] = c0.w;
+        v.col[4] = c1.x; v.col[5] = c1.y; v.col[6] = c1.z; v.col[7] = c1.w;
+        v.col[8] = c2.x; v.col[9] = c2.y; v.col[10] = c2.z; v.col[11] = c2.w;
+      }
+    }
+    if (a.noise != nullptr) {
+      const float4 nz = ldg_stream4(a.noise + base);
+      // density + randn * noise_std, two roundings (nerf_mlp.py:189-190)
+      v.sg[0] = __fadd_rn(v.sg[0], __fmul_rn(nz.x, a.noise_std));
+      v.sg[1] = __fadd_rn(v.sg[1], __fmul_rn(nz.y, a.noise_std));
+      v.sg[2] = __fadd_rn(v.sg[2], __fmul_rn(nz.z, a.noise_std));
+      v.sg[3] = __fadd_rn(v.sg[3], __fmul_rn(nz.w, a.noise_std));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (s0 + j < S) {
+        v.z[j] = ldg_stream1(a.z + base + j);
+        if (PACKED) {
+          const float *t = a.rgb + (base + j) * 4;
+          if (WITH_RGB) { v.col[3 * j] = ldg_stream1(t); v.col[3 * j + 1] = ldg_stream1(t + 1); v.col[3 * j + 2] = ldg_stream1(t + 2); }
+          v.sg[j] = ldg_stream1(t + 3);
+        } else {
+          v.sg[j] = ldg_stream1(a.density + base + j);
+          if (WITH_RGB) {
+            const float *t = a.rgb + (base + j) * 3;
+            v.col[3 * j] = ldg_stream1(t); v.col[3 * j + 1] = ldg_stream1(t + 1); v.col[3 * j + 2] = ldg_stream1(t + 2);
+          }
+        }
+        if (a.noise != nullptr)
+          v.sg[j] = __fadd_rn(v.sg[j], __fmul_rn(ldg_stream1(a.noise + base + j), a.noise_std));
+      }
+    }
+  }
+}
+
+// alpha / q / exp term of the lane's 4 samples.  `zn` = z of the sample after
+// the lane's last one.  Invalid samples get alpha 0, q 1 (they vanish from
+// every product and sum).
+struct Alpha4 {
+  float alpha[4], q[4], e[4], dist[4];
+};
+
+__device__ __forceinline__ void alpha_lane(const Lane4 &v, float zn, int s0, int S, bool ray_ok,
+                                           float dnorm, Alpha4 &o) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int s = s0 + j;
+    const float znext = (j < 3) ? v.z[j + 1] : zn;
+    float d = (s == S - 1) ? 1e10f : (znext - v.z[j]);   // nerf_mlp.py:181-182
+    d = d * dnorm;                                        // :185
+    const float x = fmaxf(v.sg[j], 0.f) * d;              // relu(density) * dists  :193
+    const float e = expf(-x);
+    const float al = 1.0f - e;
+    const float q = (1.0f - al) + 1e-10f;                 // :197
+    const bool ok = ray_ok && s < S;
+    o.alpha[j] = ok ? al : 0.f;
+    o.q[j] = ok ? q : 1.f;
+    o.e[j] = ok ? e : 0.f;
+    o.dist[j] = ok ? d : 0.f;
+  }
+}
+
+// z of the sample that follows the lane's last sample.
+template <int G>
+__device__ __forceinline__ float next_z(const CompositeArgs &a, const Lane4 &v, long long ray, int c0,
+                                        int gl, bool ray_ok) {
+  float zn = __shfl_down_sync(kFullMask, v.z[0], 1, G);
+  if (gl == G - 1) {
+    const int sn = c0 + 4 * G;
+    zn = (ray_ok && sn < a.S) ? __ldg(a.z + ray * (long long)a.S + sn) : 0.f;
+  }
+  return zn;
+}
+
+// exclusive prefix product of `total` over the G lanes of a group; also returns
+// the group's full product in `all`.
+template <int G>
+__device__ __forceinline__ float group_excl_prod(float total, int gl, float &all) {
+  float inc = total;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1) {
+    const float t = __shfl_up_sync(kFullMask, inc, d, G);
+    if (gl >= d) inc *= t;
+  }
+  float exc = __shfl_up_sync(kFullMask, inc, 1, G);
+  if (gl == 0) exc = 1.f;
+  all = __shfl_sync(kFullMask, inc, G - 1, G);
+  return exc;
+}
+
+// exclusive suffix sum over the lanes of a group (lanes after me); `all` = group sum.
+template <int G>
+__device__ __forceinline__ float group_excl_suffix_sum(float total, int gl, float &all) {
+  float inc = total;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1) {
+    const float t = __shfl_down_sync(kFullMask, inc, d, G);
+    if (gl + d < G) inc += t;
+  }
+  float exc = __shfl_down_sync(kFullMask, inc, 1, G);
+  if (gl == G - 1) exc = 0.f;
+  all = __shfl_sync(kFullMask, inc, 0, G);
+  return exc;
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int d = G / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d, G);
+  return v;
+}
+
+// ------------------------------- forward -----------------------------------
+template <int G, bool ALIGNED, bool PACKED>
+__global__ void __launch_bounds__(kBlock) composite_fwd_kernel(const CompositeArgs a) {
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int kRaysPerBlock = (kBlock / 32) * kGroupsPerWarp;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const long long ray = (long long)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
+  const bool ray_ok = ray < a.n_rays;
+  const int S = a.S;
+
+  float dnorm = 0.f;
+  if (ray_ok) {
+    const float dx = __ldg(a.rays_d + ray * 3), dy = __ldg(a.rays_d + ray * 3 + 1), dz = __ldg(a.rays_d + ray * 3 + 2);
+    dnorm = sqrtf(dx * dx + dy * dy + dz * dz);   // torch.norm(rays_d, dim=-1)  nerf_mlp.py:185
+  }
+
+  float t_carry = 1.f;
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_w = 0.f;
+
+  for (int c0 = 0; c0 < S; c0 += 4 * G) {
+    const int s0 = c0 + 4 * gl;
+    Lane4 v;
+    load_lane<ALIGNED, PACKED, true>(a, ray, s0, ray_ok, v);
+    const float zn = next_z<G>(a, v, ray, c0, gl, ray_ok);
+    Alpha4 al;
+    alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+
+    // exclusive cumprod of q (nerf_mlp.py:196-199)
+    const float p1 = al.q[0], p2 = p1 * al.q[1], p3 = p2 * al.q[2], p4 = p3 * al.q[3];
+    float chunk_all;
+    const float tb = t_carry * group_excl_prod<G>(p4, gl, chunk_all);
+    const float T[4] = {tb, tb * p1, tb * p2, tb * p3};
+    t_carry *= chunk_all;
+
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = al.alpha[j] * T[j];                     // :202
+      acc_r += w[j] * v.col[3 * j];                  // :205
+      acc_g += w[j] * v.col[3 * j + 1];
+      acc_b += w[j] * v.col[3 * j + 2];
+      acc_d += w[j] * v.z[j];                        // :208
+      acc_w += w[j];
+    }
+    if (a.out_w != nullptr && ray_ok && s0 < S) {
+      float *wp = a.out_w + ray * (long long)S + s0;
+      if (ALIGNED) {
+        stg_stream4(wp, make_float4(w[0], w[1], w[2], w[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (s0 + j < S) wp[j] = w[j];
+      }
+    }
+  }
+
+  acc_r = group_sum<G>(acc_r);
+  acc_g = group_sum<G>(acc_g);
+  acc_b = group_sum<G>(acc_b);
+  acc_d = group_sum<G>(acc_d);
+  acc_w = group_sum<G>(acc_w);
+  if (ray_ok && gl == 0) {
+    if (a.white) {                                   // :211-213
+      const float bg = 1.0f - acc_w;
+      acc_r += bg; acc_g += bg; acc_b += bg;
+    }
+    a.out_rgb[ray * 3] = acc_r; a.out_rgb[ray * 3 + 1] = acc_g; a.out_rgb[ray * 3 + 2] = acc_b;
+    if (a.out_depth != nullptr) a.out_depth[ray] = acc_d;
+  }
+}
+
+// ------------------------------- backward ----------------------------------
+template <int G>
+__device__ __forceinline__ float group_prod(float v) {
+#pragma unroll
+  for (int d = G / 2; d >= 1; d >>= 1) v *= __shfl_xor_sync(kFullMask, v, d, G);
+  return v;
+}
+
+template <int G, bool ALIGNED, bool PACKED>
+__global__ void __launch_bounds__(kBlock) composite_bwd_kernel(const CompositeArgs a, const int n_chunks) {
+  extern __shared__ float s_carry[];   // [groups per block][n_chunks]; touched only when n_chunks > 1
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int kRaysPerBlock = (kBlock / 32) * kGroupsPerWarp;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int group_in_block = (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
+  const long long ray = (long long)blockIdx.x * kRaysPerBlock + group_in_block;
+  const bool ray_ok = ray < a.n_rays;
+  const int S = a.S;
+
+  float dnorm = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
+  if (ray_ok) {
+    const float dx = __ldg(a.rays_d + ray * 3), dy = __ldg(a.rays_d + ray * 3 + 1), dz = __ldg(a.rays_d + ray * 3 + 2);
+    dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    gr = __ldg(a.g_rgb + ray * 3); gg = __ldg(a.g_rgb + ray * 3 + 1); gb = __ldg(a.g_rgb + ray * 3 + 2);
+    if (a.g_depth != nullptr) gd = __ldg(a.g_depth + ray);
+  }
+  // white_bkgd adds (1 - sum_i w_i) to every channel: d/dw_i = -(g_r + g_g + g_b)
+  const float g_bg = a.white ? (gr + gg + gb) : 0.f;
+
+  float *my_carry = s_carry + group_in_block * n_chunks;
+  if (n_chunks > 1) {
+    // phase A: transmittance at the entry of every chunk (z and density only; L1/L2 re-read below)
+    float t_carry = 1.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c * 4 * G, s0 = c0 + 4 * gl;
+      if (gl == 0) my_carry[c] = t_carry;
+      Lane4 v;
+      load_lane<ALIGNED, PACKED, false>(a, ray, s0, ray_ok, v);
+      const float zn = next_z<G>(a, v, ray, c0, gl, ray_ok);
+      Alpha4 al;
+      alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+      t_carry *= group_prod<G>(al.q[0] * al.q[1] * al.q[2] * al.q[3]);
+    }
+    __syncwarp();
+  }
+
+  // phase B: chunks in reverse; r_carry = sum of G_k w_k over all later chunks
+  float r_carry = 0.f;
+  for (int c = n_chunks - 1; c >= 0; --c) {
+    const int c0 = c * 4 * G, s0 = c0 + 4 * gl;
+    Lane4 v;
+    load_lane<ALIGNED, PACKED, true>(a, ray, s0, ray_ok, v);
+    float gw_in[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.g_w != nullptr && ray_ok && s0 < S) {
+      const float *gp = a.g_w + ray * (long long)S + s0;
+      if (ALIGNED) {
+        const float4 t = ldg_stream4(gp);
+        gw_in[0] = t.x; gw_in[1] = t.y; gw_in[2] = t.z; gw_in[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (s0 + j < S) gw_in[j] = ldg_stream1(gp + j);
+      }
+    }
+    const float zn = next_z<G>(a, v, ray, c0, gl, ray_ok);
+    Alpha4 al;
+    alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+
+    const float p1 = al.q[0], p2 = p1 * al.q[1], p3 = p2 * al.q[2], p4 = p3 * al.q[3];
+    float chunk_all;
+    const float t_in = (n_chunks > 1) ? my_carry[c] : 1.f;
+    const float tb = t_in * group_excl_prod<G>(p4, gl, chunk_all);
+    const float T[4] = {tb, tb * p1, tb * p2, tb * p3};
+
+    float w[4], Gi[4], gwk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = al.alpha[j] * T[j];
+      Gi[j] = gr * v.col[3 * j] + gg * v.col[3 * j + 1] + gb * v.col[3 * j + 2] + gd * v.z[j] + gw_in[j] - g_bg;
+      gwk[j] = Gi[j] * w[j];
+    }
+    // exclusive suffix sums inside the lane, then across the lanes, then across the chunks
+    const float e3 = 0.f, e2 = gwk[3], e1 = e2 + gwk[2], e0 = e1 + gwk[1];
+    float chunk_sum;
+    const float rb = r_carry + group_excl_suffix_sum<G>(e0 + gwk[0], gl, chunk_sum);
+    const float R[4] = {rb + e0, rb + e1, rb + e2, rb + e3};
+    r_carry += chunk_sum;
+
+    float ds[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dalpha = Gi[j] * T[j] - R[j] / al.q[j];
+      // d alpha / d density = dists * exp(-relu(density) dists) * [density > 0]
+      ds[j] = (v.sg[j] > 0.f) ? dalpha * al.dist[j] * al.e[j] : 0.f;
+    }
+
+    if (ray_ok && s0 < S) {
+      const long long base = ray * (long long)S + s0;
+      if (PACKED) {
+        float *op = a.d_rgb + base * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ALIGNED || s0 + j < S) {
+            const float4 o = make_float4(w[j] * gr, w[j] * gg, w[j] * gb, ds[j]);
+            if (ALIGNED) stg_stream4(op + 4 * j, o);
+            else { op[4 * j] = o.x; op[4 * j + 1] = o.y; op[4 * j + 2] = o.z; op[4 * j + 3] = o.w; }
+          }
+        }
+      } else if (ALIGNED) {
+        float *op = a.d_rgb + base * 3;
+        stg_stream4(op,     make_float4(w[0] * gr, w[0] * gg, w[0] * gb, w[1] * gr));
+        stg_stream4(op + 4, make_float4(w[1] * gg, w[1] * gb, w[2] * gr, w[2] * gg));
+        stg_stream4(op + 8, make_float4(w[2] * gb, w[3] * gr, w[3] * gg, w[3] * gb));
+        stg_stream4(a.d_density + base, make_float4(ds[0], ds[1], ds[2], ds[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (s0 + j < S) {
+            float *op = a.d_rgb + (base + j) * 3;
+            op[0] = w[j] * gr; op[1] = w[j] * gg; op[2] = w[j] * gb;
+            a.d_density[base + j] = ds[j];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------- dispatch -----------------------------------
+int pick_group(int S) { return S <= 32 ? 8 : (S <= 64 ? 16 : 32); }
+
+template <int G, bool ALIGNED, bool PACKED>
+int launch_fwd(const CompositeArgs &a, cudaStream_t st) {
+  constexpr int kRaysPerBlock = (kBlock / 32) * (32 / G);
+  const long long blocks = (a.n_rays + kRaysPerBlock - 1) / kRaysPerBlock;
+  if (blocks > 0x7fffffffLL) return fail_arg("nfs_composite_fwd", NFS_E_TOOLARGE, "too many rays for one launch");
+  composite_fwd_kernel<G, ALIGNED, PACKED><<<(unsigned)blocks, kBlock, 0, st>>>(a);
+  return check_launch("nfs_composite_fwd");
+}
+
+template <int G, bool ALIGNED, bool PACKED>
+int launch_bwd(const CompositeArgs &a, cudaStream_t st) {
+  constexpr int kRaysPerBlock = (kBlock / 32) * (32 / G);
+  const long long blocks = (a.n_rays + kRaysPerBlock - 1) / kRaysPerBlock;
+  if (blocks > 0x7fffffffLL) return fail_arg("nfs_composite_bwd", NFS_E_TOOLARGE, "too many rays for one launch");
+  const int n_chunks = (a.S + 4 * G - 1) / (4 * G);
+  const size_t smem = n_chunks > 1 ? sizeof(float) * (size_t)n_chunks * kRaysPerBlock : 0;
+  if (smem > 48 * 1024) return fail_arg("nfs_composite_bwd", NFS_E_TOOLARGE, "n_samples too large");
+  composite_bwd_kernel<G, ALIGNED, PACKED><<<(unsigned)blocks, kBlock, smem, st>>>(a, n_chunks);
+  return check_launch("nfs_composite_bwd");
+}
+
+template <bool FWD>
+int dispatch(const CompositeArgs &a, bool aligned, bool packed, cudaStream_t st) {
+  const int G = pick_group(a.S);
+#define NFS_CASE(GV, AL, PK)                                                         \
+  if (G == GV && aligned == AL && packed == PK)                                      \
+    return FWD ? launch_fwd<GV, AL, PK>(a, st) : launch_bwd<GV, AL, PK>(a, st);
+  NFS_CASE(8, true, false)  NFS_CASE(8, true, true)  NFS_CASE(8, false, false)  NFS_CASE(8, false, true)
+  NFS_CASE(16, true, false) NFS_CASE(16, true, true) NFS_CASE(16, false, false) NFS_CASE(16, false, true)
+  NFS_CASE(32, true, false) NFS_CASE(32, true, true) NFS_CASE(32, false, false) NFS_CASE(32, false, true)
+#undef NFS_CASE
+  return fail_arg("nfs_composite", NFS_E_UNSUPPORTED, "no kernel variant");
+}
+
+}  // namespace
+}  // namespace nfs
+
+using namespace nfs;
+
+extern "C" int nfs_composite_fwd(const float *rgb, const float *density, const float *z_vals,
+                                 const float *rays_d, const float *noise, float noise_std,
+                                 int64_t n_rays, int32_t n_samples, int32_t white_bkgd, int32_t packed,
+                                 float *out_rgb, float *out_depth, float *out_weights, void *stream) {
+  const char *fn = "nfs_composite_fwd";
+  if (n_rays < 0 || n_samples <= 0) return fail_arg(fn, NFS_E_BADARG, "n_rays < 0 or n_samples <= 0");
+  if (n_rays == 0) return 0;
+  if (!rgb || !z_vals || !rays_d || !out_rgb || (!packed && !density))
+    return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  CompositeArgs a{};
+  a.rgb = rgb; a.density = density; a.z = z_vals; a.rays_d = rays_d; a.noise = noise; a.noise_std = noise_std;
+  a.n_rays = n_rays; a.S = n_samples; a.white = white_bkgd;
+  a.out_rgb = out_rgb; a.out_depth = out_depth; a.out_w = out_weights;
+  const bool aligned = (n_samples % 4 == 0) && aligned16(rgb) && aligned16(z_vals) &&
+                       (packed || aligned16(density)) && (!noise || aligned16(noise)) &&
+                       (!out_weights || aligned16(out_weights));
+  return dispatch<true>(a, aligned, packed != 0, (cudaStream_t)stream);
+}
+
+extern "C" int nfs_composite_bwd(const float *rgb, const float *density, const float *z_vals,
+                                 const float *rays_d, const float *noise, float noise_std,
+                                 const float *g_rgb, const float *g_depth, const float *g_weights,
+                                 int64_t n_rays, int32_t n_samples, int32_t white_bkgd, int32_t packed,
+                                 float *d_rgb, float *d_density, void *stream) {
+  const char *fn = "nfs_composite_bwd";
+  if (n_rays < 0 || n_samples <= 0) return fail_arg(fn, NFS_E_BADARG, "n_rays < 0 or n_samples <= 0");
+  if (n_rays == 0) return 0;
+  if (!rgb || !z_vals || !rays_d || !g_rgb || !d_rgb || (!packed && (!density || !d_density)))
+    return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  CompositeArgs a{};
+  a.rgb = rgb; a.density = density; a.z = z_vals; a.rays_d = rays_d; a.noise = noise; a.noise_std = noise_std;
+  a.n_rays = n_rays; a.S = n_samples; a.white = white_bkgd;
+  a.g_rgb = g_rgb; a.g_depth = g_depth; a.g_w = g_weights; a.d_rgb = d_rgb; a.d_density = d_density;
+  const bool aligned = (n_samples % 4 == 0) && aligned16(rgb) && aligned16(z_vals) &&
+                       (packed || (aligned16(density) && aligned16(d_density))) &&
+                       (!noise || aligned16(noise)) && (!g_weights || aligned16(g_weights)) && aligned16(d_rgb);
+  return dispatch<false>(a, aligned, packed != 0, (cudaStream_t)stream);
+}

@@ -1,0 +1,50 @@
+// Shared helpers for the sm_100a kernels behind include/nfs_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/nfs_b200.h"
+
+namespace nfs {
+
+// ---- error plumbing (per host thread) --------------------------------------
+void set_error(const char *where, const char *what);
+int  fail_cuda(const char *where, cudaError_t e);
+int  fail_arg(const char *where, int code, const char *what);
+void count_launch(int n = 1);
+
+// Checks the launch that was just issued on this thread.
+static inline int check_launch(const char *where) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail_cuda(where, e); }
+  count_launch();
+  return 0;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned8(const void *p)  { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+constexpr unsigned kFullMask = 0xffffffffu;
+__device__ __forceinline__ bool aligned16_dev(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- streaming loads/stores: every composite operand is touched exactly once,
+// so keep it out of L1 (Guideline 13/14 of the Blackwell playbook).
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float *p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace nfs

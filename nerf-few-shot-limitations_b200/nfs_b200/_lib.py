@@ -1,0 +1,82 @@
+"""ctypes binding of the C ABI declared in include/nfs_b200.h.
+
+The shared object is built in-tree by nfs_b200/build.py.  There is no CPU path and
+no fallback: if the library is missing, or an entry point returns non-zero, a
+RuntimeError naming the kernel is raised (SURVEY.md section 8b "Error convention").
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnfs_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "nfs_b200.h")
+
+_p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_f32 = ctypes.c_float
+
+# name -> (restype, argtypes); must stay in sync with include/nfs_b200.h
+# (tests/test_abi.py parses the header and checks both directions).
+SIGNATURES = {
+    "nfs_abi_version": (ctypes.c_int, []),
+    "nfs_last_error_string": (ctypes.c_char_p, []),
+    "nfs_launch_count": (ctypes.c_uint64, []),
+    "nfs_composite_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "nfs_composite_bwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "nfs_posenc_fwd": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p]),
+    "nfs_sample_stratified": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p]),
+    "nfs_sample_hierarchical": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def declared_symbols(header_path=HEADER_PATH):
+    """Names of every function the public header declares."""
+    with open(header_path) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nfs_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """dlopen the in-tree library (once) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "nfs_b200: %s is missing - run `python __graft_entry__.py build` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise RuntimeError("nfs_b200: %s does not export %s (stale build?)" % (LIB_PATH, name))
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().nfs_last_error_string().decode("utf-8", "replace")
+
+
+def launch_count():
+    return int(load().nfs_launch_count())
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise RuntimeError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (status %d): %s" % (name, rc, last_error()))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

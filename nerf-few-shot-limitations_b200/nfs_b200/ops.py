@@ -1,0 +1,241 @@
+"""Host-side operators over the C ABI (include/nfs_b200.h): argument checking,
+output allocation on the input's device, launch on torch's current stream, and
+the autograd glue.  Nothing here computes on the CPU; every function raises if the
+tensors are not CUDA tensors or the library is missing.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(name, *tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "%s: expected CUDA tensors (got device %s). nfs_b200 has no CPU fallback; the "
+                "reference's CPU path lives in the reference itself." % (name, t.device))
+
+
+def _f32c(t):
+    """fp32 + contiguous (no copy when already so)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------- K1
+class _CompositeFn(torch.autograd.Function):
+    """VolumeRenderer.forward (nerf_mlp.py:165-215) / volume_render_radiance
+    (volume_renderer.py:4-43) as one kernel per direction.  Nothing but the inputs
+    is saved: the backward recomputes alpha / T (include/nfs_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, rgb, density, z_vals, rays_d, noise, noise_std, white_bkgd, packed, want_aux):
+        n_samples = z_vals.shape[-1]
+        n_rays = z_vals.numel() // max(n_samples, 1)
+        dev = z_vals.device
+        out_rgb = torch.empty((n_rays, 3), device=dev, dtype=torch.float32)
+        out_depth = torch.empty((n_rays,), device=dev, dtype=torch.float32) if want_aux else None
+        out_w = torch.empty((n_rays, n_samples), device=dev, dtype=torch.float32) if want_aux else None
+        with torch.cuda.device(dev):
+            _lib.call("nfs_composite_fwd", ptr(rgb), ptr(density), ptr(z_vals), ptr(rays_d), ptr(noise),
+                      float(noise_std), n_rays, n_samples, int(bool(white_bkgd)), int(bool(packed)),
+                      ptr(out_rgb), ptr(out_depth), ptr(out_w), _stream())
+        ctx.save_for_backward(rgb, density, z_vals, rays_d, noise)
+        ctx.cfg = (float(noise_std), int(bool(white_bkgd)), int(bool(packed)), n_rays, n_samples)
+        ctx.set_materialize_grads(False)
+        if want_aux:
+            return out_rgb, out_depth, out_w
+        return out_rgb, None, None
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_w):
+        rgb, density, z_vals, rays_d, noise = ctx.saved_tensors
+        noise_std, white, packed, n_rays, n_samples = ctx.cfg
+        dev = z_vals.device
+        if g_rgb is None:
+            g_rgb = torch.zeros((n_rays, 3), device=dev, dtype=torch.float32)
+        g_rgb, g_depth, g_w = _f32c(g_rgb), _f32c(g_depth), _f32c(g_w)
+        d_rgb = torch.empty_like(rgb)
+        d_density = None if packed else torch.empty_like(density)
+        with torch.cuda.device(dev):
+            _lib.call("nfs_composite_bwd", ptr(rgb), ptr(density), ptr(z_vals), ptr(rays_d), ptr(noise),
+                      noise_std, ptr(g_rgb), ptr(g_depth), ptr(g_w), n_rays, n_samples, white, packed,
+                      ptr(d_rgb), ptr(d_density), _stream())
+        return d_rgb, d_density, None, None, None, None, None, None, None
+
+
+def composite(rgb, density, z_vals, rays_d, noise=None, noise_std=0.0, white_bkgd=False):
+    """rgb (...,S,3), density (...,S,1)|(...,S), z_vals (...,S), rays_d (...,3)
+    -> rgb_map (...,3), depth (...), weights (...,S)."""
+    _need_cuda("composite", rgb, density, z_vals, rays_d, noise)
+    lead = z_vals.shape[:-1]
+    S = z_vals.shape[-1]
+    if density.dim() == z_vals.dim() + 1:
+        if density.shape[-1] != 1:
+            raise RuntimeError("composite: density must be (...,S,1) or (...,S)")
+        density = density.reshape(*lead, S)
+    if rgb.shape[:-1] != z_vals.shape or rgb.shape[-1] != 3 or density.shape != z_vals.shape \
+            or rays_d.shape != (*lead, 3):
+        raise RuntimeError("composite: shape mismatch rgb %s density %s z_vals %s rays_d %s" % (
+            tuple(rgb.shape), tuple(density.shape), tuple(z_vals.shape), tuple(rays_d.shape)))
+    if S == 0:
+        raise RuntimeError("composite: n_samples must be positive")
+    if S == 1:
+        # Reference quirk kept: with one sample `dists[..., :1]` of the empty difference is
+        # itself empty (nerf_mlp.py:181-182), so nothing is composited: rgb = 0 (1 on white),
+        # depth = 0, weights has shape (..., 0) and every gradient is zero.
+        zero = rgb.sum(dim=-2) * 0.0 + (density.sum(dim=-1) * 0.0)[..., None]
+        return zero + (1.0 if white_bkgd else 0.0), zero[..., 0], density[..., :0] * 0.0
+    o_rgb, o_depth, o_w = _CompositeFn.apply(_f32c(rgb), _f32c(density), _f32c(z_vals), _f32c(rays_d),
+                                             _f32c(noise), noise_std, white_bkgd, False, True)
+    return o_rgb.reshape(*lead, 3), o_depth.reshape(lead), o_w.reshape(*lead, S)
+
+
+def composite_packed(rgb_sigma, z_vals, rays_d, noise=None, noise_std=0.0):
+    """rgb_sigma (...,S,4), z_vals (...,S), rays_d (...,3) -> rgb_map (...,3)."""
+    _need_cuda("composite_packed", rgb_sigma, z_vals, rays_d, noise)
+    lead = z_vals.shape[:-1]
+    if rgb_sigma.shape[:-1] != z_vals.shape or rgb_sigma.shape[-1] != 4 or rays_d.shape != (*lead, 3):
+        raise RuntimeError("composite_packed: shape mismatch rgb_sigma %s z_vals %s rays_d %s" % (
+            tuple(rgb_sigma.shape), tuple(z_vals.shape), tuple(rays_d.shape)))
+    if z_vals.shape[-1] == 0:
+        raise RuntimeError("composite_packed: n_samples must be positive")
+    if z_vals.shape[-1] == 1:   # same reference quirk as in composite(): empty dists, rgb_map = 0
+        return rgb_sigma.sum(dim=-2)[..., :3] * 0.0
+    o_rgb, _, _ = _CompositeFn.apply(_f32c(rgb_sigma), None, _f32c(z_vals), _f32c(rays_d), _f32c(noise),
+                                     noise_std, False, True, False)
+    return o_rgb.reshape(*lead, 3)
+
+
+# --------------------------------------------------------------------------- K2
+def posenc(x, freqs, include_input=True):
+    """x (...,D) -> (..., D*(2L+include_input)); freqs: L fp32 values (any device)."""
+    _need_cuda("posenc", x)
+    x = _f32c(x)
+    D = x.shape[-1]
+    L = int(freqs.numel())
+    P = x.numel() // max(D, 1)
+    W = D * (2 * L + (1 if include_input else 0))
+    out = torch.empty((*x.shape[:-1], W), device=x.device, dtype=torch.float32)
+    if P == 0 or W == 0:
+        return out
+    fr = freqs.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.call("nfs_posenc_fwd", ptr(x), ptr(fr), P, D, L, int(bool(include_input)), ptr(out), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- K4
+def stratified_tables(near, far, n_samples, lindisp=False):
+    """The S-entry tables of ray_utils.py:57-76 / ray_sampler.py:49-56, evaluated with
+    the reference's own torch CPU arithmetic (torch.linspace on CPU is a vectorised,
+    width-dependent formula - SURVEY.md section 8c - so it is never re-derived in a kernel).
+    Returns (z_base, lower, upper), each (S,) fp32 on the CPU."""
+    t_vals = torch.linspace(0.0, 1.0, steps=n_samples)
+    if lindisp:
+        z = 1.0 / (1.0 / near * (1.0 - t_vals) + 1.0 / far * t_vals)
+    else:
+        z = near * (1.0 - t_vals) + far * t_vals
+    mids = 0.5 * (z[1:] + z[:-1])
+    upper = torch.cat([mids, z[-1:]], -1)
+    lower = torch.cat([z[:1], mids], -1)
+    return z, lower, upper
+
+
+_table_cache = {}
+
+
+def _tables_on(device, near, far, n_samples, lindisp):
+    key = (str(device), float(near), float(far), int(n_samples), bool(lindisp))
+    hit = _table_cache.get(key)
+    if hit is None:
+        hit = tuple(t.to(device) for t in stratified_tables(near, far, n_samples, lindisp))
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        _table_cache[key] = hit
+    return hit
+
+
+def sample_stratified(rays_o, rays_d, near, far, n_samples, t_rand=None, lindisp=False, want_pts=True):
+    """rays (...,3) -> pts (...,S,3), z (...,S).  t_rand (...,S) = the uniform draws of
+    ray_utils.py:78 (None = perturb=False)."""
+    _need_cuda("sample_stratified", rays_o, rays_d, t_rand)
+    lead = rays_o.shape[:-1]
+    if rays_o.shape[-1] != 3 or rays_d.shape != rays_o.shape:
+        raise RuntimeError("sample_stratified: rays must be (...,3) with equal shapes")
+    if n_samples <= 0:
+        raise RuntimeError("sample_stratified: N_samples must be positive")
+    rays_o, rays_d, t_rand = _f32c(rays_o), _f32c(rays_d), _f32c(t_rand)
+    n_rays = rays_o.numel() // 3
+    if t_rand is not None and t_rand.shape != (*lead, n_samples):
+        raise RuntimeError("sample_stratified: t_rand must be rays.shape[:-1] + (S,)")
+    dev = rays_o.device
+    z_base, lower, upper = _tables_on(dev, near, far, n_samples, lindisp)
+    z = torch.empty((*lead, n_samples), device=dev, dtype=torch.float32)
+    pts = torch.empty((*lead, n_samples, 3), device=dev, dtype=torch.float32) if want_pts else None
+    if n_rays:
+        with torch.cuda.device(dev):
+            _lib.call("nfs_sample_stratified", ptr(rays_o), ptr(rays_d), ptr(z_base), ptr(lower), ptr(upper),
+                      ptr(t_rand), n_rays, n_samples, ptr(z), ptr(pts), _stream())
+    return pts, z
+
+
+def sample_hierarchical(rays_o, rays_d, z_vals, weights, n_importance, u=None, cdf=None, debug=False,
+                        want_pts=True):
+    """Inverse-CDF resampling (ray_utils.py:101-143).  z_vals (N,M+1), weights (N,M);
+    u (N,Ni) uniform draws or a (Ni,) table broadcast to every ray (perturb=False).
+    cdf (N,M+1): use this cdf instead of the kernel's own (kernel-level parity).
+    Returns pts (N,M+1+Ni,3), z (N,M+1+Ni) [, dict(cdf, idx, samples) when debug]."""
+    _need_cuda("sample_hierarchical", rays_o, rays_d, z_vals, weights, u, cdf)
+    if z_vals.dim() != 2 or weights.dim() != 2:
+        raise RuntimeError("sample_hierarchical: z_vals and weights must be 2-D")
+    N, M1 = z_vals.shape
+    M = weights.shape[-1]
+    if M1 != M + 1 or weights.shape[0] != N:
+        # the reference raises here too (expand of (N,S) to last dim S+1, ray_utils.py:127-129)
+        raise RuntimeError(
+            "sample_hierarchical: z_vals (N,%d) needs weights (N,%d), got %s - the reference's gather "
+            "only works for weights.shape[-1] == z_vals.shape[-1] - 1" % (M1, M1 - 1, tuple(weights.shape)))
+    if M <= 0:
+        raise RuntimeError("sample_hierarchical: need at least one bin")
+    Ni = int(n_importance)
+    dev = z_vals.device
+    rays_o, rays_d, z_vals, weights, cdf = _f32c(rays_o), _f32c(rays_d), _f32c(z_vals), _f32c(weights), _f32c(cdf)
+    if u is None:
+        raise RuntimeError("sample_hierarchical: u is required (draws or the linspace table)")
+    u = _f32c(u)
+    if u.dim() == 1:
+        u_stride = 0
+        if u.numel() != Ni:
+            raise RuntimeError("sample_hierarchical: u table must have N_importance entries")
+    else:
+        if u.shape != (N, Ni):
+            raise RuntimeError("sample_hierarchical: u must be (N, N_importance)")
+        u_stride = Ni
+    total = M1 + Ni
+    z_out = torch.empty((N, total), device=dev, dtype=torch.float32)
+    pts = torch.empty((N, total, 3), device=dev, dtype=torch.float32) if want_pts else None
+    dbg = None
+    if debug:
+        dbg = dict(cdf=torch.empty((N, M1), device=dev, dtype=torch.float32),
+                   idx=torch.empty((N, Ni), device=dev, dtype=torch.int64),
+                   samples=torch.empty((N, Ni), device=dev, dtype=torch.float32))
+    if N:
+        with torch.cuda.device(dev):
+            _lib.call("nfs_sample_hierarchical", ptr(rays_o), ptr(rays_d), ptr(z_vals), ptr(weights), ptr(u),
+                      u_stride, ptr(cdf), N, M, Ni, ptr(z_out), ptr(pts),
+                      ptr(dbg["cdf"]) if debug else None, ptr(dbg["idx"]) if debug else None,
+                      ptr(dbg["samples"]) if debug else None, _stream())
+    if debug:
+        return pts, z_out, dbg
+    return pts, z_out

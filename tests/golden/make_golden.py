@@ -1,0 +1,222 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference, imported from /root/reference/src.
+
+Run in the build container only (the reference does not travel to the GPU box):
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+Each fixture holds seeded inputs and the reference's outputs (and autograd gradients where
+the path is differentiable).  The reference has no tests / golden vectors of its own
+(SURVEY.md section 4), so these files are what pins oracle/nerf_oracle.py.
+"""
+import os
+import sys
+
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+REF = "/root/reference/src"
+sys.path[:0] = [REF, REF + "/models", REF + "/utils"]
+
+import torch  # noqa: E402
+
+from models.nerf_mlp import NeRFLoss, NeRFWithDINO, VolumeRenderer  # noqa: E402
+from models.nerf_mlp import PositionalEncoding as PE4  # noqa: E402
+from models.nerf_model import NeRFMLP  # noqa: E402
+from models.positional_encoding import PositionalEncoding as PE3  # noqa: E402
+from models.ray_sampler import get_rays  # noqa: E402
+from models.ray_sampler import sample_points_along_rays as sample_hw  # noqa: E402
+from models.volume_renderer import volume_render_radiance  # noqa: E402
+from utils import ray_utils  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(1)
+
+
+def save(name, obj):
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(obj, path)
+    print("%-28s %8.1f KB" % (name + ".pt", os.path.getsize(path) / 1024))
+
+
+def rays(n, gen):
+    o = torch.tensor([0.5, -3.2, 2.1]).expand(n, 3).contiguous()
+    d = torch.randn(n, 3, generator=gen)
+    d = d / d.norm(dim=-1, keepdim=True) * (1.0 + 0.2 * torch.rand(n, 1, generator=gen))
+    return o, d
+
+
+def render_cases():
+    gen = torch.Generator().manual_seed(101)
+    cases = []
+    for (n, s, scale, white) in [(48, 64, 10.0, False), (48, 64, 1.0, True), (6, 1, 5.0, False),
+                                 (6, 2, 5.0, True), (7, 33, 100.0, False), (5, 192, 10.0, True),
+                                 (9, 48, 3.0, False), (4, 128, 30.0, False)]:
+        _, rd = rays(n, gen)
+        rgb = torch.rand(n, s, 3, generator=gen).requires_grad_()
+        den = (torch.randn(n, s, 1, generator=gen) * scale).requires_grad_()
+        z = torch.sort(2.0 + 4.0 * torch.rand(n, s, generator=gen), dim=-1).values
+        t_rgb, t_depth = torch.rand(n, 3, generator=gen), 2.0 + 4.0 * torch.rand(n, generator=gen)
+        vr = VolumeRenderer().eval()
+        o_rgb, o_depth, o_w = vr(rgb, den, z, rd, white_bkgd=white)
+        loss = ((o_rgb - t_rgb) ** 2).mean() + 0.1 * (o_depth - t_depth).abs().mean() + 0.01 * (o_w ** 2).mean()
+        g_rgb, g_depth, g_w = torch.autograd.grad(loss, [o_rgb, o_depth, o_w], retain_graph=True)
+        d_rgb, d_den = torch.autograd.grad(loss, [rgb, den])
+        cases.append(dict(rgb=rgb.detach(), density=den.detach(), z_vals=z, rays_d=rd, white_bkgd=white,
+                          out_rgb=o_rgb.detach(), out_depth=o_depth.detach(), out_weights=o_w.detach(),
+                          g_rgb=g_rgb, g_depth=g_depth, g_weights=g_w, d_rgb=d_rgb, d_density=d_den))
+    # training-mode noise (nerf_mlp.py:188-190): same seed -> same randn_like draw
+    n, s = 16, 64
+    _, rd = rays(n, gen)
+    rgb = torch.rand(n, s, 3, generator=gen)
+    den = torch.randn(n, s, 1, generator=gen) * 4.0
+    z = torch.sort(2.0 + 4.0 * torch.rand(n, s, generator=gen), dim=-1).values
+    torch.manual_seed(7)
+    o = VolumeRenderer().train()(rgb, den, z, rd, noise_std=1.0)
+    torch.manual_seed(7)
+    noise = torch.randn_like(den)
+    cases.append(dict(rgb=rgb, density=den, z_vals=z, rays_d=rd, white_bkgd=False, noise=noise, noise_std=1.0,
+                      out_rgb=o[0], out_depth=o[1], out_weights=o[2]))
+    save("render", cases)
+
+
+def packed_cases():
+    gen = torch.Generator().manual_seed(202)
+    cases = []
+    for shape, s in [((5, 7), 32), ((12,), 64), ((2, 3), 5)]:
+        rs = torch.rand(*shape, s, 4, generator=gen)
+        rs[..., 3] = torch.randn(*shape, s, generator=gen) * 8.0
+        rs.requires_grad_()
+        z = torch.sort(2.0 + 4.0 * torch.rand(*shape, s, generator=gen), dim=-1).values
+        rd = torch.randn(*shape, 3, generator=gen)
+        out = volume_render_radiance(rs, z, rd)
+        tgt = torch.rand(*shape, 3, generator=gen)
+        (g,) = torch.autograd.grad(((out - tgt) ** 2).mean(), [rs])
+        cases.append(dict(rgb_sigma=rs.detach(), z_vals=z, rays_d=rd, out=out.detach(), target=tgt, d_rgb_sigma=g))
+    save("render_packed", cases)
+
+
+def posenc_cases():
+    gen = torch.Generator().manual_seed(303)
+    x = (torch.rand(200, 3, generator=gen) - 0.5) * 12.0
+    cases = []
+    for kw in [dict(num_freqs=10), dict(num_freqs=4), dict(num_freqs=6, log_sampling=False),
+               dict(num_freqs=10, include_input=False), dict(num_freqs=0)]:
+        cases.append(dict(kind="positional_encoding", kwargs=kw, x=x, out=PE3(**kw)(x)))
+    x5 = torch.randn(3, 4, 5, generator=gen)
+    cases.append(dict(kind="positional_encoding", kwargs=dict(num_freqs=3), x=x5, out=PE3(num_freqs=3)(x5)))
+    for L in (12, 4):
+        cases.append(dict(kind="nerf_mlp", kwargs=dict(num_freqs=L), x=x, out=PE4(L)(x)))
+    save("posenc", cases)
+
+
+def stratified_cases():
+    gen = torch.Generator().manual_seed(404)
+    cases = []
+    # image-shaped (ray_sampler.py)
+    c2w = torch.eye(4)
+    c2w[:3, 3] = torch.tensor([0.1, 0.2, 4.0])
+    ro, rd = get_rays(6, 5, 7.5, c2w)
+    ro = ro.contiguous()
+    for perturb in (True, False):
+        torch.manual_seed(11)
+        pts, z = sample_hw(ro, rd, 2.0, 6.0, 64, perturb=perturb)
+        torch.manual_seed(11)
+        t_rand = torch.rand(6, 5, 64) if perturb else None
+        cases.append(dict(kind="ray_sampler", rays_o=ro, rays_d=rd, near=2.0, far=6.0, n_samples=64,
+                          t_rand=t_rand, lindisp=False, pts=pts, z=z.contiguous()))
+    # flat (ray_utils.py)
+    for (n, s, near, far, lindisp, perturb) in [(40, 64, 2.0, 6.0, False, True), (40, 64, 2.0, 6.0, True, True),
+                                                (9, 1, 2.0, 6.0, False, True), (9, 2, 0.5, 3.0, False, True),
+                                                (5, 37, 2.0, 6.0, False, True), (8, 192, 2.0, 6.0, False, False),
+                                                (8, 128, 1.0, 9.0, True, False)]:
+        o, d = rays(n, gen)
+        torch.manual_seed(n * 1000 + s)
+        pts, z = ray_utils.sample_points_along_rays(o, d, near, far, s, perturb=perturb, lindisp=lindisp)
+        torch.manual_seed(n * 1000 + s)
+        t_rand = torch.rand(n, s) if perturb else None
+        cases.append(dict(kind="ray_utils", rays_o=o, rays_d=d, near=near, far=far, n_samples=s,
+                          t_rand=t_rand, lindisp=lindisp, pts=pts, z=z.contiguous()))
+    save("stratified", cases)
+
+
+def hierarchical_cases():
+    gen = torch.Generator().manual_seed(505)
+    cases = []
+    for (n, m1, ni, perturb, peaky) in [(64, 64, 128, True, True), (64, 64, 128, False, True),
+                                        (16, 64, 128, True, False), (10, 17, 40, True, True),
+                                        (6, 2, 5, True, False), (12, 64, 128, True, "zero")]:
+        o, d = rays(n, gen)
+        z = torch.sort(2.0 + 4.0 * torch.rand(n, m1, generator=gen), dim=-1).values
+        w = torch.rand(n, m1 - 1, generator=gen)
+        if peaky is True:
+            w = w ** 8
+        elif peaky == "zero":
+            w = torch.zeros(n, m1 - 1)          # all mass from the +1e-5 floor; many ties
+            w[:, 5] = 1.0
+        grabbed = {}
+        real = torch.searchsorted
+
+        def spy(cdf, u, **kw):
+            idx = real(cdf, u, **kw)
+            grabbed.update(cdf=cdf.clone(), u=u.clone(), idx=idx.clone())
+            return idx
+
+        torch.searchsorted = spy
+        try:
+            torch.manual_seed(n + ni)
+            pts, zc = ray_utils.hierarchical_sampling(o, d, z, w, ni, perturb=perturb)
+        finally:
+            torch.searchsorted = real
+        cases.append(dict(rays_o=o, rays_d=d, z_vals=z, weights=w, n_importance=ni, perturb=perturb,
+                          u=grabbed["u"], cdf=grabbed["cdf"], idx=grabbed["idx"], pts=pts, z=zc))
+    save("hierarchical", cases)
+
+
+def mlp_cases():
+    gen = torch.Generator().manual_seed(606)
+    cases = []
+    for kw in [dict(), dict(pos_dim=75, hidden_dim=256, n_layers=8), dict(pos_dim=63, hidden_dim=128, n_layers=4)]:
+        torch.manual_seed(1234)
+        m = NeRFMLP(**kw)
+        x = torch.randn(96, kw.get("pos_dim", 63), generator=gen)
+        out = m(x)
+        tgt = torch.rand_like(out)
+        loss = ((out - tgt) ** 2).mean()
+        grads = torch.autograd.grad(loss, list(m.parameters()))
+        names = [k for k, _ in m.named_parameters()]
+        cases.append(dict(kind="g1", seed=1234, kwargs=kw, x=x, out=out.detach(), target=tgt,
+                          param_sums={k: float(v.double().sum()) for k, v in m.state_dict().items()},
+                          grad_norms={k: float(g.double().norm()) for k, g in zip(names, grads)},
+                          grad_sigma_out_w=grads[names.index("sigma_out.weight")],
+                          grad_layer0_w_row0=grads[0][0].clone()))
+    for kw in [dict(), dict(pos_freq=12, dino_dim=64), dict(dino_dim=0), dict(num_density_layers=2, hidden_dim=128)]:
+        torch.manual_seed(4321)
+        m = NeRFWithDINO(**kw)
+        dd = kw.get("dino_dim", 64)
+        pos = torch.randn(80, 3, generator=gen) * 2.0
+        dirs = torch.randn(80, 3, generator=gen)
+        feat = torch.randn(80, dd, generator=gen)
+        rgb, den = m(pos, dirs, feat)
+        cases.append(dict(kind="g3", seed=4321, kwargs=kw, positions=pos, directions=dirs, dino=feat,
+                          rgb=rgb.detach(), density=den.detach(),
+                          keys=list(m.state_dict().keys()),
+                          param_sums={k: float(v.double().sum()) for k, v in m.state_dict().items()}))
+    save("mlp", cases)
+
+
+def loss_cases():
+    gen = torch.Generator().manual_seed(707)
+    pred = dict(rgb=torch.rand(50, 3, generator=gen), depth=torch.rand(50, generator=gen) * 6,
+                weights=torch.rand(50, 64, generator=gen))
+    tgt = dict(rgb=torch.rand(50, 3, generator=gen), depth=torch.rand(50, generator=gen) * 6)
+    full = NeRFLoss()(pred, tgt)
+    rgb_only = NeRFLoss(2.0, 0.5, 0.1)({"rgb": pred["rgb"]}, {"rgb": tgt["rgb"]})
+    save("loss", dict(pred=pred, target=tgt, full={k: v.clone() for k, v in full.items()},
+                      rgb_only={k: v.clone() for k, v in rgb_only.items()}))
+
+
+if __name__ == "__main__":
+    render_cases()
+    packed_cases()
+    posenc_cases()
+    stratified_cases()
+    hierarchical_cases()
+    mlp_cases()
+    loss_cases()

@@ -1,0 +1,37 @@
+"""Tolerance helpers shared by the parity tests."""
+import torch
+
+
+def rel_err(got, ref, floor=0.0):
+    """max elementwise |got-ref| / max(|ref|, floor)."""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    den = ref.abs().clamp_min(floor if floor > 0 else 1e-30)
+    return float(((got - ref).abs() / den).max()) if ref.numel() else 0.0
+
+
+def per_ray_err(got, ref):
+    """max over rays of max_s|got-ref| / max_s|ref|  - the measure for (N,S[,C]) outputs and
+    gradients, whose tiny entries suffer cancellation in 1-alpha."""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    if ref.numel() == 0:
+        return 0.0
+    n = ref.shape[0]
+    d = (got - ref).abs().reshape(n, -1).max(dim=1).values
+    s = ref.abs().reshape(n, -1).max(dim=1).values.clamp_min(1e-30)
+    return float((d / s).max())
+
+
+def bit_equal(a, b):
+    a, b = a.cpu().contiguous(), b.cpu().contiguous()
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if a.dtype == torch.float32:
+        return bool(torch.equal(a.view(torch.int32), b.view(torch.int32)))
+    return bool(torch.equal(a, b))
+
+
+def ulp_diff(a, b):
+    """max distance in units of last place between two fp32 tensors of equal sign pattern."""
+    ai = a.cpu().contiguous().view(torch.int32).long()
+    bi = b.cpu().contiguous().view(torch.int32).long()
+    return int((ai - bi).abs().max()) if ai.numel() else 0
