@@ -136,6 +136,28 @@ int nfs_sample_hierarchical(const float *rays_o, const float *rays_d,
                             float *cdf_out, int64_t *idx_out, float *samples_out,
                             void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * K3 — NeRF MLP dense layers on tcgen05 tensor cores
+ *   replaces the nn.Linear(+ReLU / sigmoid) chains of
+ *     nerf_model.NeRFMLP.forward               src/models/nerf_model.py:16-24
+ *     nerf_mlp.NeRFWithDINO.forward            src/models/nerf_mlp.py:134-158
+ *     NeRFDINOFusion.forward                   src/models/dino_feature_model.py:175-197
+ *   and the dgrad / wgrad GEMMs of their autograd backward.
+ *
+ * nfs_linear_bf16: Y[P,N] = act( X[P,K] . W[N,K]^T + bias[N] ) (* relu mask)
+ *   X [P,K], W [N,K] bf16 row-major (K contiguous; K % 64 == 0, K <= 320;
+ *   N % 32 == 0, N <= 256 - operands are zero-padded to these shapes), bias fp32
+ *   |NULL, fp32 accumulation in TMEM.  act: 0 none, 1 relu, 2 sigmoid on columns
+ *   0..2 only ([rgb|sigma] head of nerf_model.py:22-24), 3 sigmoid.
+ *   relu_mask_src (bf16 [P,N])|NULL: result *= [relu_mask_src > 0] (ReLU backward
+ *   fused into the dgrad epilogue; call with W^T as the weight).
+ *   Outputs: y_bf16 [P,N] and/or y_f32 [P,out_cols] (first out_cols columns).
+ * ------------------------------------------------------------------------- */
+int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const float *bias,
+                    const void *relu_mask_src,
+                    int64_t n_points, int32_t k_dim, int32_t n_dim, int32_t act,
+                    int32_t out_cols, void *y_bf16, float *y_f32, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -239,3 +239,33 @@ def sample_hierarchical(rays_o, rays_d, z_vals, weights, n_importance, u=None, c
     if debug:
         return pts, z_out, dbg
     return pts, z_out
+
+
+# --------------------------------------------------------------------------- K3 building blocks
+def _bf16c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.bfloat16:
+        raise RuntimeError("expected a bfloat16 tensor, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def linear_bf16(x, w, bias=None, act=0, relu_mask_src=None, out_bf16=True, out_f32_cols=0):
+    """Y = act(X W^T + b) on tcgen05 (nfs_linear_bf16).  x [P,K] bf16, w [N,K] bf16 (K % 64 == 0,
+    N % 32 == 0), bias fp32 [N].  Returns (y_bf16 [P,N] | None, y_f32 [P,out_f32_cols] | None)."""
+    _need_cuda("linear_bf16", x, w, bias, relu_mask_src)
+    x, w, relu_mask_src = _bf16c(x), _bf16c(w), _bf16c(relu_mask_src)
+    P, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise RuntimeError("linear_bf16: x [P,%d] does not match w %s" % (K, tuple(w.shape)))
+    if relu_mask_src is not None and relu_mask_src.shape != (P, N):
+        raise RuntimeError("linear_bf16: relu_mask_src must be [P,N]")
+    bias = _f32c(bias)
+    y16 = torch.empty((P, N), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    y32 = torch.empty((P, out_f32_cols), device=x.device, dtype=torch.float32) if out_f32_cols else None
+    if P:
+        with torch.cuda.device(x.device):
+            _lib.call("nfs_linear_bf16", ptr(x), ptr(w), ptr(bias), ptr(relu_mask_src), P, K, N, int(act),
+                      int(out_f32_cols), ptr(y16), ptr(y32), _stream())
+    return y16, y32
