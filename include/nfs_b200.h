@@ -158,6 +158,19 @@ int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const float *bias,
                     int64_t n_points, int32_t k_dim, int32_t n_dim, int32_t act,
                     int32_t out_cols, void *y_bf16, float *y_f32, void *stream);
 
+/* nfs_wgrad_bf16: D[m,n] += sum_p U[p,m] * V[p,n]   (fp32 red.add into dw[m*ld_m + n*ld_n]),
+ *   the wgrad GEMM of Linear backward: dW[n_out,k_in] = sum_p dY[p,n_out] X[p,k_in]
+ *   (autograd of nerf_model.py:18 / nerf_mlp.py:60-66,82-84).  U [P,M] (row pitch u_pitch),
+ *   V [P,N] (row pitch v_pitch) bf16 row-major; M in {128,256}, N % 64 == 0, N <= 256.
+ *   Lanes own consecutive m: pass the operand whose column index is contiguous in dW as U
+ *   (ld_m = 1) when its width allows.  colsum (fp32)|NULL also receives += the column sums of
+ *   V (colsum_of_v != 0, N entries) or U (M entries): the bias gradient db[n] = sum_p dY[p,n].
+ *   The destination must be zeroed (or hold the running gradient) beforehand. */
+int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int64_t v_pitch,
+                   int64_t n_points, int32_t m_dim, int32_t n_dim,
+                   float *dw, int64_t ld_m, int64_t ld_n,
+                   float *colsum, int32_t colsum_of_v, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,3 +269,22 @@ def linear_bf16(x, w, bias=None, act=0, relu_mask_src=None, out_bf16=True, out_f
             _lib.call("nfs_linear_bf16", ptr(x), ptr(w), ptr(bias), ptr(relu_mask_src), P, K, N, int(act),
                       int(out_f32_cols), ptr(y16), ptr(y32), _stream())
     return y16, y32
+
+
+def wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True):
+    """dw[m*ld_m + n*ld_n] += sum_p u[p,m] v[p,n]  (nfs_wgrad_bf16).  u [P,M], v [P,N] bf16 (row
+    slices of wider tensors are fine: the row pitch is taken from the strides); dw fp32."""
+    _need_cuda("wgrad_bf16", u, v, dw, colsum)
+    if u.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or u.stride(1) != 1 or v.stride(1) != 1:
+        raise RuntimeError("wgrad_bf16: operands must be bf16 with contiguous columns")
+    if dw.dtype != torch.float32 or (colsum is not None and colsum.dtype != torch.float32):
+        raise RuntimeError("wgrad_bf16: destinations must be fp32")
+    P, M = u.shape
+    N = v.shape[1]
+    if v.shape[0] != P:
+        raise RuntimeError("wgrad_bf16: operands disagree on the number of points")
+    if P:
+        with torch.cuda.device(u.device):
+            _lib.call("nfs_wgrad_bf16", ptr(u), u.stride(0), ptr(v), v.stride(0), P, M, N, ptr(dw), int(ld_m),
+                      int(ld_n), ptr(colsum), int(bool(colsum_of_v)), _stream())
+    return dw

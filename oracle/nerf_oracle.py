@@ -82,7 +82,8 @@ def render_backward_closed_form(rgb, density, z_vals, rays_d, g_rgb, g_depth=Non
     if white_bkgd:
         G = G - g_rgb.sum(-1, keepdim=True)
     gw = G * w
-    suffix = torch.flip(torch.cumsum(torch.flip(gw, [-1]), -1), [-1]) - gw     # sum_{k>i} G_k w_k
+    incl = torch.flip(torch.cumsum(torch.flip(gw, [-1]), -1), [-1])             # sum_{k>=i} G_k w_k
+    suffix = torch.cat([incl[..., 1:], torch.zeros_like(incl[..., :1])], -1)   # sum_{k>i}: shifted, never subtracted
     d_alpha = G * T - suffix / q
     d_sigma = d_alpha * gaps * e * (sig > 0).to(sig.dtype)
     return w[..., None] * g_rgb[..., None, :], d_sigma[..., None]

@@ -9,16 +9,30 @@ def rel_err(got, ref, floor=0.0):
     return float(((got - ref).abs() / den).max()) if ref.numel() else 0.0
 
 
-def per_ray_err(got, ref):
-    """max over rays of max_s|got-ref| / max_s|ref|  - the measure for (N,S[,C]) outputs and
-    gradients, whose tiny entries suffer cancellation in 1-alpha."""
+def per_ray_err(got, ref, floor=0.0, floor_frac=0.0):
+    """max over rays of max_s|got-ref| / max(max_s|ref|, floor, floor_frac * max|ref|) - the
+    measure for (N,S[,C]) outputs and gradients, whose tiny entries suffer cancellation in
+    1-alpha.  `floor` (absolute) / `floor_frac` (fraction of the batch
+    maximum) bound the denominator for rays whose whole row is negligible."""
     got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
     if ref.numel() == 0:
         return 0.0
     n = ref.shape[0]
     d = (got - ref).abs().reshape(n, -1).max(dim=1).values
-    s = ref.abs().reshape(n, -1).max(dim=1).values.clamp_min(1e-30)
+    lo = max(floor, floor_frac * float(ref.abs().max()), 1e-30)
+    s = ref.abs().reshape(n, -1).max(dim=1).values.clamp_min(lo)
     return float((d / s).max())
+
+
+def record(name, **values):
+    """Append measured parity numbers to gpurun_out/parity_metrics.jsonl (when that directory
+    exists) so the figures quoted in DESIGN.md / profiles/ come from the test run itself."""
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_metrics.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **values)) + "\n")
 
 
 def bit_equal(a, b):
