@@ -165,11 +165,51 @@ int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const float *bias,
  *   Lanes own consecutive m: pass the operand whose column index is contiguous in dW as U
  *   (ld_m = 1) when its width allows.  colsum (fp32)|NULL also receives += the column sums of
  *   V (colsum_of_v != 0, N entries) or U (M entries): the bias gradient db[n] = sum_p dY[p,n].
+ *   Only entries m < m_valid, n < n_valid are written (0 = all): the operands are zero-padded
+ *   to the tile shapes, the destination is the un-padded parameter gradient.
  *   The destination must be zeroed (or hold the running gradient) beforehand. */
 int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int64_t v_pitch,
                    int64_t n_points, int32_t m_dim, int32_t n_dim,
+                   int32_t m_valid, int32_t n_valid,
                    float *dw, int64_t ld_m, int64_t ld_n,
                    float *colsum, int32_t colsum_of_v, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2 fused with the operand cast of the first dense layer
+ *   (positional_encoding.py:27-33 / nerf_mlp.py:24-33, the torch.cat with DINO features of
+ *   dino_feature_model.py:182,195 and the fp32->bf16 cast feeding nn.Linear):
+ *   out row (bf16, k_pad entries) = [ enc(x) * scale_enc | extra * scale_extra | 0 ... ]
+ *   enc(x) = [x, sin(x f_0), cos(x f_0), ...] (D*(2L+1)); extra (P,E)|NULL; scale_* (P)|NULL
+ *   are the per-point attention gates of dino_feature_model.py:191-192.
+ * ------------------------------------------------------------------------- */
+int nfs_posenc_bf16(const float *x, const float *freqs, const float *extra,
+                    const float *scale_enc, const float *scale_extra,
+                    int64_t n_points, int32_t dim, int32_t n_freqs, int32_t extra_dim,
+                    int32_t k_pad, void *out_bf16, void *stream);
+
+/* fp32 master weight [n_dim,k_dim] -> block (row0,col0) of the zero-padded bf16 operands
+ * w_bf16 [n_pad,k_pad] (forward) and wt_bf16 [k_pad,n_pad] (dgrad); either may be NULL.
+ * Parameters keep the reference's names / [out,in] fp32 layout;
+ * these are the cached operand copies refreshed after an optimizer step. */
+int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n_pad, int32_t k_pad,
+                         int32_t row0, int32_t col0, void *w_bf16, void *wt_bf16, void *stream);
+
+/* dY (bf16 [P,n_pad], zero padded) = g_out * act'(out) for the fp32 network outputs
+ * out, g_out [P,n_cols]: act 0 identity, 1 relu, 2 sigmoid on columns 0..2 (nerf_model.py:22-24),
+ * 3 sigmoid (nerf_mlp.py:80).  First step of the MLP backward. */
+int nfs_act_grad_bf16(const float *out, const float *g_out, int64_t n_points, int32_t n_cols,
+                      int32_t act, int32_t n_pad, void *dy_bf16, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused Adam / AdamW step over one flat fp32 buffer
+ *   replaces optim.Adam(...).step()   src/training/train.py:114-118,286   (decoupled = 0)
+ *        and optim.AdamW(...).step()  src/training/train_multiscale.py:61 (decoupled = 1)
+ *   grad is multiplied by grad_scale first (1/world_size after a sum-allreduce).
+ * ------------------------------------------------------------------------- */
+int nfs_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                  int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int32_t step, float grad_scale, int32_t decoupled,
+                  void *stream);
 
 #ifdef __cplusplus
 }

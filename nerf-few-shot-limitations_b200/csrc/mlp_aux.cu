@@ -1,0 +1,194 @@
+// K2 fused with the operand cast of the first dense layer, plus the small kernels around
+// the tcgen05 GEMMs of K3: weight packing (fp32 master -> zero-padded bf16 W and W^T),
+// output-activation backward, and the fused flat Adam step.
+//
+// Reference lines replaced:
+//   positional encoding + cast   /root/reference/src/models/positional_encoding.py:27-33,
+//                                /root/reference/src/models/nerf_mlp.py:24-33 (+ torch.cat with the
+//                                DINO features, dino_feature_model.py:182,195)
+//   sigmoid / relu backward      autograd of nerf_model.py:22-24, nerf_mlp.py:62,80
+//   optimizer step               /root/reference/src/training/train.py:114-118,286 (Adam),
+//                                /root/reference/src/training/train_multiscale.py:61 (AdamW)
+#include "tc_common.cuh"
+
+namespace nfs {
+namespace {
+
+// ------------------------------------------------------------------ posenc -> bf16 operand
+constexpr int kEncThreads = 256;
+constexpr int kEncTile = 64;   // points per CTA
+
+__global__ void __launch_bounds__(kEncThreads)
+posenc_bf16_kernel(const float *__restrict__ x, const float *__restrict__ freqs, const float *__restrict__ extra,
+                   const float *__restrict__ scale_enc, const float *__restrict__ scale_extra, long long n_points,
+                   int D, int L, int E, int k_pad, __nv_bfloat16 *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(s_raw);     // [kEncTile][k_pad]
+  const long long p0 = (long long)blockIdx.x * kEncTile;
+  const int np = (int)min((long long)kEncTile, n_points - p0);
+  const int enc_w = D * (2 * L + 1);
+
+  // zero the padding columns (and everything else; cheap) so the GEMM sees exact zeros
+  for (int t = threadIdx.x; t < np * k_pad / 8; t += kEncThreads) reinterpret_cast<uint4 *>(tile)[t] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  const int per_pt = L * D;
+  for (int t = threadIdx.x; t < np * per_pt; t += kEncThreads) {
+    const int p = t / per_pt, r = t - p * per_pt;
+    const int k = r / D, d = r - k * D;
+    const float arg = __fmul_rn(__ldg(x + (p0 + p) * D + d), __ldg(freqs + k));
+    float s, c;
+    sincosf(arg, &s, &c);
+    const float g = scale_enc ? __ldg(scale_enc + p0 + p) : 1.f;
+    __nv_bfloat16 *row = tile + p * k_pad + D + 2 * k * D;
+    row[d] = __float2bfloat16_rn(s * g);
+    row[D + d] = __float2bfloat16_rn(c * g);
+  }
+  for (int t = threadIdx.x; t < np * D; t += kEncThreads) {
+    const int p = t / D, d = t - p * D;
+    const float g = scale_enc ? __ldg(scale_enc + p0 + p) : 1.f;
+    tile[p * k_pad + d] = __float2bfloat16_rn(__ldg(x + (p0 + p) * D + d) * g);
+  }
+  if (extra != nullptr)
+    for (int t = threadIdx.x; t < np * E; t += kEncThreads) {
+      const int p = t / E, j = t - p * E;
+      const float g = scale_extra ? __ldg(scale_extra + p0 + p) : 1.f;
+      tile[p * k_pad + enc_w + j] = __float2bfloat16_rn(__ldg(extra + (p0 + p) * E + j) * g);
+    }
+  __syncthreads();
+  uint4 *dst = reinterpret_cast<uint4 *>(out + p0 * k_pad);
+  const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+  for (int t = threadIdx.x; t < np * k_pad / 8; t += kEncThreads) dst[t] = src[t];
+}
+
+// ------------------------------------------------------------------ weight packing
+// W fp32 [N,K] (row pitch K) -> w16 [n_pad,k_pad] and w16t [k_pad,n_pad], zero padded.
+// `row0` places the block at a row offset of the packed matrices (heads stacked in one operand).
+__global__ void __launch_bounds__(256)
+pack_linear_kernel(const float *__restrict__ w, int N, int K, int n_pad, int k_pad, int row0, int col0,
+                   __nv_bfloat16 *__restrict__ w16, __nv_bfloat16 *__restrict__ w16t) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(w + idx));
+  if (w16) w16[(long long)(row0 + n) * k_pad + col0 + k] = v;
+  if (w16t) w16t[(long long)(col0 + k) * n_pad + row0 + n] = v;
+}
+
+// ------------------------------------------------------------------ output activation backward
+// out, g_out fp32 [P,C] -> dY bf16 [P,n_pad] = g_out * act'(out), zero padded.
+//   act 0 identity, 1 relu (out > 0), 2 sigmoid on the first 3 columns, 3 sigmoid on all.
+__global__ void __launch_bounds__(256)
+act_grad_kernel(const float *__restrict__ out, const float *__restrict__ g_out, long long n_points, int C, int act,
+                int n_pad, __nv_bfloat16 *__restrict__ dy) {
+  const int chunks = n_pad / 8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_points * chunks) return;
+  const long long p = t / chunks;
+  const int c0 = (int)(t - p * chunks) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float r = 0.f;
+    if (c < C) {
+      const float o = __ldg(out + p * C + c), g = __ldg(g_out + p * C + c);
+      if (act == 0) r = g;
+      else if (act == 1) r = o > 0.f ? g : 0.f;
+      else if (act == 2) r = c < 3 ? g * o * (1.f - o) : g;
+      else r = g * o * (1.f - o);
+    }
+    v[j] = r;
+  }
+  *reinterpret_cast<uint4 *>(dy + p * n_pad + c0) =
+      make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                 tc::pack_bf16x2(v[6], v[7]));
+}
+
+// ------------------------------------------------------------------ Adam / AdamW over a flat buffer
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+            int decoupled) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * gscale, w = p[i];
+  if (wd != 0.f) {
+    if (decoupled) w *= 1.f - lr * wd;      // AdamW
+    else grad += wd * w;                    // Adam (L2)
+  }
+  const float mi = b1 * m[i] + (1.f - b1) * grad;
+  const float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = w - (lr / bc1) * (mi / denom);
+}
+
+}  // namespace
+}  // namespace nfs
+
+using namespace nfs;
+
+extern "C" int nfs_posenc_bf16(const float *x, const float *freqs, const float *extra, const float *scale_enc,
+                               const float *scale_extra, int64_t n_points, int32_t dim, int32_t n_freqs,
+                               int32_t extra_dim, int32_t k_pad, void *out_bf16, void *stream) {
+  const char *fn = "nfs_posenc_bf16";
+  if (n_points < 0 || dim <= 0 || n_freqs < 0 || extra_dim < 0) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
+  if (n_points == 0) return 0;
+  if (!x || !out_bf16 || (n_freqs > 0 && !freqs) || (extra_dim > 0 && !extra))
+    return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  const int w = dim * (2 * n_freqs + 1) + extra_dim;
+  if (k_pad % 8 != 0 || k_pad < w) return fail_arg(fn, NFS_E_BADARG, "k_pad must be a multiple of 8 and >= the row width");
+  if (!aligned16(out_bf16)) return fail_arg(fn, NFS_E_ALIGN, "out must be 16-byte aligned");
+  const size_t smem = (size_t)kEncTile * k_pad * 2;
+  if (smem > 48 * 1024) return fail_arg(fn, NFS_E_TOOLARGE, "k_pad too large");
+  const long long blocks = (n_points + kEncTile - 1) / kEncTile;
+  if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
+  posenc_bf16_kernel<<<(unsigned)blocks, kEncThreads, smem, (cudaStream_t)stream>>>(
+      x, freqs, extra_dim > 0 ? extra : nullptr, scale_enc, scale_extra, n_points, dim, n_freqs, extra_dim, k_pad,
+      (__nv_bfloat16 *)out_bf16);
+  return check_launch(fn);
+}
+
+extern "C" int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n_pad, int32_t k_pad,
+                                    int32_t row0, int32_t col0, void *w_bf16, void *wt_bf16, void *stream) {
+  const char *fn = "nfs_pack_linear_bf16";
+  if (n_dim <= 0 || k_dim <= 0 || row0 < 0 || col0 < 0 || row0 + n_dim > n_pad || col0 + k_dim > k_pad)
+    return fail_arg(fn, NFS_E_BADARG, "block does not fit the padded matrix");
+  if (!w || (!w_bf16 && !wt_bf16)) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  const int total = n_dim * k_dim;
+  pack_linear_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w, n_dim, k_dim, n_pad, k_pad, row0, col0, (__nv_bfloat16 *)w_bf16, (__nv_bfloat16 *)wt_bf16);
+  return check_launch(fn);
+}
+
+extern "C" int nfs_act_grad_bf16(const float *out, const float *g_out, int64_t n_points, int32_t n_cols, int32_t act,
+                                 int32_t n_pad, void *dy_bf16, void *stream) {
+  const char *fn = "nfs_act_grad_bf16";
+  if (n_points < 0 || n_cols <= 0 || n_pad % 8 != 0 || n_pad < n_cols || act < 0 || act > 3)
+    return fail_arg(fn, NFS_E_BADARG, "bad sizes");
+  if (n_points == 0) return 0;
+  if (!out || !g_out || !dy_bf16) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  const long long threads = n_points * (n_pad / 8);
+  const long long blocks = (threads + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
+  act_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, g_out, n_points, n_cols, act, n_pad,
+                                                                     (__nv_bfloat16 *)dy_bf16);
+  return check_launch(fn);
+}
+
+extern "C" int nfs_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                             int32_t decoupled, void *stream) {
+  const char *fn = "nfs_adam_step";
+  if (n < 0 || step <= 0) return fail_arg(fn, NFS_E_BADARG, "n < 0 or step <= 0");
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const long long blocks = (n + 255) / 256;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                 eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+                                                                 grad_scale, decoupled);
+  return check_launch(fn);
+}

@@ -32,6 +32,7 @@ struct WgradArgs {
   int M, N;
   float *dw;
   long long ld_m, ld_n;
+  int m_valid, n_valid;   // only m < m_valid, n < n_valid are written (operands are zero-padded)
   float *colsum;      // bias gradient destination | NULL
   int colsum_of_v;    // 1: columns of V (N of them), 0: columns of U (M of them)
   int n_stages, tmem_cols;
@@ -128,7 +129,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + stage);
       }
-      if (active) { atomicAdd(a.colsum + col, s0); atomicAdd(a.colsum + col + 1, s1); }
+      const int cvalid = a.colsum_of_v ? a.n_valid : a.m_valid;
+      if (active && col < cvalid) atomicAdd(a.colsum + col, s0);
+      if (active && col + 1 < cvalid) atomicAdd(a.colsum + col + 1, s1);
     }
     // drain the accumulators
     mbar_wait(acc_full, 0);
@@ -142,8 +145,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
           float v[32];
           tmem_ld32(taddr + c0, v);
           float *dst = a.dw + m * a.ld_m + (long long)c0 * a.ld_n;
+          if (m < a.m_valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j * a.ld_n, v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < a.n_valid) atomicAdd(dst + j * a.ld_n, v[j]);
+          }
         }
       }
     }
@@ -163,8 +169,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
 using namespace nfs;
 
 extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int64_t v_pitch,
-                              int64_t n_points, int32_t m_dim, int32_t n_dim, float *dw, int64_t ld_m, int64_t ld_n,
-                              float *colsum, int32_t colsum_of_v, void *stream) {
+                              int64_t n_points, int32_t m_dim, int32_t n_dim, int32_t m_valid, int32_t n_valid,
+                              float *dw, int64_t ld_m, int64_t ld_n, float *colsum, int32_t colsum_of_v, void *stream) {
   const char *fn = "nfs_wgrad_bf16";
   if (n_points < 0 || m_dim <= 0 || n_dim <= 0) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
   if (n_points == 0) return 0;
@@ -182,6 +188,8 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   WgradArgs a{};
   a.P = n_points; a.M = m_dim; a.N = n_dim; a.dw = dw; a.ld_m = ld_m; a.ld_n = ld_n;
   a.colsum = colsum; a.colsum_of_v = colsum_of_v;
+  a.m_valid = (m_valid <= 0 || m_valid > m_dim) ? m_dim : m_valid;
+  a.n_valid = (n_valid <= 0 || n_valid > n_dim) ? n_dim : n_valid;
   const int stage_bytes = ((m_dim + n_dim) / 64) * kBlockBytes;
   int stages = (227 * 1024 - 1024 - 256) / stage_bytes;
   if (stages > 6) stages = 6;

@@ -1,0 +1,55 @@
+"""Drop-in for /root/reference/src/models/nerf_model.py (R5 in SURVEY.md section 8a)."""
+try:
+    from . import _bootstrap  # noqa: F401
+except ImportError:
+    import _bootstrap  # noqa: F401
+
+import torch.nn as nn
+
+from nfs_b200 import mlp as _mlp
+
+
+class NeRFMLP(nn.Module):
+    """8 x (Linear 256 + ReLU) -> raw sigma, sigmoid rgb; returns (P,4) = [rgb | sigma].
+
+    Same constructor, parameter names and [out,in] fp32 shapes as nerf_model.py:5-24
+    (`layers.{i}.weight/bias`, `sigma_out.*`, `rgb_out.*`), so state_dicts interchange with the
+    reference.  forward runs every dense layer on tcgen05 tensor cores (bf16 operands, fp32
+    accumulation in TMEM; nfs_linear_bf16 / nfs_wgrad_bf16) - there is no eager fallback.
+
+    train.py constructs this class with NeRFWithDINO's keyword arguments (pos_freq=...,
+    num_density_layers=..., use_dino=..., dino_dim=...): that form builds the
+    view-dependent topology of nerf_mlp.NeRFWithDINO and returns (rgb, density) instead.
+    """
+
+    def __new__(cls, *args, **kwargs):
+        if cls is NeRFMLP and any(k in kwargs for k in ("pos_freq", "dir_freq", "num_density_layers", "use_dino",
+                                                        "dino_dim")):
+            from models.nerf_mlp import _train_py_model
+            return _train_py_model(**kwargs)
+        return super().__new__(cls)
+
+    def __init__(self, pos_dim=63, hidden_dim=256, n_layers=8):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        for i in range(n_layers):
+            in_dim = pos_dim if i == 0 else hidden_dim
+            self.layers.append(nn.Linear(in_dim, hidden_dim))
+        self.sigma_out = nn.Linear(hidden_dim, 1)
+        self.rgb_out = nn.Linear(hidden_dim, 3)
+        self._plan = None
+
+    def _get_plan(self):
+        if self._plan is None:
+            self._plan = _mlp.G1Plan(self)
+        return self._plan
+
+    def forward(self, x, dir_enc=None):
+        """x: (..., pos_dim) already encoded (reference calling convention); dir_enc is accepted
+        and ignored exactly like the reference (nerf_model.py:16)."""
+        return _mlp.g1_forward(self._get_plan(), x=x)
+
+    def forward_points(self, points, freq_bands):
+        """points (...,3) fp32 -> (...,4) with the sin/cos expansion fused into the first layer's
+        bf16 operand (the (P,63) fp32 encoding is never written).  Not part of the reference API."""
+        return _mlp.g1_forward(self._get_plan(), points=points, freqs=freq_bands)

@@ -1,0 +1,219 @@
+"""Host-side engine of K3: runs the reference's MLPs as chains of tcgen05 GEMM launches.
+
+The nn.Modules in models/ keep the reference's fp32 parameters (names, [out,in] shapes); this
+file owns the cached bf16 operand copies (zero-padded W and W^T per layer), the launch
+sequences for forward / backward and the autograd glue.  Dense layers run in
+nfs_linear_bf16 (forward and dgrad, with bias / ReLU / sigmoid / ReLU-mask epilogues) and
+nfs_wgrad_bf16 (weight + bias gradients); nothing here computes on the CPU.
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import ptr
+from .ops import _stream
+
+
+def _ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def pad_in(k):
+    """K (reduction) padding of a GEMM operand: multiple of 64 (one 128-byte swizzle row)."""
+    return _ceil_to(k, 64)
+
+
+def pad_hidden(n):
+    """Hidden widths are both an N (<= 256, % 32) and the next layer's K (% 64), and the wgrad
+    kernel wants its M side in {128, 256}."""
+    if n <= 128:
+        return 128
+    if n <= 256:
+        return 256
+    raise RuntimeError("nfs_b200: hidden widths above 256 are not supported by the tcgen05 dense kernels")
+
+
+class PackedLinear:
+    """bf16 operand copies of one (or several row-stacked) fp32 nn.Linear layers."""
+
+    def __init__(self, linears, k_pad, n_pad):
+        self.linears = list(linears)
+        self.k_pad, self.n_pad = k_pad, n_pad
+        self.k = self.linears[0].in_features
+        self.rows = [l.out_features for l in self.linears]
+        self.n = sum(self.rows)
+        assert self.n <= n_pad and self.k <= k_pad
+        self._key = None
+        self.w16 = self.w16t = self.bias = None
+
+    def refresh(self):
+        params = [p for l in self.linears for p in (l.weight, l.bias)]
+        dev = params[0].device
+        key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._key:
+            return self
+        if not params[0].is_cuda:
+            raise RuntimeError("nfs_b200: model parameters must live on a CUDA device (no CPU fallback)")
+        if self.w16 is None or self.w16.device != dev:
+            self.w16 = torch.zeros(self.n_pad, self.k_pad, device=dev, dtype=torch.bfloat16)
+            self.w16t = torch.zeros(self.k_pad, self.n_pad, device=dev, dtype=torch.bfloat16)
+            self.bias = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+        row = 0
+        with torch.cuda.device(dev), torch.no_grad():
+            for l in self.linears:
+                w = l.weight.detach()
+                if w.dtype != torch.float32 or not w.is_contiguous():
+                    w = w.float().contiguous()
+                _lib.call("nfs_pack_linear_bf16", ptr(w), l.out_features, l.in_features, self.n_pad, self.k_pad,
+                          row, 0, ptr(self.w16), ptr(self.w16t), _stream())
+                self.bias[row:row + l.out_features].copy_(l.bias.detach())
+                row += l.out_features
+        self._key = key
+        return self
+
+
+def encode_operand(x, freqs, k_pad, extra=None, scale_enc=None, scale_extra=None):
+    """fp32 rows -> bf16 GEMM operand [P,k_pad] = [enc(x) | extra | 0] (nfs_posenc_bf16).
+    freqs=None copies x itself (already-encoded input)."""
+    x = ops._f32c(x)
+    P, D = x.shape
+    L = 0 if freqs is None else int(freqs.numel())
+    E = 0 if extra is None else extra.shape[-1]
+    out = torch.empty((P, k_pad), device=x.device, dtype=torch.bfloat16)
+    if P:
+        fr = None if freqs is None else freqs.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(x.device):
+            _lib.call("nfs_posenc_bf16", ptr(x), ptr(fr), ptr(ops._f32c(extra)), ptr(ops._f32c(scale_enc)),
+                      ptr(ops._f32c(scale_extra)), P, D, L, E, k_pad, ptr(out), _stream())
+    return out
+
+
+def act_grad(out, g_out, act, n_pad):
+    out, g_out = ops._f32c(out), ops._f32c(g_out)
+    P, C = out.shape
+    dy = torch.empty((P, n_pad), device=out.device, dtype=torch.bfloat16)
+    if P:
+        with torch.cuda.device(out.device):
+            _lib.call("nfs_act_grad_bf16", ptr(out), ptr(g_out), P, C, int(act), n_pad, ptr(dy), _stream())
+    return dy
+
+
+# --------------------------------------------------------------------------------- G1
+class G1Plan:
+    """Launch plan for nerf_model.NeRFMLP (nerf_model.py:5-24): n_layers x (Linear + ReLU),
+    then the [rgb|sigma] head = rgb_out and sigma_out stacked into one 64-row operand."""
+
+    def __init__(self, module):
+        self.module = module
+        layers = list(module.layers)
+        self.in_dim = layers[0].in_features
+        self.hidden = layers[0].out_features
+        self.k0 = pad_in(self.in_dim)
+        self.h_pad = pad_hidden(self.hidden)
+        self.packed = [PackedLinear([l], self.k0 if i == 0 else self.h_pad, self.h_pad) for i, l in enumerate(layers)]
+        self.head = PackedLinear([module.rgb_out, module.sigma_out], self.h_pad, 64)
+
+    def params(self):
+        m = self.module
+        ps = []
+        for l in m.layers:
+            ps += [l.weight, l.bias]
+        ps += [m.sigma_out.weight, m.sigma_out.bias, m.rgb_out.weight, m.rgb_out.bias]
+        return ps
+
+    def refresh(self):
+        for p in self.packed:
+            p.refresh()
+        self.head.refresh()
+
+    # forward over an already-built bf16 operand; returns (out fp32 [P,4], saved activations)
+    def run_forward(self, x16, keep):
+        acts = [x16]
+        h = x16
+        for p in self.packed:
+            h, _ = ops.linear_bf16(h, p.w16, p.bias, act=1)
+            if keep:
+                acts.append(h)
+        if not keep:
+            acts.append(h)
+        _, out = ops.linear_bf16(h, self.head.w16, self.head.bias, act=2, out_bf16=False, out_f32_cols=4)
+        return out, acts
+
+    def run_backward(self, acts, out, g_out):
+        """Returns the list of parameter gradients in params() order."""
+        m = self.module
+        dev = out.device
+        ps = self.params()
+        sizes = [p.numel() for p in ps]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        views, off = [], 0
+        for p, n in zip(ps, sizes):
+            views.append(flat[off:off + n].view(p.shape))
+            off += n
+        n_layers = len(self.packed)
+        h_last = acts[-1]
+        dy = act_grad(out, g_out, 2, 64)
+        # head: rows 0..2 rgb_out, row 3 sigma_out
+        tmp_w = torch.zeros(64, self.h_pad, device=dev, dtype=torch.float32)
+        tmp_b = torch.zeros(64, device=dev, dtype=torch.float32)
+        ops.wgrad_bf16(h_last, dy, tmp_w, 1, self.h_pad, colsum=tmp_b, colsum_of_v=True)
+        hd = self.hidden
+        views[2 * n_layers + 0].copy_(tmp_w[3:4, :hd])      # sigma_out.weight
+        views[2 * n_layers + 1].copy_(tmp_b[3:4])
+        views[2 * n_layers + 2].copy_(tmp_w[0:3, :hd])      # rgb_out.weight
+        views[2 * n_layers + 3].copy_(tmp_b[0:3])
+        dh, _ = ops.linear_bf16(dy, self.head.w16t, None, act=0, relu_mask_src=h_last)
+        for i in range(n_layers - 1, 0, -1):
+            x_in = acts[i]                                   # input of layer i (= output of layer i-1)
+            if hd == self.h_pad:
+                ops.wgrad_bf16(x_in, dh, views[2 * i], 1, hd, colsum=views[2 * i + 1], colsum_of_v=True)
+            else:
+                ops.wgrad_bf16(x_in, dh, views[2 * i], 1, hd, colsum=views[2 * i + 1], colsum_of_v=True,
+                               m_valid=hd, n_valid=hd)
+            dh, _ = ops.linear_bf16(dh, self.packed[i].w16t, None, act=0, relu_mask_src=x_in)
+        # first layer: its K side (the encoding width) is not a multiple of 128 -> M = out features
+        ops.wgrad_bf16(dh, acts[0], views[0], self.in_dim, 1, colsum=views[1], colsum_of_v=False,
+                       m_valid=hd, n_valid=self.in_dim)
+        return views
+
+
+class _G1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, keep, x16, *params):
+        out, acts = plan.run_forward(x16, keep)
+        ctx.plan = plan
+        ctx.keep = keep
+        if keep:
+            ctx.save_for_backward(out, *acts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        out, *acts = ctx.saved_tensors
+        grads = ctx.plan.run_backward(acts, out, g_out.contiguous())
+        return (None, None, None) + tuple(grads)
+
+
+def g1_forward(plan, x=None, points=None, freqs=None):
+    """out [P,4] = [sigmoid rgb | raw sigma].  Either `x` (fp32 [P,in_dim], already encoded, the
+    reference's calling convention) or `points` (fp32 [P,3]) + `freqs` (encoding fused into the
+    operand build, never materialised in fp32)."""
+    plan.refresh()
+    src = x if x is not None else points
+    ops._need_cuda("NeRFMLP", src)
+    if src.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("NeRFMLP: gradients w.r.t. the input coordinates are not supported")
+    lead = src.shape[:-1]
+    flat = src.reshape(-1, src.shape[-1])
+    if x is not None:
+        if flat.shape[-1] != plan.in_dim:
+            raise RuntimeError("NeRFMLP: expected %d input features, got %d" % (plan.in_dim, flat.shape[-1]))
+        x16 = encode_operand(flat, None, plan.k0)
+    else:
+        width = flat.shape[-1] * (2 * int(freqs.numel()) + 1)
+        if width != plan.in_dim:
+            raise RuntimeError("NeRFMLP: encoding width %d does not match the first layer (%d)" % (width, plan.in_dim))
+        x16 = encode_operand(flat, freqs, plan.k0)
+    params = plan.params()
+    keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    out = _G1Fn.apply(plan, keep, x16, *params)
+    return out.reshape(*lead, 4)

@@ -271,7 +271,7 @@ def linear_bf16(x, w, bias=None, act=0, relu_mask_src=None, out_bf16=True, out_f
     return y16, y32
 
 
-def wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True):
+def wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True, m_valid=0, n_valid=0):
     """dw[m*ld_m + n*ld_n] += sum_p u[p,m] v[p,n]  (nfs_wgrad_bf16).  u [P,M], v [P,N] bf16 (row
     slices of wider tensors are fine: the row pitch is taken from the strides); dw fp32."""
     _need_cuda("wgrad_bf16", u, v, dw, colsum)
@@ -285,6 +285,6 @@ def wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True):
         raise RuntimeError("wgrad_bf16: operands disagree on the number of points")
     if P:
         with torch.cuda.device(u.device):
-            _lib.call("nfs_wgrad_bf16", ptr(u), u.stride(0), ptr(v), v.stride(0), P, M, N, ptr(dw), int(ld_m),
-                      int(ld_n), ptr(colsum), int(bool(colsum_of_v)), _stream())
+            _lib.call("nfs_wgrad_bf16", ptr(u), u.stride(0), ptr(v), v.stride(0), P, M, N, int(m_valid), int(n_valid),
+                      ptr(dw), int(ld_m), int(ld_n), ptr(colsum), int(bool(colsum_of_v)), _stream())
     return dw
