@@ -13,6 +13,16 @@ from ._lib import ptr
 from .ops import _stream
 
 
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch():
+    """Called by optimisers that update parameter storage behind autograd's back (FusedAdam):
+    invalidates every cached bf16 operand copy."""
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
 def _ceil_to(v, m):
     return (v + m - 1) // m * m
 
@@ -48,7 +58,7 @@ class PackedLinear:
     def refresh(self):
         params = [p for l in self.linears for p in (l.weight, l.bias)]
         dev = params[0].device
-        key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (str(dev), _WEIGHT_EPOCH) + tuple((p.data_ptr(), p._version) for p in params)
         if key == self._key:
             return self
         if not params[0].is_cuda:

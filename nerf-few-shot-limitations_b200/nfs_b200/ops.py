@@ -101,8 +101,9 @@ def composite(rgb, density, z_vals, rays_d, noise=None, noise_std=0.0, white_bkg
     return o_rgb.reshape(*lead, 3), o_depth.reshape(lead), o_w.reshape(*lead, S)
 
 
-def composite_packed(rgb_sigma, z_vals, rays_d, noise=None, noise_std=0.0):
-    """rgb_sigma (...,S,4), z_vals (...,S), rays_d (...,3) -> rgb_map (...,3)."""
+def composite_packed(rgb_sigma, z_vals, rays_d, noise=None, noise_std=0.0, white_bkgd=False, want_aux=False):
+    """rgb_sigma (...,S,4), z_vals (...,S), rays_d (...,3) -> rgb_map (...,3)
+    [, depth (...), weights (...,S) when want_aux]."""
     _need_cuda("composite_packed", rgb_sigma, z_vals, rays_d, noise)
     lead = z_vals.shape[:-1]
     if rgb_sigma.shape[:-1] != z_vals.shape or rgb_sigma.shape[-1] != 4 or rays_d.shape != (*lead, 3):
@@ -112,8 +113,10 @@ def composite_packed(rgb_sigma, z_vals, rays_d, noise=None, noise_std=0.0):
         raise RuntimeError("composite_packed: n_samples must be positive")
     if z_vals.shape[-1] == 1:   # same reference quirk as in composite(): empty dists, rgb_map = 0
         return rgb_sigma.sum(dim=-2)[..., :3] * 0.0
-    o_rgb, _, _ = _CompositeFn.apply(_f32c(rgb_sigma), None, _f32c(z_vals), _f32c(rays_d), _f32c(noise),
-                                     noise_std, False, True, False)
+    o_rgb, o_depth, o_w = _CompositeFn.apply(_f32c(rgb_sigma), None, _f32c(z_vals), _f32c(rays_d), _f32c(noise),
+                                             noise_std, white_bkgd, True, want_aux)
+    if want_aux:
+        return o_rgb.reshape(*lead, 3), o_depth.reshape(lead), o_w.reshape(*lead, z_vals.shape[-1])
     return o_rgb.reshape(*lead, 3)
 
 

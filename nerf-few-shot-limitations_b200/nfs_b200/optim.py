@@ -1,0 +1,68 @@
+"""Fused flat Adam / AdamW (nfs_adam_step) for the small NeRF MLPs, plus gradient flattening.
+
+Replaces optim.Adam(...).step() of train.py:114-118,286 and optim.AdamW of
+train_multiscale.py:61 with one kernel over one flat fp32 buffer; the nn.Parameters become
+views of that buffer, so names, shapes and state_dict() are unchanged.  torch.optim works on
+the drop-in modules too - this class only removes ~40 tiny launches per step and gives the
+data-parallel driver a single buffer to all-reduce.
+"""
+import torch
+
+from . import _lib, mlp
+from ._lib import ptr
+from .ops import _stream
+
+
+class FusedAdam:
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FusedAdam: no trainable parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdam: parameters must live on a CUDA device (no CPU fallback)")
+        self.lr, self.betas, self.eps, self.weight_decay, self.decoupled = lr, betas, eps, weight_decay, decoupled
+        self.sizes = [p.numel() for p in self.params]
+        n = sum(self.sizes)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p, k in zip(self.params, self.sizes):
+                self.flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)       # parameter is now a view of the flat buffer
+                off += k
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.grad = torch.zeros_like(self.flat)
+        self.step_count = 0
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        """Flatten the parameters' .grad into self.grad (one concatenation kernel)."""
+        parts = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(parts, out=self.grad)
+        return self.grad
+
+    def step(self, grad_scale=1.0, gathered=False):
+        if not gathered:
+            self.gather_grads()
+        self.step_count += 1
+        with torch.cuda.device(self.flat.device):
+            _lib.call("nfs_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                      self.flat.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                      float(self.weight_decay), int(self.step_count), float(grad_scale), int(bool(self.decoupled)),
+                      _stream())
+        mlp.bump_weight_epoch()          # cached bf16 operand copies are stale now
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr = sd.get("lr", self.lr)

@@ -1,0 +1,87 @@
+"""CPU tests of host-side logic: sampler tables, ray sharding, gradient all-reduce over gloo
+(world_size 2), module state_dict compatibility with the reference's parameter names."""
+import os
+import subprocess
+import sys
+
+import torch
+
+from oracle import nerf_oracle as O
+
+
+def test_stratified_tables_match_oracle_arithmetic():
+    from nfs_b200.ops import stratified_tables
+    for near, far, S, lin in [(2.0, 6.0, 64, False), (2.0, 6.0, 1, False), (0.5, 9.0, 37, True), (2.0, 6.0, 192, False)]:
+        z, lo, up = stratified_tables(near, far, S, lin)
+        ro, rd = torch.zeros(1, 3), torch.zeros(1, 3)
+        _, z0 = O.stratified(ro, rd, near, far, S, t_rand=torch.zeros(1, S), lindisp=lin)
+        _, z1 = O.stratified(ro, rd, near, far, S, t_rand=torch.ones(1, S), lindisp=lin)
+        _, zb = O.stratified(ro, rd, near, far, S, lindisp=lin)
+        assert torch.equal(lo, z0[0]) and torch.equal(zb[0].contiguous(), z)
+        assert torch.equal(lo + (up - lo) * torch.ones(S), z1[0])
+
+
+def test_shard_range_partitions_exactly():
+    from nfs_b200.dist import shard_batch, shard_range
+    for n in (0, 1, 7, 4096, 640000, 640001):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    perm = torch.randperm(1000, generator=torch.Generator().manual_seed(0))
+    parts = [shard_batch(perm, 256, 512, r, 4) for r in range(4)]
+    assert torch.equal(torch.cat(parts), perm[256:768])
+    assert shard_batch(perm, 900, 512, 3, 4).numel() == 25
+
+
+def test_state_dict_matches_reference_names():
+    from models.nerf_model import NeRFMLP
+    ref = O.PlainNeRF()
+    mod = NeRFMLP()
+    assert list(mod.state_dict().keys()) == list(ref.state_dict().keys())
+    assert all(a.shape == b.shape and a.dtype == torch.float32
+               for a, b in zip(mod.state_dict().values(), ref.state_dict().values()))
+    mod.load_state_dict(ref.state_dict())
+    assert sum(p.numel() for p in mod.parameters()) == 477956
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path[:0] = [%r, %r]
+from nfs_b200 import dist as nd
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world, _ = nd.world()
+# every rank walks the same permutation; union of shards == the single-GPU batch
+perm = torch.randperm(4096, generator=torch.Generator().manual_seed(0))
+mine = nd.shard_batch(perm, 1024, 1024, rank, world)
+# toy 'gradient': sum over my rays of a per-ray vector, scaled so that the all-reduced result is the global mean
+table = torch.arange(4096 * 6, dtype=torch.float32).reshape(4096, 6) / 1000.0
+g = table[mine].sum(0) * (nd.loss_scale(mine.numel(), 1024) / max(mine.numel(), 1))
+nd.allreduce_sum_(g)
+expect = table[perm[1024:2048]].mean(0)
+assert torch.allclose(g, expect, rtol=1e-5), (g, expect)
+rows = table[mine][:, :3]
+counts = [nd.shard_range(1024, r, world)[1] - nd.shard_range(1024, r, world)[0] for r in range(world)]
+full = nd.gather_rows(rows, counts)
+assert torch.equal(full, table[perm[1024:2048]][:, :3])
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharding_and_allreduce(tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % (root, os.path.join(root, "nerf-few-shot-limitations_b200")))
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
