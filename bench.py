@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling aid (ncu): no clock-settle loop, no e2e leg, no CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -223,9 +225,9 @@ def main():
 
     # clock record: nvidia-smi samples every 200 ms, so keep the GPU under the same load for ~1.5 s
     # around the (much shorter) timed region; only samples taken under load are reported.
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank) if rank == 0 and not args.quick else None
     t_settle = time.perf_counter()
-    while time.perf_counter() - t_settle < 1.0:
+    while not args.quick and time.perf_counter() - t_settle < 1.0:
         for _ in range(50):
             fwd(); bwd()
         torch.cuda.synchronize()
@@ -279,8 +281,8 @@ def main():
         h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         return r.grad, s.grad
 
-    e2e_steps = max(3, min(steps, 10))
-    for _ in range(3):
+    e2e_steps = 1 if args.quick else max(3, min(steps, 10))
+    for _ in range(0 if args.quick else 3):
         e2e_step()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -329,7 +331,7 @@ def main():
             line["roofline"]["traffic"] = json.load(open(traffic_file)).get(dom)
         except Exception:
             pass
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not args.quick:
         threads = os.cpu_count() or 1
         sample = 1 << 17
         rate, sec, best = cpu_reference_rate(sample, 8, threads)

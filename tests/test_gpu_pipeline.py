@@ -73,6 +73,8 @@ def test_train_step_learns(cuda):
     from nfs_b200.optim import FusedAdam
     _, mod = _models(cuda, seed=9)
     mod.train()
+    with torch.no_grad():
+        mod.sigma_out.bias.fill_(0.3)      # default init can start with sigma <= 0 everywhere: relu-dead, zero gradient
     opt = FusedAdam(mod.parameters(), lr=5e-4)
     n = 1024
     ro, rd = O.lego_rays(n, seed=3)
