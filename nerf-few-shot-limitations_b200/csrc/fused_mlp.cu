@@ -1,0 +1,331 @@
+// K3 (fused multi-layer MLP forward) — a whole chain of dense layers per launch, activations
+// kept in shared memory / TMEM, weights streamed by TMA, every layer on tcgen05 tensor cores.
+//
+// Replaces the Linear(+ReLU) chain + heads of
+//   nerf_model.NeRFMLP.forward    /root/reference/src/models/nerf_model.py:16-24
+// (and any sub-chain of nerf_mlp.NeRFWithDINO, nerf_mlp.py:134-158) for 256 points per CTA step.
+//
+// One persistent CTA per SM works on PAIRS of 128-point tiles (A, B):
+//   * act[A], act[B]  : 2 x 64 KB shared memory, the bf16 activations of the current layer in
+//                       the canonical K-major SWIZZLE_128B operand layout (4 slabs of [128 x 64]);
+//                       the epilogue overwrites them IN PLACE with the next layer's input;
+//   * weight ring     : 3 x 32 KB stages, one [N x 64] K-slab of one layer each, TMA-loaded from a
+//                       single stacked bf16 weight tensor (L2 resident, ~1 MB) and shared by both
+//                       tiles - 128 KB of weights per layer feed 2 x 16 MMAs;
+//   * TMEM            : two 128 x 256 fp32 accumulators (512 columns), one per tile.
+// The MMA thread interleaves the two tiles slab by slab, so tile A's accumulator completes four
+// MMAs before tile B's: A's epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> swizzled st.shared)
+// overlaps B's last MMAs and B's epilogue overlaps A's first MMAs of the next layer.
+// When activations must be saved for the backward pass each epilogue warp TMA-stores the
+// 32-row x 64-column boxes it has just written (cp.async.bulk.tensor, bulk groups).
+// The last layer of the chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
+// written as fp32 with the reference's output activation.
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue (two per TMEM lane
+// quadrant, each taking half of the columns).
+#include "tc_common.cuh"
+
+namespace nfs {
+namespace {
+
+using namespace tc;
+
+constexpr int kFmThreads = 320;
+constexpr int kFmMaxLayers = 12;
+constexpr int kActBytes = 128 * 256 * 2;
+constexpr int kActSlab = 128 * 128;
+constexpr int kWStage = 256 * 128;
+constexpr int kWStages = 3;
+
+struct FusedArgs {
+  long long P;
+  long long save_rows;                 // rows per layer in the saved-activation tensor (P rounded up to 128)
+  int n_layers;
+  int K[kFmMaxLayers], N[kFmMaxLayers], act[kFmMaxLayers], row0[kFmMaxLayers];
+  const float *bias;                   // stacked like the weights: bias[row0[l] + n]
+  float *out;                          // [P, out_cols] fp32
+  int out_cols;
+  int save;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float fm_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(kFmThreads, 1)
+fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_save, const FusedArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *act[2] = {smem, smem + kActBytes};
+  uint8_t *wring = smem + 2 * kActBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWStages * kWStage);
+  uint64_t *w_full = bars, *w_empty = bars + kWStages;
+  uint64_t *in_full = bars + 2 * kWStages;       // [2] input operand of the chain landed (TMA)
+  uint64_t *act_free = in_full + 2;              // [2] last layer's MMAs have read act[t]
+  uint64_t *act_ready = act_free + 2;            // [2] epilogue wrote next layer's operand into act[t]
+  uint64_t *acc_full = act_ready + 2;            // [2] accumulator of tile t complete
+  uint64_t *head_done = acc_full + 2;            // [2] head epilogue drained accumulator t
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(head_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.n_layers;
+  const long long n_tiles = (a.P + 127) / 128;
+  const long long n_pairs = (n_tiles + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 8);
+      mbar_init(acc_full + t, 1); mbar_init(head_done + t, 8);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    if (a.save) tma_prefetch_desc(&tmap_save);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t wit = 0, iter = 0;
+      const int ks0 = a.K[0] >> 6;
+      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++iter) {
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(act_free + t, (iter & 1) ^ 1);
+          mbar_wait(head_done + t, (iter & 1) ^ 1);
+          mbar_expect_tx(in_full + t, (uint32_t)(ks0 * kActSlab));
+          for (int s = 0; s < ks0; ++s)
+            tma_load_2d(act[t] + s * kActSlab, &tmap_x, in_full + t, s * 64, (int)((2 * pair + t) * 128));
+        }
+        for (int l = 0; l < L; ++l) {
+          const int ks = a.K[l] >> 6, nb = a.N[l] >> 6;
+          for (int s = 0; s < ks; ++s, ++wit) {
+            const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
+            mbar_wait(w_empty + stage, ph ^ 1);
+            mbar_expect_tx(w_full + stage, (uint32_t)(a.N[l] * 128));
+            for (int b = 0; b < nb; ++b)
+              tma_load_2d(wring + stage * kWStage + b * 8192, &tmap_w, w_full + stage, s * 64, a.row0[l] + b * 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t wit = 0, iter = 0, n_ready[2] = {0, 0};
+      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++iter) {
+        for (int l = 0; l < L; ++l) {
+          const int ks = a.K[l] >> 6;
+          const uint32_t idesc = umma_idesc_bf16(128, a.N[l], 0, 0);
+          for (int s = 0; s < ks; ++s, ++wit) {
+            const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
+            mbar_wait(w_full + stage, ph);
+            tc_fence_after();
+            const uint32_t wa = smem_u32(wring + stage * kWStage);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              if (s == 0) {
+                if (l == 0) {
+                  mbar_wait(head_done + t, (iter & 1) ^ 1);    // accumulator t drained by the previous pair's head
+                  mbar_wait(in_full + t, iter & 1);
+                } else {
+                  mbar_wait(act_ready + t, n_ready[t] & 1);
+                  ++n_ready[t];
+                }
+                tc_fence_after();
+              }
+              const uint32_t xa = smem_u32(act[t] + s * kActSlab);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, umma_desc_sw128(xa + k * 32, 16, 1024), umma_desc_sw128(wa + k * 32, 16, 1024), idesc,
+                          (uint32_t)((s | k) != 0));
+              if (s == ks - 1) {
+                umma_commit(acc_full + t);
+                if (l == L - 1) umma_commit(act_free + t);
+              }
+            }
+            umma_commit(w_empty + stage);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int q = warp & 3;                  // TMEM lane quadrant
+    const int hsel = (warp - 2) >> 2;        // which half of the columns
+    const int r_in = q * 32 + lane;
+    uint32_t n_full[2] = {0, 0};
+    bool store_pending = false;
+    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        const int Nl = a.N[l], half = Nl >> 1, c_begin = hsel * half;
+        const float *bias = a.bias + a.row0[l];
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(acc_full + t, n_full[t] & 1);
+          ++n_full[t];
+          tc_fence_after();
+          const long long tile = 2 * pair + t;
+          const long long row = tile * 128 + r_in;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+          if (!last) {
+            // this warp's previous TMA store from act[t] (one layer ago) has finished READING the region it
+            // is about to overwrite; the store issued for the other tile a moment ago may stay in flight
+            if (store_pending) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
+            for (int c0 = c_begin; c0 < c_begin + half; c0 += 32) {
+              float v[32];
+              tmem_ld32(taddr + c0, v);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + g);
+                v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+              }
+              if (a.act[l] == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              uint8_t *slab = act[t] + (c0 >> 6) * kActSlab + r_in * 128;
+              const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 pk = make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                                            pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+                *reinterpret_cast<uint4 *>(slab + (((ch0 + g) ^ (r_in & 7)) << 4)) = pk;
+              }
+            }
+            tc_fence_before();
+            fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(act_ready + t);
+              if (a.save && tile < n_tiles) {
+                for (int c0 = c_begin; c0 < c_begin + half; c0 += 64)
+                  tma_store_2d(&tmap_save, act[t] + (c0 >> 6) * kActSlab + q * 32 * 128, c0,
+                               (int)(l * a.save_rows + tile * 128 + q * 32));
+                bulk_commit();
+              }
+            }
+            store_pending = a.save != 0;
+          } else {
+            // head: first out_cols columns, fp32, reference output activation
+            if (c_begin < a.out_cols) {
+              for (int c0 = c_begin; c0 < c_begin + half && c0 < a.out_cols; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (row < a.P) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    if (c0 + j < a.out_cols) {
+                      float x = v[j] + __ldg(bias + c0 + j);
+                      const int act = a.act[l];
+                      if (act == 1) x = fmaxf(x, 0.f);
+                      else if (act == 3 || (act == 2 && c0 + j < 3)) x = fm_sigmoid(x);
+                      v[j] = x;
+                    }
+                  }
+                  if (a.out_cols == 4 && c0 == 0) {
+                    *reinterpret_cast<float4 *>(a.out + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                      if (c0 + j < a.out_cols) a.out[row * a.out_cols + c0 + j] = v[j];
+                  }
+                }
+              }
+            }
+            tc_fence_before();
+            if (store_pending) { if (lane == 0) bulk_wait_read0(); store_pending = false; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(head_done + t);
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait0();               // all saved activations are in global memory
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+}  // namespace nfs
+
+using namespace nfs;
+
+// Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
+// default only in their row count (64 resp. 32).
+extern "C" int nfs_mlp_chain_fwd(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                                 const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                                 const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                                 void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
+                                 void *stream) {
+  const char *fn = "nfs_mlp_chain_fwd";
+  if (n_points < 0 || n_layers < 2 || n_layers > kFmMaxLayers) return fail_arg(fn, NFS_E_BADARG, "need 2..12 layers");
+  if (n_points == 0) return 0;
+  if (!x_bf16 || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || !bias_stack || !out_f32)
+    return fail_arg(fn, NFS_E_BADARG, "null pointer");
+  FusedArgs a{};
+  a.P = n_points; a.n_layers = n_layers; a.bias = bias_stack; a.out = out_f32; a.out_cols = out_cols;
+  a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
+  for (int l = 0; l < n_layers; ++l) {
+    a.K[l] = k_dims[l]; a.N[l] = n_dims[l]; a.act[l] = acts[l]; a.row0[l] = row0[l];
+    if (a.K[l] % 64 || a.K[l] <= 0 || a.K[l] > 256 || a.N[l] % 64 || a.N[l] <= 0 || a.N[l] > 256 ||
+        a.row0[l] < 0 || a.row0[l] + a.N[l] > w_rows)
+      return fail_arg(fn, NFS_E_UNSUPPORTED, "layer dims must be multiples of 64 in [64,256] and fit the weight stack");
+    if (l > 0 && a.K[l] != a.N[l - 1]) return fail_arg(fn, NFS_E_BADARG, "layer l input width != layer l-1 output width");
+  }
+  if (out_cols <= 0 || out_cols > a.N[n_layers - 1]) return fail_arg(fn, NFS_E_BADARG, "out_cols out of range");
+  if (a.save && save_rows_per_layer < ((n_points + 127) / 128) * 128)
+    return fail_arg(fn, NFS_E_BADARG, "save_rows_per_layer must be >= n_points rounded up to 128");
+  if (a.save)
+    for (int l = 0; l + 1 < n_layers; ++l)
+      if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal hidden widths");
+
+  CUtensorMap tx, tw, ts;
+  int rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)n_points, (uint64_t)a.K[0], (uint64_t)a.K[0], 128, fn);
+  if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tw, w_stack_bf16, (uint64_t)w_rows, 256, 256, 64, fn);
+  if (rc) return rc;
+  if (a.save) {
+    rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * (n_layers - 1)), (uint64_t)a.N[0],
+                            (uint64_t)a.N[0], 32, fn);
+    if (rc) return rc;
+  } else {
+    ts = tx;
+  }
+  const size_t smem = 1024 + 2 * kActBytes + kWStages * kWStage + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail_cuda(fn, e);
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_pairs = ((n_points + 127) / 128 + 1) / 2;
+  const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
+  fused_mlp_kernel<<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+  return check_launch(fn);
+}

@@ -6,6 +6,9 @@ sequences for forward / backward and the autograd glue.  Dense layers run in
 nfs_linear_bf16 (forward and dgrad, with bias / ReLU / sigmoid / ReLU-mask epilogues) and
 nfs_wgrad_bf16 (weight + bias gradients); nothing here computes on the CPU.
 """
+import ctypes
+import os
+
 import torch
 
 from . import _lib, ops
@@ -131,12 +134,61 @@ class G1Plan:
         return ps
 
     def refresh(self):
+        stale = any(p._key is None for p in self.packed + [self.head])
+        keys = [p._key for p in self.packed + [self.head]]
         for p in self.packed:
             p.refresh()
         self.head.refresh()
+        if keys != [p._key for p in self.packed + [self.head]] or stale or getattr(self, "w_stack", None) is None:
+            self._build_stack()
+
+    def _build_stack(self):
+        """One [rows,256] bf16 tensor holding every layer's padded W (and the biases likewise) for
+        the fused chain kernel."""
+        layers = self.packed + [self.head]
+        self.fusable = self.k0 <= 256 and len(layers) <= 12
+        if not self.fusable:
+            return
+        dev = self.head.w16.device
+        rows = sum(p.n_pad for p in layers)
+        w = torch.zeros(rows, 256, device=dev, dtype=torch.bfloat16)
+        b = torch.zeros(rows, device=dev, dtype=torch.float32)
+        r, row0 = 0, []
+        for p in layers:
+            w[r:r + p.n_pad, :p.k_pad].copy_(p.w16)
+            b[r:r + p.n_pad].copy_(p.bias)
+            row0.append(r)
+            r += p.n_pad
+        self.w_stack, self.b_stack, self.w_rows = w, b, rows
+        n = len(layers)
+        arr = ctypes.c_int32 * n
+        self.c_k = arr(*[p.k_pad for p in layers])
+        self.c_n = arr(*[p.n_pad for p in layers])
+        self.c_act = arr(*([1] * (n - 1) + [2]))
+        self.c_row0 = arr(*row0)
+
+    def run_forward_fused(self, x16, keep):
+        """nfs_mlp_chain_fwd: all layers in one launch; hidden activations are written to HBM only
+        when the backward pass will need them."""
+        P = x16.shape[0]
+        dev = x16.device
+        n_hidden = len(self.packed)
+        out = torch.empty((P, 4), device=dev, dtype=torch.float32)
+        save, rows = None, 0
+        if keep:
+            rows = _ceil_to(P, 128)
+            save = torch.empty((n_hidden, rows, self.h_pad), device=dev, dtype=torch.bfloat16)
+        if P:
+            with torch.cuda.device(dev):
+                _lib.call("nfs_mlp_chain_fwd", ptr(x16), P, n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0,
+                          ptr(self.w_stack), self.w_rows, ptr(self.b_stack), ptr(save), rows, ptr(out), 4, _stream())
+        acts = [x16] + ([save[i, :P] for i in range(n_hidden)] if keep else [])
+        return out, acts
 
     # forward over an already-built bf16 operand; returns (out fp32 [P,4], saved activations)
     def run_forward(self, x16, keep):
+        if getattr(self, "fusable", False) and os.environ.get("NFS_MLP_FUSED", "1") != "0":
+            return self.run_forward_fused(x16, keep)
         acts = [x16]
         h = x16
         for p in self.packed:

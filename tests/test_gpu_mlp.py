@@ -144,3 +144,26 @@ def test_g1_training_tracks_fp32(cuda):
     with torch.no_grad():
         out = mod(enc_c).cpu()
     assert float((out[:, :3] - ref(enc)[:, :3]).abs().max()) <= 5e-2
+
+
+@pytest.mark.parametrize("P", [1, 127, 128, 129, 256, 257, 40000, 148 * 256 * 3 + 5])
+def test_fused_chain_matches_layerwise(cuda, P, monkeypatch):
+    """nfs_mlp_chain_fwd (one launch, activations on chip) == the layer-by-layer launches: same bf16
+    operands, same fp32 accumulation order per layer -> identical saved activations and outputs."""
+    from models.nerf_model import NeRFMLP
+    torch.manual_seed(2)
+    mod = NeRFMLP().to(cuda)
+    plan = mod._get_plan()
+    plan.refresh()
+    g = torch.Generator().manual_seed(P)
+    x16 = torch.randn(P, 64, generator=g).to(torch.bfloat16).to(cuda)
+    x16[:, 63] = 0
+    out_f, acts_f = plan.run_forward_fused(x16, keep=True)
+    monkeypatch.setenv("NFS_MLP_FUSED", "0")
+    out_l, acts_l = plan.run_forward(x16, keep=True)
+    assert len(acts_f) == len(acts_l) == 9
+    for i, (a, b) in enumerate(zip(acts_f, acts_l)):
+        assert a.shape == b.shape and torch.equal(a, b), "activation %d differs" % i
+    assert torch.equal(out_f, out_l)
+    out_n, acts_n = plan.run_forward_fused(x16, keep=False)        # inference: nothing saved
+    assert torch.equal(out_n, out_f) and len(acts_n) == 1
