@@ -174,22 +174,29 @@ int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int6
                    float *dw, int64_t ld_m, int64_t ld_n,
                    float *colsum, int32_t colsum_of_v, void *stream);
 
-/* nfs_mlp_chain_fwd: a whole chain of dense layers in ONE launch (fused multi-layer MLP):
+/* nfs_mlp_chain: a whole chain of dense layers in ONE launch (fused multi-layer MLP):
  *   h_0 = X;  h_{l+1} = act_l( h_l . W_l^T + b_l ),  l = 0 .. n_layers-1
- *   replaces nerf_model.NeRFMLP.forward (src/models/nerf_model.py:16-24): activations stay in
- *   shared memory / TMEM between layers, weights are TMA-streamed from one stacked bf16 tensor
- *   w_stack [w_rows, 256] (layer l = rows row0[l] .. row0[l]+N_l, columns 0..K_l, zero padded),
- *   biases stacked the same way (bias_stack[row0[l] + n]).  K_l, N_l multiples of 64 in
- *   [64,256], K_l == N_{l-1}.  acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid.
- *   The LAST layer is the output head: its first out_cols columns are written as fp32 to
- *   out_f32 [P,out_cols].  save_bf16 (|NULL): [(n_layers-1), save_rows_per_layer, N_0] bf16 -
- *   when given, every hidden layer's output is TMA-stored there for the backward pass
- *   (save_rows_per_layer >= P rounded up to 128). */
-int nfs_mlp_chain_fwd(const void *x_bf16, int64_t n_points, int32_t n_layers,
-                      const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
-                      const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
-                      const float *bias_stack, void *save_bf16, int64_t save_rows_per_layer,
-                      float *out_f32, int32_t out_cols, void *stream);
+ *   Forward use: replaces nerf_model.NeRFMLP.forward (src/models/nerf_model.py:16-24).
+ *   Backward use: the dgrad chain of its autograd backward (X = dL/d(head pre-activation),
+ *   W_l = transposed weights in reverse order, act 4 = ReLU backward).
+ *   Activations stay in shared memory / TMEM between layers; weights are TMA-streamed from one
+ *   stacked bf16 tensor w_stack [w_rows, 256] (layer l = rows row0[l] .. row0[l]+N_l, columns
+ *   0..K_l, zero padded); biases stacked the same way (bias_stack[row0[l] + n]) or NULL.
+ *   K_l, N_l multiples of 64 in [64,256], K_l == N_{l-1}.
+ *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 4 multiply by
+ *   [mask[mask_idx[l]][p][n] > 0] with mask_bf16 = [*, mask_rows_per_layer, N_l] bf16 (the
+ *   activations saved by the forward chain).
+ *   out_f32 != NULL: the LAST layer is an output head whose first out_cols columns are written
+ *   as fp32 [P,out_cols].  save_bf16 != NULL: [n_saved, save_rows_per_layer, N_0] bf16 receives
+ *   every non-head layer's output by TMA store (n_saved = n_layers - 1 with a head, else
+ *   n_layers); *_rows_per_layer >= P rounded up to 128. */
+int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
+                  const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
+                  const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
+                  const float *bias_stack,
+                  const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
+                  void *save_bf16, int64_t save_rows_per_layer,
+                  float *out_f32, int32_t out_cols, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * K2 fused with the operand cast of the first dense layer

@@ -45,7 +45,21 @@ struct FusedArgs {
   float *out;                          // [P, out_cols] fp32
   int out_cols;
   int save;
+  int head;                            // 1: last layer is the fp32 output head; 0: it is a regular (saved) layer
+  const __nv_bfloat16 *mask;           // act 4: [n, mask_rows, N] bf16, result *= [mask[mask_idx[l]][row][col] > 0]
+  long long mask_rows;
+  int mask_idx[kFmMaxLayers];
 };
+
+// zero v[8*g .. 8*g+7] where the corresponding bf16 of m is not > 0 (ReLU backward)
+__device__ __forceinline__ void apply_relu_mask(float (&v)[32], int g, const uint4 &m) {
+  const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    if (!((w[h] & 0x7FFFu) != 0 && (w[h] & 0x8000u) == 0)) v[g * 8 + 2 * h] = 0.f;
+    if (!((w[h] & 0x7FFF0000u) != 0 && (w[h] & 0x80000000u) == 0)) v[g * 8 + 2 * h + 1] = 0.f;
+  }
+}
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c_inner, int c_outer) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -176,30 +190,51 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
+        const bool is_head = last && a.head != 0;
         const int Nl = a.N[l], half = Nl >> 1, c_begin = hsel * half;
-        const float *bias = a.bias + a.row0[l];
+        const float *bias = a.bias ? a.bias + a.row0[l] : nullptr;
+        const bool masked = a.act[l] == 4;
         for (int t = 0; t < 2; ++t) {
+          // ReLU-backward mask rows come straight from HBM: start the first chunk's loads before
+          // blocking on the accumulator, then stay one chunk ahead
+          const __nv_bfloat16 *mrow = nullptr;
+          uint4 mk[4] = {};
+          if (masked && (2 * pair + t) < n_tiles) {
+            mrow = a.mask + ((long long)a.mask_idx[l] * a.mask_rows + (2 * pair + t) * 128 + r_in) * Nl;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c_begin) + g);
+          }
           mbar_wait(acc_full + t, n_full[t] & 1);
           ++n_full[t];
           tc_fence_after();
           const long long tile = 2 * pair + t;
           const long long row = tile * 128 + r_in;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
-          if (!last) {
+          if (!is_head) {
             // this warp's previous TMA store from act[t] (one layer ago) has finished READING the region it
             // is about to overwrite; the store issued for the other tile a moment ago may stay in flight
             if (store_pending) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
             for (int c0 = c_begin; c0 < c_begin + half; c0 += 32) {
               float v[32];
               tmem_ld32(taddr + c0, v);
+              if (bias != nullptr) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + g);
-                v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+                for (int g = 0; g < 8; ++g) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + g);
+                  v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+                }
               }
               if (a.act[l] == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (masked) {
+                uint4 cur[4] = {mk[0], mk[1], mk[2], mk[3]};
+                if (mrow != nullptr && c0 + 32 < c_begin + half) {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c0 + 32) + g);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) apply_relu_mask(v, g, cur[g]);
               }
               uint8_t *slab = act[t] + (c0 >> 6) * kActSlab + r_in * 128;
               const int ch0 = (c0 & 63) >> 3;
@@ -214,7 +249,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
             __syncwarp();
             if (lane == 0) {
-              mbar_arrive(act_ready + t);
+              if (!last) mbar_arrive(act_ready + t);
               if (a.save && tile < n_tiles) {
                 for (int c0 = c_begin; c0 < c_begin + half; c0 += 64)
                   tma_store_2d(&tmap_save, act[t] + (c0 >> 6) * kActSlab + q * 32 * 128, c0,
@@ -223,6 +258,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               }
             }
             store_pending = a.save != 0;
+            if (last) {                          // chain ends in a regular layer: tile t is finished once the
+              if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
+              store_pending = false;
+              __syncwarp();
+              if (lane == 0) mbar_arrive(head_done + t);
+            }
           } else {
             // head: first out_cols columns, fp32, reference output activation
             if (c_begin < a.out_cols) {
@@ -233,7 +274,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                   for (int j = 0; j < 32; ++j) {
                     if (c0 + j < a.out_cols) {
-                      float x = v[j] + __ldg(bias + c0 + j);
+                      float x = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
                       const int act = a.act[l];
                       if (act == 1) x = fmaxf(x, 0.f);
                       else if (act == 3 || (act == 2 && c0 + j < 3)) x = fm_sigmoid(x);
@@ -276,32 +317,43 @@ using namespace nfs;
 
 // Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
 // default only in their row count (64 resp. 32).
-extern "C" int nfs_mlp_chain_fwd(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
-                                 const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
-                                 const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
-                                 void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
-                                 void *stream) {
-  const char *fn = "nfs_mlp_chain_fwd";
+extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                             const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                             const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                             const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
+                             void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
+                             void *stream) {
+  const char *fn = "nfs_mlp_chain";
   if (n_points < 0 || n_layers < 2 || n_layers > kFmMaxLayers) return fail_arg(fn, NFS_E_BADARG, "need 2..12 layers");
   if (n_points == 0) return 0;
-  if (!x_bf16 || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || !bias_stack || !out_f32)
+  if (!x_bf16 || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || (!out_f32 && !save_bf16))
     return fail_arg(fn, NFS_E_BADARG, "null pointer");
   FusedArgs a{};
   a.P = n_points; a.n_layers = n_layers; a.bias = bias_stack; a.out = out_f32; a.out_cols = out_cols;
   a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
+  a.head = out_f32 != nullptr;
+  a.mask = (const __nv_bfloat16 *)mask_bf16; a.mask_rows = mask_rows_per_layer;
   for (int l = 0; l < n_layers; ++l) {
     a.K[l] = k_dims[l]; a.N[l] = n_dims[l]; a.act[l] = acts[l]; a.row0[l] = row0[l];
+    a.mask_idx[l] = mask_idx ? mask_idx[l] : 0;
+    if (a.act[l] == 4 && (!mask_bf16 || !mask_idx || a.mask_idx[l] < 0))
+      return fail_arg(fn, NFS_E_BADARG, "act 4 (ReLU-backward mask) needs mask_bf16 and mask_idx");
+    if (a.act[l] < 0 || a.act[l] > 4) return fail_arg(fn, NFS_E_BADARG, "act must be 0..4");
     if (a.K[l] % 64 || a.K[l] <= 0 || a.K[l] > 256 || a.N[l] % 64 || a.N[l] <= 0 || a.N[l] > 256 ||
         a.row0[l] < 0 || a.row0[l] + a.N[l] > w_rows)
       return fail_arg(fn, NFS_E_UNSUPPORTED, "layer dims must be multiples of 64 in [64,256] and fit the weight stack");
     if (l > 0 && a.K[l] != a.N[l - 1]) return fail_arg(fn, NFS_E_BADARG, "layer l input width != layer l-1 output width");
   }
-  if (out_cols <= 0 || out_cols > a.N[n_layers - 1]) return fail_arg(fn, NFS_E_BADARG, "out_cols out of range");
-  if (a.save && save_rows_per_layer < ((n_points + 127) / 128) * 128)
+  if (a.head && (out_cols <= 0 || out_cols > a.N[n_layers - 1])) return fail_arg(fn, NFS_E_BADARG, "out_cols out of range");
+  const long long rows128 = ((n_points + 127) / 128) * 128;
+  if (a.save && save_rows_per_layer < rows128)
     return fail_arg(fn, NFS_E_BADARG, "save_rows_per_layer must be >= n_points rounded up to 128");
+  if (mask_bf16 && mask_rows_per_layer < rows128)
+    return fail_arg(fn, NFS_E_BADARG, "mask_rows_per_layer must be >= n_points rounded up to 128");
+  const int n_saved = a.head ? n_layers - 1 : n_layers;
   if (a.save)
-    for (int l = 0; l + 1 < n_layers; ++l)
-      if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal hidden widths");
+    for (int l = 0; l < n_saved; ++l)
+      if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal layer widths");
 
   CUtensorMap tx, tw, ts;
   int rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)n_points, (uint64_t)a.K[0], (uint64_t)a.K[0], 128, fn);
@@ -309,7 +361,7 @@ extern "C" int nfs_mlp_chain_fwd(const void *x_bf16, int64_t n_points, int32_t n
   rc = tc::make_tmap_bf16(&tw, w_stack_bf16, (uint64_t)w_rows, 256, 256, 64, fn);
   if (rc) return rc;
   if (a.save) {
-    rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * (n_layers - 1)), (uint64_t)a.N[0],
+    rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * n_saved), (uint64_t)a.N[0],
                             (uint64_t)a.N[0], 32, fn);
     if (rc) return rc;
   } else {

@@ -166,9 +166,27 @@ class G1Plan:
         self.c_n = arr(*[p.n_pad for p in layers])
         self.c_act = arr(*([1] * (n - 1) + [2]))
         self.c_row0 = arr(*row0)
+        # dgrad chain: X = dL/d(head pre-activation) [P,64]; layer j multiplies by the transposed
+        # weight of forward layer (n_hidden - j) (j = 0: the head) and masks with that layer's input
+        nh = n - 1
+        back = [self.head] + [self.packed[i] for i in range(nh - 1, 0, -1)]
+        rows_t = sum(p.k_pad for p in back)
+        wt = torch.zeros(rows_t, 256, device=dev, dtype=torch.bfloat16)
+        r, row0_t = 0, []
+        for p in back:
+            wt[r:r + p.k_pad, :p.n_pad].copy_(p.w16t)
+            row0_t.append(r)
+            r += p.k_pad
+        self.wt_stack, self.wt_rows = wt, rows_t
+        arr_b = ctypes.c_int32 * nh
+        self.cb_k = arr_b(*[p.n_pad for p in back])
+        self.cb_n = arr_b(*[p.k_pad for p in back])
+        self.cb_act = arr_b(*([4] * nh))
+        self.cb_row0 = arr_b(*row0_t)
+        self.cb_mask = arr_b(*[nh - 1 - j for j in range(nh)])      # h_{nh-j} = forward save[nh-1-j]
 
     def run_forward_fused(self, x16, keep):
-        """nfs_mlp_chain_fwd: all layers in one launch; hidden activations are written to HBM only
+        """nfs_mlp_chain: all layers in one launch; hidden activations are written to HBM only
         when the backward pass will need them."""
         P = x16.shape[0]
         dev = x16.device
@@ -180,13 +198,28 @@ class G1Plan:
             save = torch.empty((n_hidden, rows, self.h_pad), device=dev, dtype=torch.bfloat16)
         if P:
             with torch.cuda.device(dev):
-                _lib.call("nfs_mlp_chain_fwd", ptr(x16), P, n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0,
-                          ptr(self.w_stack), self.w_rows, ptr(self.b_stack), ptr(save), rows, ptr(out), 4, _stream())
+                _lib.call("nfs_mlp_chain", ptr(x16), P, n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0,
+                          ptr(self.w_stack), self.w_rows, ptr(self.b_stack), None, 0, None, ptr(save), rows,
+                          ptr(out), 4, _stream())
         acts = [x16] + ([save[i, :P] for i in range(n_hidden)] if keep else [])
-        return out, acts
+        return out, acts, save
+
+    def dgrad_chain_fused(self, dy, save_fwd, P):
+        """All dgrad GEMMs of the backward pass in one launch (nfs_mlp_chain with act 4): returns
+        [n_hidden, rows, h_pad] bf16 whose slice j is dL/d(pre-activation of layer n_hidden-1-j)."""
+        n_hidden = len(self.packed)
+        rows = save_fwd.shape[1]
+        out = torch.empty((n_hidden, rows, self.h_pad), device=dy.device, dtype=torch.bfloat16)
+        with torch.cuda.device(dy.device):
+            _lib.call("nfs_mlp_chain", ptr(dy), P, n_hidden, self.cb_k, self.cb_n, self.cb_act, self.cb_row0,
+                      ptr(self.wt_stack), self.wt_rows, None, ptr(save_fwd), rows, self.cb_mask, ptr(out), rows,
+                      None, 0, _stream())
+        return out
 
     # forward over an already-built bf16 operand; returns (out fp32 [P,4], saved activations)
     def run_forward(self, x16, keep):
+        """-> (out, acts, save): `save` is the forward chain's [n_hidden, rows, h_pad] activation tensor
+        (fused path) or None (layer-by-layer path)."""
         if getattr(self, "fusable", False) and os.environ.get("NFS_MLP_FUSED", "1") != "0":
             return self.run_forward_fused(x16, keep)
         acts = [x16]
@@ -198,9 +231,9 @@ class G1Plan:
         if not keep:
             acts.append(h)
         _, out = ops.linear_bf16(h, self.head.w16, self.head.bias, act=2, out_bf16=False, out_f32_cols=4)
-        return out, acts
+        return out, acts, None
 
-    def run_backward(self, acts, out, g_out):
+    def run_backward(self, acts, out, g_out, save_fwd=None):
         """Returns the list of parameter gradients in params() order."""
         m = self.module
         dev = out.device
@@ -223,6 +256,16 @@ class G1Plan:
         views[2 * n_layers + 1].copy_(tmp_b[3:4])
         views[2 * n_layers + 2].copy_(tmp_w[0:3, :hd])      # rgb_out.weight
         views[2 * n_layers + 3].copy_(tmp_b[0:3])
+        if save_fwd is not None and n_layers >= 2 and os.environ.get("NFS_MLP_FUSED_BWD", "1") != "0":
+            P = out.shape[0]
+            dys = self.dgrad_chain_fused(dy, save_fwd, P)
+            for i in range(n_layers - 1, 0, -1):
+                dyi = dys[n_layers - 1 - i, :P]
+                ops.wgrad_bf16(acts[i], dyi, views[2 * i], 1, hd, colsum=views[2 * i + 1], colsum_of_v=True,
+                               m_valid=hd, n_valid=hd)
+            ops.wgrad_bf16(dys[n_layers - 1, :P], acts[0], views[0], self.in_dim, 1, colsum=views[1],
+                           colsum_of_v=False, m_valid=hd, n_valid=self.in_dim)
+            return views
         dh, _ = ops.linear_bf16(dy, self.head.w16t, None, act=0, relu_mask_src=h_last)
         for i in range(n_layers - 1, 0, -1):
             x_in = acts[i]                                   # input of layer i (= output of layer i-1)
@@ -241,17 +284,26 @@ class G1Plan:
 class _G1Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, keep, x16, *params):
-        out, acts = plan.run_forward(x16, keep)
+        out, acts, save = plan.run_forward(x16, keep)
         ctx.plan = plan
-        ctx.keep = keep
+        ctx.fused = save is not None
         if keep:
-            ctx.save_for_backward(out, *acts)
+            if ctx.fused:
+                ctx.save_for_backward(out, x16, save)
+            else:
+                ctx.save_for_backward(out, *acts)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        out, *acts = ctx.saved_tensors
-        grads = ctx.plan.run_backward(acts, out, g_out.contiguous())
+        if ctx.fused:
+            out, x16, save = ctx.saved_tensors
+            P = out.shape[0]
+            acts = [x16] + [save[i, :P] for i in range(save.shape[0])]
+        else:
+            out, *acts = ctx.saved_tensors
+            save = None
+        grads = ctx.plan.run_backward(acts, out, g_out.contiguous(), save_fwd=save)
         return (None, None, None) + tuple(grads)
 
 

@@ -158,12 +158,19 @@ def test_fused_chain_matches_layerwise(cuda, P, monkeypatch):
     g = torch.Generator().manual_seed(P)
     x16 = torch.randn(P, 64, generator=g).to(torch.bfloat16).to(cuda)
     x16[:, 63] = 0
-    out_f, acts_f = plan.run_forward_fused(x16, keep=True)
+    out_f, acts_f, save_f = plan.run_forward_fused(x16, keep=True)
     monkeypatch.setenv("NFS_MLP_FUSED", "0")
-    out_l, acts_l = plan.run_forward(x16, keep=True)
+    out_l, acts_l, _ = plan.run_forward(x16, keep=True)
     assert len(acts_f) == len(acts_l) == 9
     for i, (a, b) in enumerate(zip(acts_f, acts_l)):
         assert a.shape == b.shape and torch.equal(a, b), "activation %d differs" % i
     assert torch.equal(out_f, out_l)
-    out_n, acts_n = plan.run_forward_fused(x16, keep=False)        # inference: nothing saved
+    out_n, acts_n, _ = plan.run_forward_fused(x16, keep=False)     # inference: nothing saved
     assert torch.equal(out_n, out_f) and len(acts_n) == 1
+    # backward: fused dgrad chain == layer-by-layer dgrad launches (same operands), gradients bit-equal up to
+    # the order of the fp32 atomics in wgrad
+    g_out = torch.randn(P, 4, generator=g).to(cuda)
+    grads_l = plan.run_backward(acts_l, out_l, g_out, save_fwd=None)
+    grads_f = plan.run_backward(acts_f, out_f, g_out, save_fwd=save_f)
+    for a, b in zip(grads_f, grads_l):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max() + 1e-12) + 1e-7
