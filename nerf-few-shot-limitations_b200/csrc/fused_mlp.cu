@@ -20,8 +20,8 @@
 // 32-row x 64-column boxes it has just written (cp.async.bulk.tensor, bulk groups).
 // The last layer of the chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
 // written as fp32 with the reference's output activation.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue (two per TMEM lane
-// quadrant, each taking half of the columns).
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue of tile A, 10..17 =
+// epilogue of tile B (two warps per TMEM lane quadrant, each taking half of the columns).
 #include "tc_common.cuh"
 
 namespace nfs {
@@ -29,7 +29,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kFmThreads = 320;
+constexpr int kFmThreads = 576;   // 18 warps
 constexpr int kFmMaxLayers = 12;
 constexpr int kActBytes = 128 * 256 * 2;
 constexpr int kActSlab = 128 * 128;
@@ -51,7 +51,7 @@ struct FusedArgs {
   int mask_idx[kFmMaxLayers];
 };
 
-// zero v[8*g .. 8*g+7] where the corresponding bf16 of m is not > 0 (ReLU backward)
+// (layer-by-layer reference form, kept for documentation) zero v where the bf16 of m is not > 0
 __device__ __forceinline__ void apply_relu_mask(float (&v)[32], int g, const uint4 &m) {
   const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
@@ -73,6 +73,25 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 
 __device__ __forceinline__ float fm_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// bf16x2 pack with the ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// ReLU backward on a packed pair: keep v where the saved activation h (>= 0, output of a ReLU) is
+// non-zero.  min(h * 2^126, 1) is exactly 1.0 for every positive bf16 and 0 for +0.
+__device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t v, uint32_t h) {
+  const uint32_t big = 0x7E807E80u;   // bf16x2 {2^126, 2^126}
+  const uint32_t one = 0x3F803F80u;   // bf16x2 {1, 1}
+  uint32_t m, r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(big));
+  asm("min.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(m), "r"(one));
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(m));
+  return r;
+}
+
+template <bool kMasked>
 __global__ void __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_save, const FusedArgs a) {
@@ -181,121 +200,128 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    const int q = warp & 3;                  // TMEM lane quadrant
-    const int hsel = (warp - 2) >> 2;        // which half of the columns
+    // ------------------------------------------------------------------ epilogue (2 x 8 warps)
+    // warps 2..9 own tile A, warps 10..17 tile B; within a tile: TMEM lane quadrant q x column half
+    const int t = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int hsel = ((warp - 2) >> 2) & 1;
     const int r_in = q * 32 + lane;
-    uint32_t n_full[2] = {0, 0};
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+    uint32_t n_full = 0;
     bool store_pending = false;
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const long long tile = 2 * pair + t;
+      const long long row = tile * 128 + r_in;
       for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
         const bool is_head = last && a.head != 0;
         const int Nl = a.N[l], half = Nl >> 1, c_begin = hsel * half;
         const float *bias = a.bias ? a.bias + a.row0[l] : nullptr;
-        const bool masked = a.act[l] == 4;
-        for (int t = 0; t < 2; ++t) {
-          // ReLU-backward mask rows come straight from HBM: start the first chunk's loads before
-          // blocking on the accumulator, then stay one chunk ahead
-          const __nv_bfloat16 *mrow = nullptr;
-          uint4 mk[4] = {};
-          if (masked && (2 * pair + t) < n_tiles) {
-            mrow = a.mask + ((long long)a.mask_idx[l] * a.mask_rows + (2 * pair + t) * 128 + r_in) * Nl;
+        // ReLU-backward mask rows come straight from HBM: start the first chunk's loads before
+        // blocking on the accumulator, then stay one chunk ahead
+        const __nv_bfloat16 *mrow = nullptr;
+        uint4 mk[4] = {};
+        if (kMasked && a.act[l] == 4 && tile < n_tiles) {
+          mrow = a.mask + ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c_begin) + g);
-          }
-          mbar_wait(acc_full + t, n_full[t] & 1);
-          ++n_full[t];
-          tc_fence_after();
-          const long long tile = 2 * pair + t;
-          const long long row = tile * 128 + r_in;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
-          if (!is_head) {
-            // this warp's previous TMA store from act[t] (one layer ago) has finished READING the region it
-            // is about to overwrite; the store issued for the other tile a moment ago may stay in flight
-            if (store_pending) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
-            for (int c0 = c_begin; c0 < c_begin + half; c0 += 32) {
-              float v[32];
-              tmem_ld32(taddr + c0, v);
-              if (bias != nullptr) {
+          for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c_begin) + g);
+        }
+        mbar_wait(acc_full + t, n_full & 1);
+        ++n_full;
+        tc_fence_after();
+        if (!is_head) {
+          // this warp's TMA store of the previous layer has finished READING the region overwritten below
+          if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+          const bool relu = a.act[l] == 1;
+          for (int c0 = c_begin; c0 < c_begin + half; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            if (bias != nullptr) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + g);
-                  v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
-                }
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + g);
+                v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
               }
-              if (a.act[l] == 1) {
+            }
+            uint32_t pk[16];
+            if (relu) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              } else if (masked) {
-                uint4 cur[4] = {mk[0], mk[1], mk[2], mk[3]};
-                if (mrow != nullptr && c0 + 32 < c_begin + half) {
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+            } else {
 #pragma unroll
-                  for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c0 + 32) + g);
-                }
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
+            if (kMasked && a.act[l] == 4) {
+              const uint4 cur[4] = {mk[0], mk[1], mk[2], mk[3]};
+              if (mrow != nullptr && c0 + 32 < c_begin + half) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) apply_relu_mask(v, g, cur[g]);
+                for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c0 + 32) + g);
               }
-              uint8_t *slab = act[t] + (c0 >> 6) * kActSlab + r_in * 128;
-              const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                const uint4 pk = make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                                            pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-                *reinterpret_cast<uint4 *>(slab + (((ch0 + g) ^ (r_in & 7)) << 4)) = pk;
+                pk[4 * g] = relu_mask_bf16x2(pk[4 * g], cur[g].x);
+                pk[4 * g + 1] = relu_mask_bf16x2(pk[4 * g + 1], cur[g].y);
+                pk[4 * g + 2] = relu_mask_bf16x2(pk[4 * g + 2], cur[g].z);
+                pk[4 * g + 3] = relu_mask_bf16x2(pk[4 * g + 3], cur[g].w);
               }
             }
-            tc_fence_before();
-            fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
-            __syncwarp();
-            if (lane == 0) {
-              if (!last) mbar_arrive(act_ready + t);
-              if (a.save && tile < n_tiles) {
-                for (int c0 = c_begin; c0 < c_begin + half; c0 += 64)
-                  tma_store_2d(&tmap_save, act[t] + (c0 >> 6) * kActSlab + q * 32 * 128, c0,
-                               (int)(l * a.save_rows + tile * 128 + q * 32));
-                bulk_commit();
-              }
-            }
-            store_pending = a.save != 0;
-            if (last) {                          // chain ends in a regular layer: tile t is finished once the
-              if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
-              store_pending = false;
-              __syncwarp();
-              if (lane == 0) mbar_arrive(head_done + t);
-            }
-          } else {
-            // head: first out_cols columns, fp32, reference output activation
-            if (c_begin < a.out_cols) {
-              for (int c0 = c_begin; c0 < c_begin + half && c0 < a.out_cols; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                if (row < a.P) {
+            uint8_t *slab = act[t] + (c0 >> 6) * kActSlab + r_in * 128;
+            const int ch0 = (c0 & 63) >> 3;
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    if (c0 + j < a.out_cols) {
-                      float x = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
-                      const int act = a.act[l];
-                      if (act == 1) x = fmaxf(x, 0.f);
-                      else if (act == 3 || (act == 2 && c0 + j < 3)) x = fm_sigmoid(x);
-                      v[j] = x;
-                    }
-                  }
-                  if (a.out_cols == 4 && c0 == 0) {
-                    *reinterpret_cast<float4 *>(a.out + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                      if (c0 + j < a.out_cols) a.out[row * a.out_cols + c0 + j] = v[j];
-                  }
-                }
-              }
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4 *>(slab + (((ch0 + g) ^ (r_in & 7)) << 4)) =
+                  make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+          tc_fence_before();
+          fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
+          __syncwarp();
+          if (lane == 0) {
+            if (!last) mbar_arrive(act_ready + t);
+            if (a.save && tile < n_tiles) {
+              for (int c0 = c_begin; c0 < c_begin + half; c0 += 64)
+                tma_store_2d(&tmap_save, act[t] + (c0 >> 6) * kActSlab + q * 32 * 128, c0,
+                             (int)(l * a.save_rows + tile * 128 + q * 32));
+              bulk_commit();
             }
-            tc_fence_before();
-            if (store_pending) { if (lane == 0) bulk_wait_read0(); store_pending = false; }
+          }
+          store_pending = a.save != 0;
+          if (last) {                          // chain ends in a regular layer: tile t is finished once the
+            if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
+            store_pending = false;
             __syncwarp();
             if (lane == 0) mbar_arrive(head_done + t);
           }
+        } else {
+          // head: first out_cols columns, fp32, reference output activation
+          if (c_begin < a.out_cols) {
+            for (int c0 = c_begin; c0 < c_begin + half && c0 < a.out_cols; c0 += 32) {
+              float v[32];
+              tmem_ld32(taddr + c0, v);
+              if (row < a.P) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (c0 + j < a.out_cols) {
+                    float x = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
+                    const int act = a.act[l];
+                    if (act == 1) x = fmaxf(x, 0.f);
+                    else if (act == 3 || (act == 2 && c0 + j < 3)) x = fm_sigmoid(x);
+                    v[j] = x;
+                  }
+                }
+                if (a.out_cols == 4 && c0 == 0) {
+                  *reinterpret_cast<float4 *>(a.out + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (c0 + j < a.out_cols) a.out[row * a.out_cols + c0 + j] = v[j];
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          if (store_pending) { if (lane == 0) bulk_wait_read0(); store_pending = false; }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(head_done + t);
         }
       }
     }
@@ -370,7 +396,9 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   const size_t smem = 1024 + 2 * kActBytes + kWStages * kWStage + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fused_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail_cuda(fn, e);
     attr_set = true;
   }
@@ -378,6 +406,9 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_pairs = ((n_points + 127) / 128 + 1) / 2;
   const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
-  fused_mlp_kernel<<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+  if (mask_bf16 != nullptr)
+    fused_mlp_kernel<true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+  else
+    fused_mlp_kernel<false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
   return check_launch(fn);
 }
