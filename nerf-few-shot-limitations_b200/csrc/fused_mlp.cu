@@ -20,8 +20,8 @@
 // 32-row x 64-column boxes it has just written (cp.async.bulk.tensor, bulk groups).
 // The last layer of the chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
 // written as fp32 with the reference's output activation.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue of tile A, 10..17 =
-// epilogue of tile B (two warps per TMEM lane quadrant, each taking half of the columns).
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..17 = epilogue (four warps per TMEM
+// lane quadrant, each draining a quarter of the columns of tile A, then of tile B, with one tcgen05.ld).
 #include "tc_common.cuh"
 
 namespace nfs {
@@ -50,16 +50,6 @@ struct FusedArgs {
   long long mask_rows;
   int mask_idx[kFmMaxLayers];
 };
-
-// (layer-by-layer reference form, kept for documentation) zero v where the bf16 of m is not > 0
-__device__ __forceinline__ void apply_relu_mask(float (&v)[32], int g, const uint4 &m) {
-  const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    if (!((w[h] & 0x7FFFu) != 0 && (w[h] & 0x8000u) == 0)) v[g * 8 + 2 * h] = 0.f;
-    if (!((w[h] & 0x7FFF0000u) != 0 && (w[h] & 0x80000000u) == 0)) v[g * 8 + 2 * h + 1] = 0.f;
-  }
-}
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c_inner, int c_outer) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -91,6 +81,64 @@ __device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t v, uint32_t h) {
   return r;
 }
 
+// TMEM -> registers, 64 consecutive fp32 columns of this thread's lane
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// One epilogue block: W accumulator columns of one row -> (+bias) -> ReLU | ReLU-backward mask | none
+// -> bf16 -> W/8 16-byte chunks of the row in the SWIZZLE_128B operand layout.
+template <int W, bool kMasked>
+__device__ __forceinline__ void epi_block(float (&v)[W], const float *bias, int act, const uint4 (&mk)[8],
+                                          uint8_t *srow, int ch0, int r7) {
+  if (bias != nullptr) {
+#pragma unroll
+    for (int g = 0; g < W / 4; ++g) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias) + g);
+      v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+    }
+  }
+  uint32_t pk[W / 2];
+  if (act == 1) {
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) pk[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  }
+  if (kMasked && act == 4) {
+#pragma unroll
+    for (int g = 0; g < W / 8; ++g) {
+      pk[4 * g] = relu_mask_bf16x2(pk[4 * g], mk[g].x);
+      pk[4 * g + 1] = relu_mask_bf16x2(pk[4 * g + 1], mk[g].y);
+      pk[4 * g + 2] = relu_mask_bf16x2(pk[4 * g + 2], mk[g].z);
+      pk[4 * g + 3] = relu_mask_bf16x2(pk[4 * g + 3], mk[g].w);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < W / 8; ++g)
+    *reinterpret_cast<uint4 *>(srow + (((ch0 + g) ^ r7) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+}
+
 template <bool kMasked>
 __global__ void __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -116,8 +164,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 8);
-      mbar_init(acc_full + t, 1); mbar_init(head_done + t, 8);
+      mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 16);
+      mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_x);
@@ -200,129 +248,122 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (2 x 8 warps)
-    // warps 2..9 own tile A, warps 10..17 tile B; within a tile: TMEM lane quadrant q x column half
-    const int t = (warp - 2) >> 3;
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    // Each warp drains one (TMEM lane quadrant q) x (quarter of the columns) block of the accumulator
+    // with ONE tcgen05.ld (x64 for 256-wide layers), first for tile A then for tile B.
     const int q = warp & 3;
-    const int hsel = ((warp - 2) >> 2) & 1;
+    const int cq = (warp - 2) >> 2;
     const int r_in = q * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
-    uint32_t n_full = 0;
+    uint32_t n_full[2] = {0, 0};
     bool store_pending = false;
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const long long tile = 2 * pair + t;
-      const long long row = tile * 128 + r_in;
       for (int l = 0; l < L; ++l) {
         const bool last = (l == L - 1);
         const bool is_head = last && a.head != 0;
-        const int Nl = a.N[l], half = Nl >> 1, c_begin = hsel * half;
-        const float *bias = a.bias ? a.bias + a.row0[l] : nullptr;
-        // ReLU-backward mask rows come straight from HBM: start the first chunk's loads before
-        // blocking on the accumulator, then stay one chunk ahead
-        const __nv_bfloat16 *mrow = nullptr;
-        uint4 mk[4] = {};
-        if (kMasked && a.act[l] == 4 && tile < n_tiles) {
-          mrow = a.mask + ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl;
+        const int Nl = a.N[l], quarter = Nl >> 2, c0 = cq * quarter;
+        const int act_l = a.act[l];
+        const float *bias = a.bias ? a.bias + a.row0[l] + c0 : nullptr;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c_begin) + g);
-        }
-        mbar_wait(acc_full + t, n_full & 1);
-        ++n_full;
-        tc_fence_after();
-        if (!is_head) {
-          // this warp's TMA store of the previous layer has finished READING the region overwritten below
-          if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
-          const bool relu = a.act[l] == 1;
-          for (int c0 = c_begin; c0 < c_begin + half; c0 += 32) {
-            float v[32];
-            tmem_ld32(taddr + c0, v);
-            if (bias != nullptr) {
+        for (int t = 0; t < 2; ++t) {
+          const long long tile = 2 * pair + t;
+          const long long row = tile * 128 + r_in;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+          uint8_t *act_t = smem + t * kActBytes;
+          // ReLU-backward mask row (straight from HBM): issue the loads before blocking on the accumulator
+          uint4 mk[8] = {};
+          if (kMasked && act_l == 4 && tile < n_tiles) {
+            const uint4 *mp = reinterpret_cast<const uint4 *>(a.mask + ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl + c0);
+            if (quarter == 64) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0) + g);
-                v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
-              }
-            }
-            uint32_t pk[16];
-            if (relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+              for (int g = 0; g < 8; ++g) mk[g] = __ldg(mp + g);
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              for (int g = 0; g < 4; ++g) mk[g] = __ldg(mp + g);
             }
-            if (kMasked && a.act[l] == 4) {
-              const uint4 cur[4] = {mk[0], mk[1], mk[2], mk[3]};
-              if (mrow != nullptr && c0 + 32 < c_begin + half) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) mk[g] = __ldg(reinterpret_cast<const uint4 *>(mrow + c0 + 32) + g);
-              }
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                pk[4 * g] = relu_mask_bf16x2(pk[4 * g], cur[g].x);
-                pk[4 * g + 1] = relu_mask_bf16x2(pk[4 * g + 1], cur[g].y);
-                pk[4 * g + 2] = relu_mask_bf16x2(pk[4 * g + 2], cur[g].z);
-                pk[4 * g + 3] = relu_mask_bf16x2(pk[4 * g + 3], cur[g].w);
-              }
+          }
+          mbar_wait(acc_full + t, n_full[t] & 1);
+          ++n_full[t];
+          tc_fence_after();
+          if (!is_head) {
+            // the TMA store this warp issued from act[t] one layer ago has finished READING the block that is
+            // overwritten below (the store issued for the other tile a moment ago may still be in flight)
+            // 128-wide layers: two warps (cq, cq^1) share one 64-column TMA-store box -> pair barriers
+            const bool paired = a.save && quarter == 32;
+            const uint32_t pair_bar = 1u + (uint32_t)(q * 2 + (cq >> 1));
+            if (store_pending) {
+              if (lane == 0 && (!paired || (cq & 1) == 0)) bulk_wait_read1();
+              __syncwarp();
+              if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             }
-            uint8_t *slab = act[t] + (c0 >> 6) * kActSlab + r_in * 128;
+            uint8_t *srow = act_t + (c0 >> 6) * kActSlab + r_in * 128;
             const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4 *>(slab + (((ch0 + g) ^ (r_in & 7)) << 4)) =
-                  make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
-          tc_fence_before();
-          fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
-          __syncwarp();
-          if (lane == 0) {
-            if (!last) mbar_arrive(act_ready + t);
-            if (a.save && tile < n_tiles) {
-              for (int c0 = c_begin; c0 < c_begin + half; c0 += 64)
-                tma_store_2d(&tmap_save, act[t] + (c0 >> 6) * kActSlab + q * 32 * 128, c0,
-                             (int)(l * a.save_rows + tile * 128 + q * 32));
-              bulk_commit();
-            }
-          }
-          store_pending = a.save != 0;
-          if (last) {                          // chain ends in a regular layer: tile t is finished once the
-            if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
-            store_pending = false;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(head_done + t);
-          }
-        } else {
-          // head: first out_cols columns, fp32, reference output activation
-          if (c_begin < a.out_cols) {
-            for (int c0 = c_begin; c0 < c_begin + half && c0 < a.out_cols; c0 += 32) {
+            if (quarter == 64) {
+              if constexpr (!kMasked) {
+                float v[64];
+                tmem_ld64(taddr + c0, v);
+                epi_block<64, false>(v, bias, act_l, mk, srow, ch0, r_in & 7);
+              } else {                         // masked variant: two 32-column halves keep the register count down
+                const uint4 mk_hi[8] = {mk[4], mk[5], mk[6], mk[7], mk[4], mk[5], mk[6], mk[7]};
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                epi_block<32, true>(v, bias, act_l, mk, srow, ch0, r_in & 7);
+                tmem_ld32(taddr + c0 + 32, v);
+                epi_block<32, true>(v, bias ? bias + 32 : nullptr, act_l, mk_hi, srow, ch0 + 4, r_in & 7);
+              }
+            } else {
               float v[32];
               tmem_ld32(taddr + c0, v);
+              epi_block<32, kMasked>(v, bias, act_l, mk, srow, ch0, r_in & 7);
+            }
+            tc_fence_before();
+            fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
+            __syncwarp();
+            if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            if (lane == 0) {
+              if (!last) mbar_arrive(act_ready + t);
+              if (a.save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
+                tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
+                             (int)(l * a.save_rows + tile * 128 + q * 32));
+                bulk_commit();
+              }
+            }
+            store_pending = a.save != 0;
+            if (last) {                          // chain ends in a regular layer: tile t is finished once the
+              if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
+              __syncwarp();
+              if (lane == 0) mbar_arrive(head_done + t);
+            }
+          } else {
+            // head: first out_cols (<= 16) columns, fp32, reference output activation; quarter 0 only
+            if (cq == 0) {
+              float v[16];
+              tmem_ld16(taddr, v);
               if (row < a.P) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (c0 + j < a.out_cols) {
-                    float x = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
-                    const int act = a.act[l];
-                    if (act == 1) x = fmaxf(x, 0.f);
-                    else if (act == 3 || (act == 2 && c0 + j < 3)) x = fm_sigmoid(x);
+                for (int j = 0; j < 16; ++j) {
+                  if (j < a.out_cols) {
+                    float x = v[j] + (a.bias ? __ldg(a.bias + a.row0[l] + j) : 0.f);
+                    if (act_l == 1) x = fmaxf(x, 0.f);
+                    else if (act_l == 3 || (act_l == 2 && j < 3)) x = fm_sigmoid(x);
                     v[j] = x;
                   }
                 }
-                if (a.out_cols == 4 && c0 == 0) {
+                if (a.out_cols == 4) {
                   *reinterpret_cast<float4 *>(a.out + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (c0 + j < a.out_cols) a.out[row * a.out_cols + c0 + j] = v[j];
+                  for (int j = 0; j < 16; ++j)
+                    if (j < a.out_cols) a.out[row * a.out_cols + j] = v[j];
                 }
               }
             }
+            tc_fence_before();
+            if (store_pending && lane == 0) bulk_wait_read0();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(head_done + t);
           }
-          tc_fence_before();
-          if (store_pending) { if (lane == 0) bulk_wait_read0(); store_pending = false; }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(head_done + t);
         }
+        if (last) store_pending = false;
       }
     }
     if (lane == 0) bulk_wait0();               // all saved activations are in global memory
