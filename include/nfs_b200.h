@@ -42,6 +42,9 @@ const char *nfs_last_error_string(void);
 /* Number of kernels this library has launched since load (per process);
  * bench.py reports the delta over its timed region as gpu_launches. */
 uint64_t    nfs_launch_count(void);
+/* Developer bisection switches for the fused MLP kernel (skip epilogue / weight reloads / MMAs);
+ * results are wrong while non-zero.  0 = production behaviour. */
+void        nfs_set_debug_flags(int32_t flags);
 
 /* ------------------------------------------------------------------------- *
  * K1 — alpha compositing (volume rendering)

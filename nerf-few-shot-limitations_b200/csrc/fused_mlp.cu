@@ -49,6 +49,7 @@ struct FusedArgs {
   const __nv_bfloat16 *mask;           // act 4: [n, mask_rows, N] bf16, result *= [mask[mask_idx[l]][row][col] > 0]
   long long mask_rows;
   int mask_idx[kFmMaxLayers];
+  int dbg;                             // developer bisection switches (nfs_set_debug_flags), 0 in production
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c_inner, int c_outer) {
@@ -198,6 +199,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const int ks = a.K[l] >> 6, nb = a.N[l] >> 6;
           for (int s = 0; s < ks; ++s, ++wit) {
             const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
+            if ((a.dbg & 2) && wit >= kWStages) continue;
             mbar_wait(w_empty + stage, ph ^ 1);
             mbar_expect_tx(w_full + stage, (uint32_t)(a.N[l] * 128));
             for (int b = 0; b < nb; ++b)
@@ -216,7 +218,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const uint32_t idesc = umma_idesc_bf16(128, a.N[l], 0, 0);
           for (int s = 0; s < ks; ++s, ++wit) {
             const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
-            mbar_wait(w_full + stage, ph);
+            if (!((a.dbg & 2) && wit >= kWStages)) mbar_wait(w_full + stage, ph);
             tc_fence_after();
             const uint32_t wa = smem_u32(wring + stage * kWStage);
 #pragma unroll
@@ -235,7 +237,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, umma_desc_sw128(xa + k * 32, 16, 1024), umma_desc_sw128(wa + k * 32, 16, 1024), idesc,
+                if (!(a.dbg & 4)) umma_bf16(d_tmem, umma_desc_sw128(xa + k * 32, 16, 1024), umma_desc_sw128(wa + k * 32, 16, 1024), idesc,
                           (uint32_t)((s | k) != 0));
               if (s == ks - 1) {
                 umma_commit(acc_full + t);
@@ -297,7 +299,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             uint8_t *srow = act_t + (c0 >> 6) * kActSlab + r_in * 128;
             const int ch0 = (c0 & 63) >> 3;
-            if (quarter == 64) {
+            if (a.dbg & 1) {
+              // bisection: no TMEM drain, no math, no smem writes
+            } else if (quarter == 64) {
               if constexpr (!kMasked) {
                 float v[64];
                 tmem_ld64(taddr + c0, v);
@@ -382,6 +386,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
 using namespace nfs;
 
+static int g_fm_debug = 0;
+extern "C" void nfs_set_debug_flags(int32_t flags) { g_fm_debug = flags; }
+
 // Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
 // default only in their row count (64 resp. 32).
 extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
@@ -399,6 +406,7 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   a.P = n_points; a.n_layers = n_layers; a.bias = bias_stack; a.out = out_f32; a.out_cols = out_cols;
   a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
   a.head = out_f32 != nullptr;
+  a.dbg = g_fm_debug;
   a.mask = (const __nv_bfloat16 *)mask_bf16; a.mask_rows = mask_rows_per_layer;
   for (int l = 0; l < n_layers; ++l) {
     a.K[l] = k_dims[l]; a.N[l] = n_dims[l]; a.act[l] = acts[l]; a.row0[l] = row0[l];
