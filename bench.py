@@ -17,9 +17,7 @@ import argparse
 import json
 import math
 import os
-import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -47,12 +45,35 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def lego_rays(n_rays, H=800, W=800, seed=0):
+    """Synthetic Blender-lego-shaped rays: one 800x800 pinhole view,
+    camera_angle_x = 0.6911112, camera on the r = 4.0311 sphere at phi = -30 deg looking at the
+    origin, directions NOT normalised (models/ray_sampler.py:18-30 convention); n_rays pixels
+    drawn with replacement.  Input synthesis only (host side, outside every timed region)."""
+    g = torch.Generator().manual_seed(seed)
+    focal = 0.5 * W / math.tan(0.5 * 0.6911112)
+    th = math.radians(float(torch.rand((), generator=g) * 360.0 - 180.0))
+    ph = math.radians(-30.0)
+    t = torch.tensor([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 4.0311], [0, 0, 0, 1]], dtype=torch.float32)
+    rp = torch.tensor([[1, 0, 0, 0], [0, math.cos(ph), -math.sin(ph), 0],
+                       [0, math.sin(ph), math.cos(ph), 0], [0, 0, 0, 1]], dtype=torch.float32)
+    rt = torch.tensor([[math.cos(th), 0, -math.sin(th), 0], [0, 1, 0, 0],
+                       [math.sin(th), 0, math.cos(th), 0], [0, 0, 0, 1]], dtype=torch.float32)
+    flip = torch.tensor([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=torch.float32)
+    c2w = flip @ rt @ rp @ t
+    pick = torch.randint(0, H * W, (n_rays,), generator=g)
+    i = (pick % W).float()
+    j = (pick // W).float()
+    dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[:, None, :] * c2w[:3, :3], -1)
+    return c2w[:3, 3].expand(rays_d.shape).contiguous(), rays_d.contiguous()
+
+
 def make_inputs(n_rays, n_samples, seed, device):
     """Synthetic lego-shaped batch (SURVEY.md section 8d cfg 2): rgb~U[0,1), density~10*N(0,1),
     z = one stratified draw in [2,6], unnormalised rays_d from an 800x800 Blender camera."""
-    from oracle import nerf_oracle as O     # synthetic-ray generator only (inputs, not compute)
     g = torch.Generator().manual_seed(seed)
-    _, rays_d = O.lego_rays(n_rays, seed=seed)
+    _, rays_d = lego_rays(n_rays, seed=seed)
     rgb = torch.rand(n_rays, n_samples, 3, generator=g)
     density = torch.randn(n_rays, n_samples, 1, generator=g) * 10.0
     t = torch.linspace(0.0, 1.0, n_samples)
@@ -69,52 +90,63 @@ def make_inputs(n_rays, n_samples, seed, device):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled every 50 ms by an NVML thread while the timed region
+    runs (nvidia-smi -lms to a file loses its buffered output when it is terminated)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.proc, self.path = None, None
+        self.samples, self.reasons, self.mx, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        self.thread = None
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.h = h
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:      # no NVML: the clocks record says so instead of inventing numbers
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((sm, util))
+                for nm, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.05)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
-                    continue
-                try:
-                    sm.append(float(f[0])); mx.append(float(f[1]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
+        out = {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        if self.err:
+            out["error"] = self.err
+        sm = sorted(s for s, _ in self.samples)
         if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
-        out["reasons"] = sorted(reasons)
+            out.update(sm_mhz=sm[len(sm) // 2], samples=len(sm))
+        out["reasons"] = sorted(self.reasons)
         return out
 
 

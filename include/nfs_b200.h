@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NFS_B200_ABI_VERSION 1
+#define NFS_B200_ABI_VERSION 2
 
 /* negative return codes (argument errors) */
 #define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
@@ -151,15 +151,18 @@ int nfs_sample_hierarchical(const float *rays_o, const float *rays_d,
  *   X [P,K], W [N,K] bf16 row-major (K contiguous; K % 64 == 0, K <= 320;
  *   N % 32 == 0, N <= 256 - operands are zero-padded to these shapes), bias fp32
  *   |NULL, fp32 accumulation in TMEM.  act: 0 none, 1 relu, 2 sigmoid on columns
- *   0..2 only ([rgb|sigma] head of nerf_model.py:22-24), 3 sigmoid.
+ *   0..2 only ([rgb|sigma] head of nerf_model.py:22-24), 3 sigmoid, 5 softmax over columns 0..1
+ *   (the 2-way gate of dino_feature_model.py:165-170,188).
  *   relu_mask_src (bf16 [P,N])|NULL: result *= [relu_mask_src > 0] (ReLU backward
  *   fused into the dgrad epilogue; call with W^T as the weight).
- *   Outputs: y_bf16 [P,N] and/or y_f32 [P,out_cols] (first out_cols columns).
+ *   Outputs: y_bf16 [P,N] with row pitch y_pitch elements (0 = N; a wider pitch writes a column
+ *   block of a concatenated operand, e.g. [features | encoded directions] of nerf_mlp.py:83)
+ *   and/or y_f32 [P,out_cols] (first out_cols columns).
  * ------------------------------------------------------------------------- */
 int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const float *bias,
                     const void *relu_mask_src,
                     int64_t n_points, int32_t k_dim, int32_t n_dim, int32_t act,
-                    int32_t out_cols, void *y_bf16, float *y_f32, void *stream);
+                    int32_t out_cols, void *y_bf16, int64_t y_pitch, float *y_f32, void *stream);
 
 /* nfs_wgrad_bf16: D[m,n] += sum_p U[p,m] * V[p,n]   (fp32 red.add into dw[m*ld_m + n*ld_n]),
  *   the wgrad GEMM of Linear backward: dW[n_out,k_in] = sum_p dY[p,n_out] X[p,k_in]
@@ -206,13 +209,23 @@ int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
  *   (positional_encoding.py:27-33 / nerf_mlp.py:24-33, the torch.cat with DINO features of
  *   dino_feature_model.py:182,195 and the fp32->bf16 cast feeding nn.Linear):
  *   out row (bf16, k_pad entries) = [ enc(x) * scale_enc | extra * scale_extra | 0 ... ]
- *   enc(x) = [x, sin(x f_0), cos(x f_0), ...] (D*(2L+1)); extra (P,E)|NULL; scale_* (P)|NULL
- *   are the per-point attention gates of dino_feature_model.py:191-192.
+ *   enc(x) = [x, sin(x f_0), cos(x f_0), ...] (D*(2L+1)); extra (P,E)|NULL; scale_*|NULL are
+ *   the per-point attention gates of dino_feature_model.py:191-192, read at scale_*[p*scale_stride]
+ *   (stride 2 = the two columns of the (P,2) softmax output).  Rows are written at
+ *   out + p*out_pitch (0 = k_pad), so the block can be a column range of a wider operand.
  * ------------------------------------------------------------------------- */
 int nfs_posenc_bf16(const float *x, const float *freqs, const float *extra,
-                    const float *scale_enc, const float *scale_extra,
+                    const float *scale_enc, const float *scale_extra, int32_t scale_stride,
                     int64_t n_points, int32_t dim, int32_t n_freqs, int32_t extra_dim,
-                    int32_t k_pad, void *out_bf16, void *stream);
+                    int32_t k_pad, int64_t out_pitch, void *out_bf16, void *stream);
+
+/* Backward of that gate: dc_bf16 (P rows, pitch dc_pitch) = dL/dc' for c' = [enc(x) g0 | extra g1],
+ * gate (P,2) = softmax output -> dlogits_bf16 [P,n_pad] (columns 0..1, rest zero):
+ *   dg0 = <dc'[:enc_w], enc(x)>, dg1 = <dc'[enc_w:], extra>, dlogit_i = g_i (dg_i - sum_k g_k dg_k)
+ *   (autograd of dino_feature_model.py:188-195; enc(x) is recomputed). */
+int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float *extra, const float *gate,
+                      const void *dc_bf16, int64_t dc_pitch, int64_t n_points, int32_t dim, int32_t n_freqs,
+                      int32_t extra_dim, int32_t n_pad, void *dlogits_bf16, void *stream);
 
 /* fp32 master weight [n_dim,k_dim] -> block (row0,col0) of the zero-padded bf16 operands
  * w_bf16 [n_pad,k_pad] (forward) and wt_bf16 [k_pad,n_pad] (dgrad); either may be NULL.
@@ -223,9 +236,9 @@ int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n
 
 /* dY (bf16 [P,n_pad], zero padded) = g_out * act'(out) for the fp32 network outputs
  * out, g_out [P,n_cols]: act 0 identity, 1 relu, 2 sigmoid on columns 0..2 (nerf_model.py:22-24),
- * 3 sigmoid (nerf_mlp.py:80).  First step of the MLP backward. */
+ * 3 sigmoid (nerf_mlp.py:80).  Rows at dy + p*dy_pitch (0 = n_pad).  First step of the MLP backward. */
 int nfs_act_grad_bf16(const float *out, const float *g_out, int64_t n_points, int32_t n_cols,
-                      int32_t act, int32_t n_pad, void *dy_bf16, void *stream);
+                      int32_t act, int32_t n_pad, int64_t dy_pitch, void *dy_bf16, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused Adam / AdamW step over one flat fp32 buffer

@@ -34,6 +34,7 @@ struct LinearArgs {
   __nv_bfloat16 *y_bf16;
   float *y_f32;
   long long P;
+  long long y_pitch;   // row pitch (elements) of y_bf16
   int K, N, act, out_cols;
   int n_stages, tmem_cols;
 };
@@ -144,6 +145,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
         } else if (a.act == 3) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+        } else if (a.act == 5) {                  // 2-way softmax gate  dino_feature_model.py:169,188
+          if (c0 == 0) {
+            const float mx = fmaxf(v[0], v[1]);
+            const float e0 = expf(v[0] - mx), e1 = expf(v[1] - mx);
+            const float inv = 1.0f / (e0 + e1);
+            v[0] = e0 * inv; v[1] = e1 * inv;
+          }
         }
         if (ok) {
           if (a.mask_src != nullptr) {            // ReLU backward: pass where the saved activation is > 0
@@ -161,7 +169,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             }
           }
           if (a.y_bf16 != nullptr) {
-            uint4 *yp = reinterpret_cast<uint4 *>(a.y_bf16 + row * N + c0);
+            uint4 *yp = reinterpret_cast<uint4 *>(a.y_bf16 + row * a.y_pitch + c0);
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               yp[g] = make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
@@ -206,14 +214,16 @@ using namespace nfs;
 
 extern "C" int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const float *bias, const void *relu_mask_src,
                                int64_t n_points, int32_t k_dim, int32_t n_dim, int32_t act, int32_t out_cols,
-                               void *y_bf16, float *y_f32, void *stream) {
+                               void *y_bf16, int64_t y_pitch, float *y_f32, void *stream) {
   const char *fn = "nfs_linear_bf16";
   if (n_points < 0 || k_dim <= 0 || n_dim <= 0) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
   if (n_points == 0) return 0;
   if (!x_bf16 || !w_bf16 || (!y_bf16 && !y_f32)) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
   if (k_dim % 64 != 0 || n_dim % 32 != 0 || n_dim > 256 || k_dim > 320)
     return fail_arg(fn, NFS_E_UNSUPPORTED, "need K % 64 == 0, K <= 320, N % 32 == 0, N <= 256 (pad the operands)");
-  if (act < 0 || act > 3) return fail_arg(fn, NFS_E_BADARG, "act must be 0..3");
+  if (act < 0 || act > 5 || act == 4) return fail_arg(fn, NFS_E_BADARG, "act must be 0..3 or 5");
+  if (y_pitch == 0) y_pitch = n_dim;
+  if (y_pitch < n_dim || (y_pitch & 7)) return fail_arg(fn, NFS_E_BADARG, "y_pitch must be >= N and a multiple of 8");
   if (y_f32 && (out_cols <= 0 || out_cols > n_dim)) return fail_arg(fn, NFS_E_BADARG, "out_cols must be in [1, N]");
   if ((y_bf16 && !aligned16(y_bf16)) || (relu_mask_src && !aligned16(relu_mask_src)))
     return fail_arg(fn, NFS_E_ALIGN, "bf16 tensors must be 16-byte aligned");
@@ -227,7 +237,7 @@ extern "C" int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const flo
   LinearArgs a{};
   a.bias = bias; a.mask_src = (const __nv_bfloat16 *)relu_mask_src;
   a.y_bf16 = (__nv_bfloat16 *)y_bf16; a.y_f32 = y_f32;
-  a.P = n_points; a.K = k_dim; a.N = n_dim; a.act = act; a.out_cols = out_cols;
+  a.P = n_points; a.y_pitch = y_pitch; a.K = k_dim; a.N = n_dim; a.act = act; a.out_cols = out_cols;
   const int w_bytes = (k_dim / 64) * n_dim * 128;
   const int budget = 227 * 1024 - 1024 - 256 - w_bytes;
   int stages = budget / kSlabBytesX;

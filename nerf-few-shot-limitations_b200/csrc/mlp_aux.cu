@@ -20,8 +20,9 @@ constexpr int kEncTile = 64;   // points per CTA
 
 __global__ void __launch_bounds__(kEncThreads)
 posenc_bf16_kernel(const float *__restrict__ x, const float *__restrict__ freqs, const float *__restrict__ extra,
-                   const float *__restrict__ scale_enc, const float *__restrict__ scale_extra, long long n_points,
-                   int D, int L, int E, int k_pad, __nv_bfloat16 *__restrict__ out) {
+                   const float *__restrict__ scale_enc, const float *__restrict__ scale_extra, int scale_stride,
+                   long long n_points, int D, int L, int E, int k_pad, long long out_pitch,
+                   __nv_bfloat16 *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(s_raw);     // [kEncTile][k_pad]
   const long long p0 = (long long)blockIdx.x * kEncTile;
@@ -39,26 +40,29 @@ posenc_bf16_kernel(const float *__restrict__ x, const float *__restrict__ freqs,
     const float arg = __fmul_rn(__ldg(x + (p0 + p) * D + d), __ldg(freqs + k));
     float s, c;
     sincosf(arg, &s, &c);
-    const float g = scale_enc ? __ldg(scale_enc + p0 + p) : 1.f;
+    const float g = scale_enc ? __ldg(scale_enc + (p0 + p) * scale_stride) : 1.f;
     __nv_bfloat16 *row = tile + p * k_pad + D + 2 * k * D;
     row[d] = __float2bfloat16_rn(s * g);
     row[D + d] = __float2bfloat16_rn(c * g);
   }
   for (int t = threadIdx.x; t < np * D; t += kEncThreads) {
     const int p = t / D, d = t - p * D;
-    const float g = scale_enc ? __ldg(scale_enc + p0 + p) : 1.f;
+    const float g = scale_enc ? __ldg(scale_enc + (p0 + p) * scale_stride) : 1.f;
     tile[p * k_pad + d] = __float2bfloat16_rn(__ldg(x + (p0 + p) * D + d) * g);
   }
   if (extra != nullptr)
     for (int t = threadIdx.x; t < np * E; t += kEncThreads) {
       const int p = t / E, j = t - p * E;
-      const float g = scale_extra ? __ldg(scale_extra + p0 + p) : 1.f;
+      const float g = scale_extra ? __ldg(scale_extra + (p0 + p) * scale_stride) : 1.f;
       tile[p * k_pad + enc_w + j] = __float2bfloat16_rn(__ldg(extra + (p0 + p) * E + j) * g);
     }
   __syncthreads();
-  uint4 *dst = reinterpret_cast<uint4 *>(out + p0 * k_pad);
   const uint4 *src = reinterpret_cast<const uint4 *>(tile);
-  for (int t = threadIdx.x; t < np * k_pad / 8; t += kEncThreads) dst[t] = src[t];
+  const int chunks = k_pad / 8;
+  for (int t = threadIdx.x; t < np * chunks; t += kEncThreads) {
+    const int p = t / chunks, c = t - p * chunks;
+    reinterpret_cast<uint4 *>(out + (p0 + p) * out_pitch)[c] = src[t];
+  }
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -80,7 +84,7 @@ pack_linear_kernel(const float *__restrict__ w, int N, int K, int n_pad, int k_p
 //   act 0 identity, 1 relu (out > 0), 2 sigmoid on the first 3 columns, 3 sigmoid on all.
 __global__ void __launch_bounds__(256)
 act_grad_kernel(const float *__restrict__ out, const float *__restrict__ g_out, long long n_points, int C, int act,
-                int n_pad, __nv_bfloat16 *__restrict__ dy) {
+                int n_pad, long long dy_pitch, __nv_bfloat16 *__restrict__ dy) {
   const int chunks = n_pad / 8;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_points * chunks) return;
@@ -100,9 +104,44 @@ act_grad_kernel(const float *__restrict__ out, const float *__restrict__ g_out, 
     }
     v[j] = r;
   }
-  *reinterpret_cast<uint4 *>(dy + p * n_pad + c0) =
+  *reinterpret_cast<uint4 *>(dy + p * dy_pitch + c0) =
       make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
                  tc::pack_bf16x2(v[6], v[7]));
+}
+
+// ------------------------------------------------------------------ gate backward
+// The fusion block re-weights its own input with a 2-way softmax gate (dino_feature_model.py:188-195):
+//   c' = [enc(x) * g0 | extra * g1],  g = softmax(logits).
+// Given dc' (bf16, from the dgrad GEMM of the first fusion layer) this produces the gradient of the
+// logits, bf16 [P,n_pad] zero padded (the operand of the next dgrad / wgrad GEMMs):
+//   dg0 = <dc'[0:enc_w], enc(x)>,  dg1 = <dc'[enc_w:enc_w+E], extra>,
+//   dlogit_i = g_i (dg_i - (g0 dg0 + g1 dg1)).
+// enc(x) is recomputed (sincosf), never stored.  One thread per point.
+__global__ void __launch_bounds__(128)
+gate_bwd_kernel(const float *__restrict__ x, const float *__restrict__ freqs, const float *__restrict__ extra,
+                const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dc, long long dc_pitch,
+                long long n_points, int D, int L, int E, int n_pad, __nv_bfloat16 *__restrict__ out) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  const __nv_bfloat16 *row = dc + p * dc_pitch;
+  float dg0 = 0.f, dg1 = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float xv = __ldg(x + p * D + d);
+    dg0 += __bfloat162float(row[d]) * xv;
+    for (int k = 0; k < L; ++k) {
+      float sn, cs;
+      sincosf(__fmul_rn(xv, __ldg(freqs + k)), &sn, &cs);
+      dg0 += __bfloat162float(row[D + 2 * k * D + d]) * sn + __bfloat162float(row[D + 2 * k * D + D + d]) * cs;
+    }
+  }
+  const int enc_w = D * (2 * L + 1);
+  for (int j = 0; j < E; ++j) dg1 += __bfloat162float(row[enc_w + j]) * __ldg(extra + p * E + j);
+  const float g0 = __ldg(gate + 2 * p), g1 = __ldg(gate + 2 * p + 1);
+  const float mean = g0 * dg0 + g1 * dg1;
+  __nv_bfloat16 *o = out + p * n_pad;
+  uint4 first = make_uint4(tc::pack_bf16x2(g0 * (dg0 - mean), g1 * (dg1 - mean)), 0, 0, 0);
+  reinterpret_cast<uint4 *>(o)[0] = first;
+  for (int c = 1; c < n_pad / 8; ++c) reinterpret_cast<uint4 *>(o)[c] = make_uint4(0, 0, 0, 0);
 }
 
 // ------------------------------------------------------------------ Adam / AdamW over a flat buffer
@@ -130,8 +169,9 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
 using namespace nfs;
 
 extern "C" int nfs_posenc_bf16(const float *x, const float *freqs, const float *extra, const float *scale_enc,
-                               const float *scale_extra, int64_t n_points, int32_t dim, int32_t n_freqs,
-                               int32_t extra_dim, int32_t k_pad, void *out_bf16, void *stream) {
+                               const float *scale_extra, int32_t scale_stride, int64_t n_points, int32_t dim,
+                               int32_t n_freqs, int32_t extra_dim, int32_t k_pad, int64_t out_pitch, void *out_bf16,
+                               void *stream) {
   const char *fn = "nfs_posenc_bf16";
   if (n_points < 0 || dim <= 0 || n_freqs < 0 || extra_dim < 0) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
   if (n_points == 0) return 0;
@@ -139,14 +179,17 @@ extern "C" int nfs_posenc_bf16(const float *x, const float *freqs, const float *
     return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
   const int w = dim * (2 * n_freqs + 1) + extra_dim;
   if (k_pad % 8 != 0 || k_pad < w) return fail_arg(fn, NFS_E_BADARG, "k_pad must be a multiple of 8 and >= the row width");
+  if (out_pitch == 0) out_pitch = k_pad;
+  if (out_pitch < k_pad || (out_pitch & 7)) return fail_arg(fn, NFS_E_BADARG, "out_pitch must be >= k_pad and a multiple of 8");
+  if (scale_stride <= 0) scale_stride = 1;
   if (!aligned16(out_bf16)) return fail_arg(fn, NFS_E_ALIGN, "out must be 16-byte aligned");
   const size_t smem = (size_t)kEncTile * k_pad * 2;
   if (smem > 48 * 1024) return fail_arg(fn, NFS_E_TOOLARGE, "k_pad too large");
   const long long blocks = (n_points + kEncTile - 1) / kEncTile;
   if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
   posenc_bf16_kernel<<<(unsigned)blocks, kEncThreads, smem, (cudaStream_t)stream>>>(
-      x, freqs, extra_dim > 0 ? extra : nullptr, scale_enc, scale_extra, n_points, dim, n_freqs, extra_dim, k_pad,
-      (__nv_bfloat16 *)out_bf16);
+      x, freqs, extra_dim > 0 ? extra : nullptr, scale_enc, scale_extra, scale_stride, n_points, dim, n_freqs,
+      extra_dim, k_pad, out_pitch, (__nv_bfloat16 *)out_bf16);
   return check_launch(fn);
 }
 
@@ -163,17 +206,39 @@ extern "C" int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim
 }
 
 extern "C" int nfs_act_grad_bf16(const float *out, const float *g_out, int64_t n_points, int32_t n_cols, int32_t act,
-                                 int32_t n_pad, void *dy_bf16, void *stream) {
+                                 int32_t n_pad, int64_t dy_pitch, void *dy_bf16, void *stream) {
   const char *fn = "nfs_act_grad_bf16";
   if (n_points < 0 || n_cols <= 0 || n_pad % 8 != 0 || n_pad < n_cols || act < 0 || act > 3)
     return fail_arg(fn, NFS_E_BADARG, "bad sizes");
   if (n_points == 0) return 0;
   if (!out || !g_out || !dy_bf16) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  if (dy_pitch == 0) dy_pitch = n_pad;
+  if (dy_pitch < n_pad || (dy_pitch & 7) || !aligned16(dy_bf16))
+    return fail_arg(fn, NFS_E_BADARG, "dy_pitch must be >= n_pad, a multiple of 8, and dy 16-byte aligned");
   const long long threads = n_points * (n_pad / 8);
   const long long blocks = (threads + 255) / 256;
   if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
   act_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, g_out, n_points, n_cols, act, n_pad,
-                                                                     (__nv_bfloat16 *)dy_bf16);
+                                                                     dy_pitch, (__nv_bfloat16 *)dy_bf16);
+  return check_launch(fn);
+}
+
+extern "C" int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float *extra, const float *gate,
+                                 const void *dc_bf16, int64_t dc_pitch, int64_t n_points, int32_t dim, int32_t n_freqs,
+                                 int32_t extra_dim, int32_t n_pad, void *dlogits_bf16, void *stream) {
+  const char *fn = "nfs_gate_bwd_bf16";
+  if (n_points < 0 || dim <= 0 || n_freqs < 0 || extra_dim < 0 || n_pad < 8 || (n_pad & 7))
+    return fail_arg(fn, NFS_E_BADARG, "bad sizes");
+  if (n_points == 0) return 0;
+  if (!x || !gate || !dc_bf16 || !dlogits_bf16 || (n_freqs > 0 && !freqs) || (extra_dim > 0 && !extra))
+    return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  if (dc_pitch < dim * (2 * n_freqs + 1) + extra_dim) return fail_arg(fn, NFS_E_BADARG, "dc_pitch smaller than the row");
+  if (!aligned16(dlogits_bf16)) return fail_arg(fn, NFS_E_ALIGN, "dlogits must be 16-byte aligned");
+  const long long blocks = (n_points + 127) / 128;
+  if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
+  gate_bwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+      x, freqs, extra, gate, (const __nv_bfloat16 *)dc_bf16, dc_pitch, n_points, dim, n_freqs, extra_dim, n_pad,
+      (__nv_bfloat16 *)dlogits_bf16);
   return check_launch(fn);
 }
 

@@ -84,30 +84,46 @@ class PackedLinear:
         return self
 
 
-def encode_operand(x, freqs, k_pad, extra=None, scale_enc=None, scale_extra=None):
-    """fp32 rows -> bf16 GEMM operand [P,k_pad] = [enc(x) | extra | 0] (nfs_posenc_bf16).
-    freqs=None copies x itself (already-encoded input)."""
+def encode_operand(x, freqs, k_pad, extra=None, gate=None, out=None):
+    """fp32 rows -> bf16 GEMM operand [P,k_pad] = [enc(x) * g0 | extra * g1 | 0] (nfs_posenc_bf16).
+    freqs=None copies x itself (already-encoded input); gate (P,2) fp32 = the softmax gate of
+    dino_feature_model.py:188-192 (None = 1).  `out`: a bf16 [P,k_pad] column block of a wider tensor."""
     x = ops._f32c(x)
     P, D = x.shape
     L = 0 if freqs is None else int(freqs.numel())
     E = 0 if extra is None else extra.shape[-1]
-    out = torch.empty((P, k_pad), device=x.device, dtype=torch.bfloat16)
+    pitch = 0
+    if out is None:
+        out = torch.empty((P, k_pad), device=x.device, dtype=torch.bfloat16)
+    else:
+        if out.dtype != torch.bfloat16 or out.shape != (P, k_pad) or out.stride(1) != 1:
+            raise RuntimeError("encode_operand: out must be a bf16 [P,k_pad] block with contiguous columns")
+        pitch = out.stride(0)
     if P:
         fr = None if freqs is None else freqs.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        g0 = g1 = None
+        if gate is not None:
+            gate = ops._f32c(gate)
+            g0, g1 = ptr(gate), ctypes.c_void_p(gate.data_ptr() + 4)
         with torch.cuda.device(x.device):
-            _lib.call("nfs_posenc_bf16", ptr(x), ptr(fr), ptr(ops._f32c(extra)), ptr(ops._f32c(scale_enc)),
-                      ptr(ops._f32c(scale_extra)), P, D, L, E, k_pad, ptr(out), _stream())
+            _lib.call("nfs_posenc_bf16", ptr(x), ptr(fr), ptr(ops._f32c(extra)) if E else None, g0, g1, 2, P, D, L, E,
+                      k_pad, int(pitch), ptr(out), _stream())
     return out
 
 
-def act_grad(out, g_out, act, n_pad):
+def act_grad(out, g_out, act, n_pad, dst=None):
+    """dY bf16 [P,n_pad] = g_out * act'(out) (nfs_act_grad_bf16); `dst`: column block of a wider tensor."""
     out, g_out = ops._f32c(out), ops._f32c(g_out)
     P, C = out.shape
-    dy = torch.empty((P, n_pad), device=out.device, dtype=torch.bfloat16)
+    pitch = 0
+    if dst is None:
+        dst = torch.empty((P, n_pad), device=out.device, dtype=torch.bfloat16)
+    else:
+        pitch = dst.stride(0)
     if P:
         with torch.cuda.device(out.device):
-            _lib.call("nfs_act_grad_bf16", ptr(out), ptr(g_out), P, C, int(act), n_pad, ptr(dy), _stream())
-    return dy
+            _lib.call("nfs_act_grad_bf16", ptr(out), ptr(g_out), P, C, int(act), n_pad, int(pitch), ptr(dst), _stream())
+    return dst
 
 
 # --------------------------------------------------------------------------------- G1

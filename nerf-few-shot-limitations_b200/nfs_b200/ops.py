@@ -253,10 +253,12 @@ def _bf16c(t):
     return t.contiguous()
 
 
-def linear_bf16(x, w, bias=None, act=0, relu_mask_src=None, out_bf16=True, out_f32_cols=0):
+def linear_bf16(x, w, bias=None, act=0, relu_mask_src=None, out_bf16=True, out_f32_cols=0, out=None):
     """Y = act(X W^T + b) on tcgen05 (nfs_linear_bf16).  x [P,K] bf16, w [N,K] bf16 (K % 64 == 0,
-    N % 32 == 0), bias fp32 [N].  Returns (y_bf16 [P,N] | None, y_f32 [P,out_f32_cols] | None)."""
-    _need_cuda("linear_bf16", x, w, bias, relu_mask_src)
+    N % 32 == 0), bias fp32 [N].  `out`: a bf16 [P,N] column block (stride(1) == 1, any row pitch) of a
+    wider tensor that receives the result instead of a fresh tensor.
+    Returns (y_bf16 [P,N] | None, y_f32 [P,out_f32_cols] | None)."""
+    _need_cuda("linear_bf16", x, w, bias, relu_mask_src, out)
     x, w, relu_mask_src = _bf16c(x), _bf16c(w), _bf16c(relu_mask_src)
     P, K = x.shape
     N = w.shape[0]
@@ -265,12 +267,18 @@ def linear_bf16(x, w, bias=None, act=0, relu_mask_src=None, out_bf16=True, out_f
     if relu_mask_src is not None and relu_mask_src.shape != (P, N):
         raise RuntimeError("linear_bf16: relu_mask_src must be [P,N]")
     bias = _f32c(bias)
-    y16 = torch.empty((P, N), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    y16, pitch = None, 0
+    if out is not None:
+        if out.dtype != torch.bfloat16 or out.shape != (P, N) or out.stride(1) != 1:
+            raise RuntimeError("linear_bf16: out must be a bf16 [P,N] block with contiguous columns")
+        y16, pitch = out, out.stride(0)
+    elif out_bf16:
+        y16 = torch.empty((P, N), device=x.device, dtype=torch.bfloat16)
     y32 = torch.empty((P, out_f32_cols), device=x.device, dtype=torch.float32) if out_f32_cols else None
     if P:
         with torch.cuda.device(x.device):
             _lib.call("nfs_linear_bf16", ptr(x), ptr(w), ptr(bias), ptr(relu_mask_src), P, K, N, int(act),
-                      int(out_f32_cols), ptr(y16), ptr(y32), _stream())
+                      int(out_f32_cols), ptr(y16), int(pitch), ptr(y32), _stream())
     return y16, y32
 
 
