@@ -45,6 +45,9 @@ uint64_t    nfs_launch_count(void);
 /* Developer bisection switches for the fused MLP kernel (skip epilogue / weight reloads / MMAs);
  * results are wrong while non-zero.  0 = production behaviour. */
 void        nfs_set_debug_flags(int32_t flags);
+/* Developer timeline of the fused MLP kernel: buf = device buffer of 18*1024 uint64 (NULL = off); CTA 0 appends
+ * (clock64 << 16 | event << 12 | layer << 4 | tile) per warp, entry 0 of each warp's 1024 = count. */
+void        nfs_set_debug_trace(void *buf);
 
 /* ------------------------------------------------------------------------- *
  * K1 — alpha compositing (volume rendering)

@@ -50,6 +50,7 @@ struct FusedArgs {
   long long mask_rows;
   int mask_idx[kFmMaxLayers];
   int dbg;                             // developer bisection switches (nfs_set_debug_flags), 0 in production
+  unsigned long long *trace;           // developer timeline of CTA 0 (nfs_set_debug_trace), NULL in production
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c_inner, int c_outer) {
@@ -82,70 +83,78 @@ __device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t v, uint32_t h) {
   return r;
 }
 
-// TMEM -> registers, 64 consecutive fp32 columns of this thread's lane
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
-  uint32_t r[64];
+// TMEM -> registers, 16 consecutive fp32 columns of this thread's lane, WITHOUT waiting: the
+// registers are valid after the next tmem_ld_wait().  Lets the load of chunk i+1 fly while chunk i
+// is being processed.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
-        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
-        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
-        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
-        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One epilogue block: W accumulator columns of one row -> (+bias) -> ReLU | ReLU-backward mask | none
-// -> bf16 -> W/8 16-byte chunks of the row in the SWIZZLE_128B operand layout.
-template <int W, bool kMasked>
-__device__ __forceinline__ void epi_block(float (&v)[W], const float *bias, int act, const uint4 (&mk)[8],
-                                          uint8_t *srow, int ch0, int r7) {
-  if (bias != nullptr) {
+// One epilogue chunk: 16 accumulator columns of one row -> (+bias, read from shared memory: every
+// lane reads the same address = broadcast; packed fp32x2 adds) -> ReLU | ReLU-backward mask | none
+// -> bf16 -> two 16-byte chunks of the row in the SWIZZLE_128B operand layout.
+template <bool kMasked>
+__device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s, int act, uint4 mk0, uint4 mk1,
+                                          uint8_t *srow, int ch, int r7, int dbg) {
+  if (bias_s != nullptr && !(dbg & 8)) {
 #pragma unroll
-    for (int g = 0; g < W / 4; ++g) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias) + g);
-      v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+    for (int g = 0; g < 4; ++g) {
+      const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + 4 * g);
+      asm("{\n\t.reg .b64 a, b;\n\t"
+          "mov.b64 a, {%0, %1};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t"
+          "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%6, %7};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%2, %3}, a;\n\t}"
+          : "+r"(r[4 * g]), "+r"(r[4 * g + 1]), "+r"(r[4 * g + 2]), "+r"(r[4 * g + 3])
+          : "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w));
     }
   }
-  uint32_t pk[W / 2];
+  uint32_t pk[8];
   if (act == 1) {
 #pragma unroll
-    for (int j = 0; j < W / 2; ++j) pk[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
   } else {
 #pragma unroll
-    for (int j = 0; j < W / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
   }
   if (kMasked && act == 4) {
-#pragma unroll
-    for (int g = 0; g < W / 8; ++g) {
-      pk[4 * g] = relu_mask_bf16x2(pk[4 * g], mk[g].x);
-      pk[4 * g + 1] = relu_mask_bf16x2(pk[4 * g + 1], mk[g].y);
-      pk[4 * g + 2] = relu_mask_bf16x2(pk[4 * g + 2], mk[g].z);
-      pk[4 * g + 3] = relu_mask_bf16x2(pk[4 * g + 3], mk[g].w);
-    }
+    pk[0] = relu_mask_bf16x2(pk[0], mk0.x); pk[1] = relu_mask_bf16x2(pk[1], mk0.y);
+    pk[2] = relu_mask_bf16x2(pk[2], mk0.z); pk[3] = relu_mask_bf16x2(pk[3], mk0.w);
+    pk[4] = relu_mask_bf16x2(pk[4], mk1.x); pk[5] = relu_mask_bf16x2(pk[5], mk1.y);
+    pk[6] = relu_mask_bf16x2(pk[6], mk1.z); pk[7] = relu_mask_bf16x2(pk[7], mk1.w);
   }
+  if (dbg & 32) {                       // bisection: keep the values alive without the shared-memory stores
+    uint32_t x = 0;
 #pragma unroll
-  for (int g = 0; g < W / 8; ++g)
-    *reinterpret_cast<uint4 *>(srow + (((ch0 + g) ^ r7) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    for (int j = 0; j < 8; ++j) x ^= pk[j];
+    if (x == 0x9e3779b9u) *reinterpret_cast<uint32_t *>(srow) = x;
+    return;
+  }
+  *reinterpret_cast<uint4 *>(srow + ((ch ^ r7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4 *>(srow + (((ch + 1) ^ r7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
+
+// Developer timeline: CTA 0 appends (clock << 16 | code << 12 | layer << 4 | tile) per warp.
+#define NFS_TRACE(code, l, t)                                                                       \
+  do {                                                                                              \
+    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 1023) {                     \
+      a.trace[warp * 1024 + 1 + trace_n++] =                                                        \
+          ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 12) | ((l) << 4) | (t); \
+      a.trace[warp * 1024] = trace_n;                                                               \
+    }                                                                                               \
+  } while (0)
 
 template <bool kMasked>
 __global__ void __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_save, const FusedArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw;                      // SWIZZLE_128B operands need 1024-byte alignment (checked below)
   uint8_t *act[2] = {smem, smem + kActBytes};
   uint8_t *wring = smem + 2 * kActBytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWStages * kWStage);
@@ -155,18 +164,24 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t *act_ready = act_free + 2;            // [2] epilogue wrote next layer's operand into act[t]
   uint64_t *acc_full = act_ready + 2;            // [2] accumulator of tile t complete
   uint64_t *head_done = acc_full + 2;            // [2] head epilogue drained accumulator t
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(head_done + 2);
+  uint64_t *bias_full = head_done + 2;           // [2] bias of a layer landed in bias_s[slot] (bulk copy)
+  uint64_t *bias_empty = bias_full + 2;          // [2] all 16 epilogue warps are done with bias_s[slot]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_empty + 2);
+  float *bias_s = reinterpret_cast<float *>(bars + 32);   // [2][256] fp32: the current and the next layer's bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned trace_n = 0;
   const int L = a.n_layers;
   const long long n_tiles = (a.P + 127) / 128;
   const long long n_pairs = (n_tiles + 1) / 2;
 
   if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) { printf("nfs_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 16);
       mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16);
+      mbar_init(bias_full + t, 1); mbar_init(bias_empty + t, 16);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_x);
@@ -197,6 +212,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         for (int l = 0; l < L; ++l) {
           const int ks = a.K[l] >> 6, nb = a.N[l] >> 6;
+          if (a.bias != nullptr) {
+            const uint32_t gl = iter * (uint32_t)L + (uint32_t)l, slot = gl & 1;
+            mbar_wait(bias_empty + slot, ((gl >> 1) & 1) ^ 1);
+            mbar_expect_tx(bias_full + slot, (uint32_t)(a.N[l] * 4));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(bias_s + slot * 256)), "l"(a.bias + a.row0[l]), "r"(a.N[l] * 4),
+                           "r"(smem_u32(bias_full + slot)) : "memory");
+          }
           for (int s = 0; s < ks; ++s, ++wit) {
             const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
             if ((a.dbg & 2) && wit >= kWStages) continue;
@@ -213,17 +236,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       uint32_t wit = 0, iter = 0, n_ready[2] = {0, 0};
       for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++iter) {
+        // Issue order per layer: K-half major, tile minor - A.(s0,s1) B.(s0,s1) A.(s2,s3) B.(s2,s3).
+        // Runs of 8 MMAs stay on one accumulator (switching the D operand between consecutive MMAs costs
+        // ~150-270 cycles, scripts/ubench/mma_modes.cu), each weight slab still serves both tiles while it
+        // is resident, and tile A's accumulator completes 8 MMAs before tile B's: A's epilogue overlaps B's
+        // last MMAs and B's epilogue overlaps A's first MMAs of the next layer.
         for (int l = 0; l < L; ++l) {
           const int ks = a.K[l] >> 6;
           const uint32_t idesc = umma_idesc_bf16(128, a.N[l], 0, 0);
-          for (int s = 0; s < ks; ++s, ++wit) {
-            const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
-            if (!((a.dbg & 2) && wit >= kWStages)) mbar_wait(w_full + stage, ph);
-            tc_fence_after();
-            const uint32_t wa = smem_u32(wring + stage * kWStage);
+          const int n_ph = ks >= 2 ? 2 : 1, split = (ks + 1) >> 1;
+          for (int ph = 0; ph < n_ph; ++ph) {
+            const int s_lo = ph == 0 ? 0 : split, s_hi = ph == n_ph - 1 ? ks : split;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-              if (s == 0) {
+              if (ph == 0) {
                 if (l == 0) {
                   mbar_wait(head_done + t, (iter & 1) ^ 1);    // accumulator t drained by the previous pair's head
                   mbar_wait(in_full + t, iter & 1);
@@ -232,20 +258,31 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   ++n_ready[t];
                 }
                 tc_fence_after();
+                NFS_TRACE(1, l, t);
               }
-              const uint32_t xa = smem_u32(act[t] + s * kActSlab);
               const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+              for (int s = s_lo; s < s_hi; ++s) {
+                const uint32_t w = wit + s, stage = w % kWStages, wph = (w / kWStages) & 1;
+                if (t == 0) {
+                  if (!((a.dbg & 2) && w >= kWStages)) mbar_wait(w_full + stage, wph);
+                  tc_fence_after();
+                }
+                const uint32_t wa = smem_u32(wring + stage * kWStage);
+                const uint32_t xa = smem_u32(act[t] + s * kActSlab);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (!(a.dbg & 4)) umma_bf16(d_tmem, umma_desc_sw128(xa + k * 32, 16, 1024), umma_desc_sw128(wa + k * 32, 16, 1024), idesc,
-                          (uint32_t)((s | k) != 0));
-              if (s == ks - 1) {
+                for (int k = 0; k < 4; ++k)
+                  if (!(a.dbg & 4)) umma_bf16(d_tmem, umma_desc_sw128(xa + k * 32, 16, 1024), umma_desc_sw128(wa + k * 32, 16, 1024), idesc,
+                            (uint32_t)((s | k) != 0));
+                if (t == 1) umma_commit(w_empty + stage);
+              }
+              if (ph == n_ph - 1) {
+                NFS_TRACE(2, l, t);
                 umma_commit(acc_full + t);
                 if (l == L - 1) umma_commit(act_free + t);
               }
             }
-            umma_commit(w_empty + stage);
           }
+          wit += ks;
         }
       }
     }
@@ -256,16 +293,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int q = warp & 3;
     const int cq = (warp - 2) >> 2;
     const int r_in = q * 32 + lane;
-    uint32_t n_full[2] = {0, 0};
+    uint32_t n_full[2] = {0, 0}, gl = 0;
     bool store_pending = false;
     for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      for (int l = 0; l < L; ++l) {
+      for (int l = 0; l < L; ++l, ++gl) {
         const bool last = (l == L - 1);
         const bool is_head = last && a.head != 0;
         const int Nl = a.N[l], quarter = Nl >> 2, c0 = cq * quarter;
         const int act_l = a.act[l];
-        const float *bias = a.bias ? a.bias + a.row0[l] + c0 : nullptr;
-#pragma unroll
+        const float *bias = nullptr;                // this warp's columns of the layer's bias, in shared memory
+        if (a.bias != nullptr) {
+          mbar_wait(bias_full + (gl & 1), (gl >> 1) & 1);
+          bias = bias_s + (gl & 1) * 256 + c0;
+        }
+#pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           const long long tile = 2 * pair + t;
           const long long row = tile * 128 + r_in;
@@ -286,6 +327,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           mbar_wait(acc_full + t, n_full[t] & 1);
           ++n_full[t];
           tc_fence_after();
+          NFS_TRACE(3, l, t);
           if (!is_head) {
             // the TMA store this warp issued from act[t] one layer ago has finished READING the block that is
             // overwritten below (the store issued for the other tile a moment ago may still be in flight)
@@ -301,27 +343,26 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int ch0 = (c0 & 63) >> 3;
             if (a.dbg & 1) {
               // bisection: no TMEM drain, no math, no smem writes
-            } else if (quarter == 64) {
-              if constexpr (!kMasked) {
-                float v[64];
-                tmem_ld64(taddr + c0, v);
-                epi_block<64, false>(v, bias, act_l, mk, srow, ch0, r_in & 7);
-              } else {                         // masked variant: two 32-column halves keep the register count down
-                const uint4 mk_hi[8] = {mk[4], mk[5], mk[6], mk[7], mk[4], mk[5], mk[6], mk[7]};
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                epi_block<32, true>(v, bias, act_l, mk, srow, ch0, r_in & 7);
-                tmem_ld32(taddr + c0 + 32, v);
-                epi_block<32, true>(v, bias ? bias + 32 : nullptr, act_l, mk_hi, srow, ch0 + 4, r_in & 7);
-              }
             } else {
-              float v[32];
-              tmem_ld32(taddr + c0, v);
-              epi_block<32, kMasked>(v, bias, act_l, mk, srow, ch0, r_in & 7);
+              // `quarter` (64 or 32) columns in chunks of 16 (small chunks leave registers for a whole chunk of
+              // bias values to be in flight at once; the other three warps of the scheduler hide the latencies)
+              const int n_chunks = quarter >> 4;
+              uint32_t va[16];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c < n_chunks) {
+                  tmem_ld16_async(taddr + c0 + 16 * c, va);
+                  tmem_ld_wait();
+                  epi_chunk<kMasked>(va, bias ? bias + 16 * c : nullptr, act_l, mk[2 * c], mk[2 * c + 1],
+                                     srow, ch0 + 2 * c, r_in & 7, a.dbg);
+                }
+              }
             }
+            NFS_TRACE(4, l, t);
             tc_fence_before();
-            fence_proxy_async();               // generic-proxy smem writes -> visible to UMMA / TMA
+            if (!(a.dbg & 16)) fence_proxy_async();   // generic-proxy smem writes -> visible to UMMA / TMA
             __syncwarp();
+            NFS_TRACE(5, l, t);
             if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             if (lane == 0) {
               if (!last) mbar_arrive(act_ready + t);
@@ -346,7 +387,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   if (j < a.out_cols) {
-                    float x = v[j] + (a.bias ? __ldg(a.bias + a.row0[l] + j) : 0.f);
+                    float x = v[j] + (bias ? bias[j] : 0.f);
                     if (act_l == 1) x = fmaxf(x, 0.f);
                     else if (act_l == 3 || (act_l == 2 && j < 3)) x = fm_sigmoid(x);
                     v[j] = x;
@@ -368,6 +409,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
         }
         if (last) store_pending = false;
+        if (a.bias != nullptr) {                    // both tiles have consumed this layer's bias
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bias_empty + (gl & 1));
+        }
       }
     }
     if (lane == 0) bulk_wait0();               // all saved activations are in global memory
@@ -387,7 +432,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 using namespace nfs;
 
 static int g_fm_debug = 0;
+static unsigned long long *g_fm_trace = nullptr;
 extern "C" void nfs_set_debug_flags(int32_t flags) { g_fm_debug = flags; }
+extern "C" void nfs_set_debug_trace(void *buf) { g_fm_trace = (unsigned long long *)buf; }
 
 // Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
 // default only in their row count (64 resp. 32).
@@ -407,6 +454,7 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
   a.head = out_f32 != nullptr;
   a.dbg = g_fm_debug;
+  a.trace = g_fm_trace;
   a.mask = (const __nv_bfloat16 *)mask_bf16; a.mask_rows = mask_rows_per_layer;
   for (int l = 0; l < n_layers; ++l) {
     a.K[l] = k_dims[l]; a.N[l] = n_dims[l]; a.act[l] = acts[l]; a.row0[l] = row0[l];
@@ -442,7 +490,7 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   } else {
     ts = tx;
   }
-  const size_t smem = 1024 + 2 * kActBytes + kWStages * kWStage + 256;
+  const size_t smem = 2 * kActBytes + kWStages * kWStage + 256 + 2 * 256 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -24,6 +24,7 @@ SIGNATURES = {
     "nfs_last_error_string": (ctypes.c_char_p, []),
     "nfs_launch_count": (ctypes.c_uint64, []),
     "nfs_set_debug_flags": (None, [_i32]),
+    "nfs_set_debug_trace": (None, [_p]),
     "nfs_composite_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "nfs_composite_bwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "nfs_posenc_fwd": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p]),

@@ -19,7 +19,7 @@ def timed(keep):
     for _ in range(10): plan.run_forward_fused(x16, keep)
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / 10
-for flags in (0, 1, 2, 4, 3, 5, 6, 7):
+for flags in (0, 1, 4, 4 + 8, 4 + 16, 4 + 32, 4 + 64, 4 + 8 + 16 + 32 + 64, 8, 16, 32, 64):
     lib.nfs_set_debug_flags(flags)
-    print("flags", flags, "(1=no epilogue work, 2=no weight reloads, 4=no MMAs)  fwd %.3f ms   fwd+save %.3f ms" % (timed(False), timed(True)))
+    print("flags", flags, "(1=no epilogue, 2=no weight reloads, 4=no MMAs, 8=no bias, 16=no proxy fence, 32=no st.shared, 64=no tcgen05.ld)  fwd %.3f ms   fwd+save %.3f ms" % (timed(False), timed(True)))
 lib.nfs_set_debug_flags(0)
