@@ -266,7 +266,7 @@ __device__ __forceinline__ float group_prod(float v) {
 }
 
 template <int G, bool ALIGNED, bool PACKED>
-__global__ void __launch_bounds__(kBlock) composite_bwd_kernel(const CompositeArgs a, const int n_chunks) {
+__global__ void __launch_bounds__(kBlock, 5) composite_bwd_kernel(const CompositeArgs a, const int n_chunks) {
   extern __shared__ float s_carry[];   // [groups per block][n_chunks]; touched only when n_chunks > 1
   constexpr int kGroupsPerWarp = 32 / G;
   constexpr int kRaysPerBlock = (kBlock / 32) * kGroupsPerWarp;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kBlock) composite_bwd_kernel(const CompositeAr
     float ds[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float dalpha = Gi[j] * T[j] - R[j] / al.q[j];
+      const float dalpha = Gi[j] * T[j] - __fdividef(R[j], al.q[j]);   // q in (0, 1]: 2-ulp quotient, 1/5 of the IEEE sequence
       // d alpha / d density = dists * exp(-relu(density) dists) * [density > 0]
       ds[j] = (v.sg[j] > 0.f) ? dalpha * al.dist[j] * al.e[j] : 0.f;
     }
