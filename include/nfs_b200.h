@@ -254,6 +254,15 @@ int nfs_adam_step(float *param, const float *grad, float *exp_avg, float *exp_av
                   float weight_decay, int32_t step, float grad_scale, int32_t decoupled,
                   void *stream);
 
+/* Same update with the step count and learning rate resident on the device, so that the launch can
+ * be replayed from a CUDA graph: *step_counter is incremented first, state (3 floats) =
+ * [1 - beta1^t, sqrt(1 - beta2^t), lr]; the first two are rewritten by the call, state[2] (lr,
+ * MultiStepLR of train.py:120-124) is owned by the host. */
+int nfs_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                      int64_t n, float beta1, float beta2, float eps, float weight_decay,
+                      int32_t *step_counter, float *state, float grad_scale, int32_t decoupled,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,9 +148,10 @@ gate_bwd_kernel(const float *__restrict__ x, const float *__restrict__ freqs, co
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
-            int decoupled) {
+            int decoupled, const float *__restrict__ state) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (state != nullptr) { bc1 = __ldg(state); bc2_sqrt = __ldg(state + 1); lr = __ldg(state + 2); }
   float grad = g[i] * gscale, w = p[i];
   if (wd != 0.f) {
     if (decoupled) w *= 1.f - lr * wd;      // AdamW
@@ -161,6 +162,15 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] = w - (lr / bc1) * (mi / denom);
+}
+
+// Device-resident step counter (CUDA-graph replay cannot change a host-side step argument):
+// state = [1 - beta1^t, sqrt(1 - beta2^t), lr]; the first two are refreshed here, lr by the host.
+__global__ void adam_tick_kernel(int *step, float b1, float b2, float *state) {
+  const int t = *step + 1;
+  *step = t;
+  state[0] = (float)(1.0 - pow((double)b1, (double)t));
+  state[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
 }
 
 }  // namespace
@@ -254,6 +264,24 @@ extern "C" int nfs_adam_step(float *param, const float *grad, float *exp_avg, fl
   const long long blocks = (n + 255) / 256;
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                  eps, weight_decay, (float)bc1, (float)sqrt(bc2),
-                                                                 grad_scale, decoupled);
+                                                                 grad_scale, decoupled, nullptr);
+  return check_launch(fn);
+}
+
+extern "C" int nfs_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                                 float beta1, float beta2, float eps, float weight_decay, int32_t *step_counter,
+                                 float *state, float grad_scale, int32_t decoupled, void *stream) {
+  const char *fn = "nfs_adam_step_dev";
+  if (n < 0) return fail_arg(fn, NFS_E_BADARG, "n < 0");
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step_counter || !state)
+    return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter, beta1, beta2, state);
+  int rc = check_launch(fn);
+  if (rc) return rc;
+  const long long blocks = (n + 255) / 256;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, 0.f, beta1, beta2,
+                                                                 eps, weight_decay, 1.f, 1.f, grad_scale, decoupled,
+                                                                 state);
   return check_launch(fn);
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     "nfs_pack_linear_bf16": (ctypes.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "nfs_act_grad_bf16": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i64, _p, _p]),
     "nfs_adam_step": (ctypes.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _i32, _p]),
+    "nfs_adam_step_dev": (ctypes.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p, _f32, _i32, _p]),
     "nfs_sample_hierarchical": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -84,6 +84,23 @@ class PackedLinear:
         return self
 
 
+_freq_cache = {}
+
+
+def freqs_on(device, freqs):
+    """fp32 copy of a frequency table on `device`, cached (the reference keeps freq_bands on the CPU,
+    positional_encoding.py:14-18; copying it per call would put a pageable H2D copy in every step)."""
+    if freqs.device == device and freqs.dtype == torch.float32 and freqs.is_contiguous():
+        return freqs.detach()
+    key = (freqs.data_ptr(), freqs._version, int(freqs.numel()), str(device))
+    hit = _freq_cache.get(key)
+    if hit is None:
+        if len(_freq_cache) > 64:
+            _freq_cache.clear()
+        hit = _freq_cache[key] = freqs.detach().to(device=device, dtype=torch.float32).contiguous()
+    return hit
+
+
 def encode_operand(x, freqs, k_pad, extra=None, gate=None, out=None):
     """fp32 rows -> bf16 GEMM operand [P,k_pad] = [enc(x) * g0 | extra * g1 | 0] (nfs_posenc_bf16).
     freqs=None copies x itself (already-encoded input); gate (P,2) fp32 = the softmax gate of
@@ -100,7 +117,7 @@ def encode_operand(x, freqs, k_pad, extra=None, gate=None, out=None):
             raise RuntimeError("encode_operand: out must be a bf16 [P,k_pad] block with contiguous columns")
         pitch = out.stride(0)
     if P:
-        fr = None if freqs is None else freqs.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        fr = None if freqs is None else freqs_on(x.device, freqs)
         g0 = g1 = None
         if gate is not None:
             gate = ops._f32c(gate)

@@ -307,7 +307,8 @@ class G3Plan:
         # ---- the gate (dino_feature_model.py:188-195)
         dc2, _ = ops.linear_bf16(grad_pre(0), self.p1.w16t, None, act=0)
         dlog = torch.empty((P, 64), device=dev, dtype=torch.bfloat16)
-        fr = freqs_pos.detach().to(device=dev, dtype=torch.float32).contiguous()
+        from .mlp import freqs_on
+        fr = freqs_on(dev, freqs_pos)
         with torch.cuda.device(dev):
             _lib.call("nfs_gate_bwd_bf16", ptr(x), ptr(fr), ptr(f) if self.D else None, ptr(gate), ptr(dc2), self.k0, P,
                       3, int(fr.numel()), self.D, 64, ptr(dlog), _stream())

@@ -169,6 +169,16 @@ def _tables_on(device, near, far, n_samples, lindisp):
     return hit
 
 
+def importance_table(device, n_importance):
+    """u = linspace(0, 1, N_importance) of ray_utils.py:113 (perturb=False), evaluated by torch on the
+    CPU like the reference does and cached on `device`."""
+    key = ("u", str(device), int(n_importance))
+    hit = _table_cache.get(key)
+    if hit is None:
+        hit = _table_cache[key] = torch.linspace(0., 1., n_importance).to(device)
+    return hit
+
+
 def sample_stratified(rays_o, rays_d, near, far, n_samples, t_rand=None, lindisp=False, want_pts=True):
     """rays (...,3) -> pts (...,S,3), z (...,S).  t_rand (...,S) = the uniform draws of
     ray_utils.py:78 (None = perturb=False)."""

@@ -34,7 +34,11 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.grad = torch.zeros_like(self.flat)
-        self.step_count = 0
+        # step count and learning rate live on the device so that step() can be replayed from a CUDA graph
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._state = torch.tensor([1.0, 1.0, float(lr)], device=dev, dtype=torch.float32)
+        self._lr_on_device = float(lr)
+        self._steps_host = 0
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -46,15 +50,22 @@ class FusedAdam:
         torch.cat(parts, out=self.grad)
         return self.grad
 
+    @property
+    def step_count(self):
+        """Number of steps taken (reads the device counter: host sync; not for the hot loop)."""
+        return int(self._step_dev.item())
+
     def step(self, grad_scale=1.0, gathered=False):
         if not gathered:
             self.gather_grads()
-        self.step_count += 1
+        if float(self.lr) != self._lr_on_device:      # MultiStepLR moved the rate: refresh the device copy
+            self._state[2:3].fill_(float(self.lr))
+            self._lr_on_device = float(self.lr)
         with torch.cuda.device(self.flat.device):
-            _lib.call("nfs_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                      self.flat.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                      float(self.weight_decay), int(self.step_count), float(grad_scale), int(bool(self.decoupled)),
-                      _stream())
+            _lib.call("nfs_adam_step_dev", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                      self.flat.numel(), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                      float(self.weight_decay), ptr(self._step_dev), ptr(self._state), float(grad_scale),
+                      int(bool(self.decoupled)), _stream())
         mlp.bump_weight_epoch()          # cached bf16 operand copies are stale now
 
     def state_dict(self):
@@ -62,7 +73,7 @@ class FusedAdam:
                 "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
+        self._step_dev.fill_(int(sd["step"]))
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.lr = sd.get("lr", self.lr)

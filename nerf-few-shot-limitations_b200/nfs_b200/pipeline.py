@@ -33,8 +33,7 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
         with torch.no_grad():
             w_in = weights.detach()[:, :-1].contiguous()      # M = S-1 bins between the S coarse depths
             if u is None:
-                u = torch.rand(N, n_importance, device=dev) if perturb else \
-                    torch.linspace(0., 1., n_importance).to(dev)
+                u = torch.rand(N, n_importance, device=dev) if perturb else ops.importance_table(dev, n_importance)
             pts_f, z_f = ops.sample_hierarchical(rays_o, rays_d, z, w_in, n_importance, u=u)
         S = n_coarse + n_importance
         raw_f = model.forward_points(pts_f.reshape(-1, 3), freq_bands).reshape(N, S, 4)
@@ -75,3 +74,83 @@ def render_image(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_im
                         n_importance, perturb=False, white_bkgd=white_bkgd)
         outs.append(o["rgb"])
     return torch.cat(outs, 0) if outs else rays_o.new_zeros((0, 3))
+
+
+class GraphedTrainStep:
+    """train_step captured once into CUDA graphs and replayed: ~140 kernel launches per step
+    (samplers, operand packing, MLP chains, wgrads, compositing, loss, fused Adam) become one
+    cudaGraphLaunch, so the step is paced by the GPU instead of by Python / launch latency.
+
+    Everything the step reads is static: rays and targets are copied into fixed buffers, the
+    Adam step count and learning rate live on the device (nfs_adam_step_dev), the uniform draws
+    come from torch's graph-safe generator.  With `allreduce` (data parallel) the step is two graphs
+    with the gradient all-reduce between them: [render + backward + gradient flattening] -> NCCL
+    all-reduce of the flat buffer -> [Adam]."""
+
+    def __init__(self, model, optimizer, freq_bands, n_rays, near, far, n_coarse=64, n_importance=128,
+                 perturb=True, loss_scale=1.0, allreduce=None, warmup=3):
+        from . import mlp
+        if not hasattr(optimizer, "gather_grads"):
+            raise RuntimeError("GraphedTrainStep needs nfs_b200.optim.FusedAdam (device-resident optimizer state)")
+        self.model, self.opt, self.bands = model, optimizer, mlp.freqs_on(optimizer.flat.device, freq_bands)
+        self.cfg = (near, far, n_coarse, n_importance, perturb)
+        self.loss_scale, self.allreduce = float(loss_scale), allreduce
+        dev = optimizer.flat.device
+        self.rays_o = torch.zeros(n_rays, 3, device=dev)
+        self.rays_d = torch.zeros(n_rays, 3, device=dev)
+        self.rays_d[:, 2] = -1.0
+        self.target = torch.zeros(n_rays, 3, device=dev)
+        o = optimizer
+        snap = [t.clone() for t in (o.flat, o.exp_avg, o.exp_avg_sq, o._step_dev, o._state)]
+        rng = torch.cuda.get_rng_state(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):            # first launches: function attributes, caches, allocator
+                self._forward_backward()
+                if allreduce is not None:
+                    allreduce(o.grad)
+                self._update()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.g_step = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_step):
+            self.loss = self._forward_backward()
+            if allreduce is None:
+                self._update()
+        self.g_update = None
+        if allreduce is not None:
+            self.g_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_update, pool=self.g_step.pool()):
+                self._update()
+        for dst, src in zip((o.flat, o.exp_avg, o.exp_avg_sq, o._step_dev, o._state), snap):
+            dst.copy_(src)
+        torch.cuda.set_rng_state(rng, dev)
+        mlp.bump_weight_epoch()
+
+    def _forward_backward(self):
+        near, far, n_coarse, n_importance, perturb = self.cfg
+        self.opt.zero_grad()
+        out = render_rays(self.model, self.bands, self.rays_o, self.rays_d, near, far, n_coarse, n_importance, perturb)
+        loss = torch.mean((out["rgb"] - self.target) ** 2)
+        if n_importance > 0:
+            loss = loss + torch.mean((out["rgb_coarse"] - self.target) ** 2)
+        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        self.opt.gather_grads()
+        return loss.detach()
+
+    def _update(self):
+        self.opt.step(gathered=True)
+
+    def __call__(self, rays_o, rays_d, target):
+        """One optimisation step; returns the loss tensor of this step (static buffer, no host sync)."""
+        from . import mlp
+        self.rays_o.copy_(rays_o, non_blocking=True)
+        self.rays_d.copy_(rays_d, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        self.g_step.replay()
+        if self.g_update is not None:
+            self.allreduce(self.opt.grad)
+            self.g_update.replay()
+        mlp.bump_weight_epoch()      # the graph changed the fp32 masters: eager callers must repack
+        return self.loss

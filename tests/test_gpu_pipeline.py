@@ -87,3 +87,40 @@ def test_train_step_learns(cuda):
     assert all(torch.isfinite(p).all() for p in mod.parameters())
     img = pipeline.render_image(mod.eval(), bands, ro, rd, 2.0, 6.0, 64, 128, chunk=300)
     assert img.shape == (n, 3) and bool(torch.isfinite(img).all())
+
+
+def test_graphed_train_step_matches_eager(cuda):
+    """The CUDA-graph replay of the training step (one cudaGraphLaunch per step) follows the eager
+    step exactly: same kernels, same order, same deterministic draws (perturb=False)."""
+    import bench
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import pipeline
+    from nfs_b200.optim import FusedAdam
+    N = 1024
+    ro, rd = bench.lego_rays(N, seed=3)
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    g = torch.Generator().manual_seed(0)
+    targets = [torch.rand(N, 3, generator=g).to(cuda) for _ in range(4)]
+    bands = 2.0 ** torch.linspace(0.0, 9.0, 10)
+    losses = {}
+    finals = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(7)
+        model = NeRFMLP().to(cuda).train()
+        opt = FusedAdam(model.parameters(), lr=5e-4)
+        step = None
+        if mode == "graph":
+            step = pipeline.GraphedTrainStep(model, opt, bands, N, 2.0, 6.0, 64, 128, perturb=False)
+        ls = []
+        for t in targets:
+            if step is None:
+                ls.append(float(pipeline.train_step(model, opt, bands, ro, rd, t, 2.0, 6.0, 64, 128, perturb=False)))
+            else:
+                ls.append(float(step(ro, rd, t)))
+        losses[mode] = ls
+        finals[mode] = opt.flat.clone()
+        assert opt.step_count == len(targets)
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses["eager"], losses["graph"])      # wgrad atomics reorder fp32 sums
+    assert float((finals["eager"] - finals["graph"]).abs().max()) <= 5e-3
+    assert losses["graph"][-1] < losses["graph"][0] * 1.5
