@@ -196,6 +196,79 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measure_extras(dev, rank, world, dist, quick):
+    """BASELINE configs 3 and 5 on the same box, same run (reported under "extras"; the headline
+    stays config 2).  cfg 3: one optimisation step of the G1 model, 4096 rays per GPU, 64 coarse +
+    192 fine evaluations per ray, CUDA-graph replay, one NCCL sum-allreduce of the 1.9 MB flat
+    gradient per step when N > 1.  cfg 5: 800x800 render (640 000 rays, 64 + 192 evaluations per ray)
+    split contiguously over the N GPUs.  Times are CUDA events, max over ranks."""
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import dist as nd
+    from nfs_b200 import pipeline
+    from nfs_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    model = NeRFMLP().to(dev).train()
+    opt = FusedAdam(model.parameters(), lr=5e-4)
+    bands = 2.0 ** torch.linspace(0.0, 9.0, 10)
+    n = 4096
+    ro, rd = lego_rays(n, seed=100 + rank)
+    ro, rd = ro.to(dev), rd.to(dev)
+    target = torch.rand(n, 3, device=dev)
+    allreduce = (lambda g: nd.allreduce_sum_(g)) if world > 1 else None
+    step = pipeline.GraphedTrainStep(model, opt, bands, n, 2.0, 6.0, 64, 128, perturb=True,
+                                     loss_scale=1.0 / world, allreduce=allreduce)
+
+    def timed(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    reps = 5 if quick else 30
+    ms = timed(lambda: step(ro, rd, target), reps, 3)
+    flop_ray = 256 * 2823168.0                       # SURVEY.md 8d: 64 + 192 evaluations x train flop per point
+    out = {"train_step_cfg3": {
+        "rays_per_s": world * n / (ms * 1e-3), "ms_per_step": ms, "rays_per_gpu": n,
+        "tflops_per_gpu": n * flop_ray / (ms * 1e-3) / 1e12,
+        "frac_of_bf16_sustained_peak": n * flop_ray / (ms * 1e-3) / 1e12 / bf16_peak(),
+        "allreduce": "nccl sum of %d fp32 gradients per step" % opt.flat.numel() if world > 1 else "none (1 GPU)",
+        "launch": "CUDA graph replay"}}
+    # render: this rank's contiguous share of the 640 000 rays of one 800 x 800 frame
+    total = 640000
+    lo, hi = nd.shard_range(total, rank, world)
+    ro2, rd2 = lego_rays(hi - lo, seed=7)
+    ro2, rd2 = ro2.to(dev), rd2.to(dev)
+    model.eval()
+    ms = timed(lambda: pipeline.render_image(model, bands, ro2, rd2, 2.0, 6.0, 64, 128, chunk=65536),
+               1 if quick else 3, 1)
+    fwd_flop_ray = 256 * 951808.0
+    out["render_cfg5"] = {
+        "rays_per_s": total / (ms * 1e-3), "ms_per_frame": ms, "rays_per_gpu": hi - lo,
+        "tflops_per_gpu": (hi - lo) * fwd_flop_ray / (ms * 1e-3) / 1e12,
+        "frac_of_bf16_sustained_peak": (hi - lo) * fwd_flop_ray / (ms * 1e-3) / 1e12 / bf16_peak()}
+    return out
+
+
+def bf16_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return 1415.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +276,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg 3 / cfg 5 measurements")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): no clock-settle loop, no e2e leg, no CPU baseline")
     args = ap.parse_args()
@@ -255,11 +329,11 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # clock record: nvidia-smi samples every 200 ms, so keep the GPU under the same load for ~1.5 s
-    # around the (much shorter) timed region; only samples taken under load are reported.
+    # clock record: NVML samples every 50 ms, so keep the GPU under the same load for ~0.3 s before and
+    # ~0.2 s after the (much shorter) timed region; the samples cover settle + timed region + tail.
     clocks = ClockSampler(local_rank) if rank == 0 and not args.quick else None
     t_settle = time.perf_counter()
-    while not args.quick and time.perf_counter() - t_settle < 1.0:
+    while not args.quick and time.perf_counter() - t_settle < 0.3:
         for _ in range(50):
             fwd(); bwd()
         torch.cuda.synchronize()
@@ -285,7 +359,7 @@ def main():
     elapsed_ms = float(t.item())
     if clocks is not None:          # a few more samples under identical load, then stop
         t_settle = time.perf_counter()
-        while time.perf_counter() - t_settle < 0.5:
+        while time.perf_counter() - t_settle < 0.2:
             for _ in range(50):
                 fwd(); bwd()
             torch.cuda.synchronize()
@@ -330,6 +404,13 @@ def main():
     h2d = sum(host[k].numel() * 4 for k in host)
     d2h = h_out.numel() * 4 + 4
 
+    extras = None
+    if not args.no_extras:
+        try:
+            extras = measure_extras(dev, rank, world, dist, args.quick)
+        except Exception as e:                      # the headline line must survive a failure of the extras
+            extras = {"error": repr(e)[:300]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -356,6 +437,7 @@ def main():
                 "steps": e2e_steps, "api": "models.nerf_mlp.VolumeRenderer + autograd, pinned host buffers"},
         "gpu_launches": int(launches),
         "clocks": clk,
+        "extras": extras,
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
