@@ -5,23 +5,32 @@
 //   nerf_model.NeRFMLP.forward    /root/reference/src/models/nerf_model.py:16-24
 // (and any sub-chain of nerf_mlp.NeRFWithDINO, nerf_mlp.py:134-158) for 256 points per CTA step.
 //
-// One persistent CTA per SM works on PAIRS of 128-point tiles (A, B):
-//   * act[A], act[B]  : 2 x 64 KB shared memory, the bf16 activations of the current layer in
+// Persistent CTA PAIRS (thread-block clusters of 2 = two SMs, tcgen05 cta_group::2): each CTA keeps two
+// 128-point tiles (A, B) in flight, so a pair works on four tiles.
+//   * act[A], act[B]  : 2 x 64 KB shared memory per CTA, the bf16 activations of the current layer in
 //                       the canonical K-major SWIZZLE_128B operand layout (4 slabs of [128 x 64]);
 //                       the epilogue overwrites them IN PLACE with the next layer's input;
-//   * weight ring     : 3 x 32 KB stages, one [N x 64] K-slab of one layer each, TMA-loaded from a
-//                       single stacked bf16 weight tensor (L2 resident, ~1 MB) and shared by both
-//                       tiles - 128 KB of weights per layer feed 2 x 16 MMAs;
-//   * TMEM            : two 128 x 256 fp32 accumulators (512 columns), one per tile.
-// The MMA thread interleaves the two tiles slab by slab, so tile A's accumulator completes four
-// MMAs before tile B's: A's epilogue (tcgen05.ld -> +bias -> ReLU -> bf16 -> swizzled st.shared)
-// overlaps B's last MMAs and B's epilogue overlaps A's first MMAs of the next layer.
+//   * weight ring     : 6 x 16 KB stages per CTA.  One tcgen05.mma.cta_group::2 multiplies the pair's
+//                       256 points (128 from each CTA) by all N output columns, and each CTA supplies
+//                       HALF of the weight rows: a stage is [N/2 x 64], a whole layer is 4 stages, so
+//                       the layer's weights stay resident while tile A and then tile B use them and
+//                       the next layer's first stages are prefetched.  Per-SM shared-memory traffic per
+//                       MMA drops from 12 KB to 8 KB and the MMA runs at its 128-cycle floor
+//                       (scripts/ubench/mma_2cta.cu; the single-CTA form is smem-bound at 161 cycles);
+//   * TMEM            : two 128 x 256 fp32 accumulators (512 columns) per CTA, one per tile.
+// The leader CTA's MMA thread runs tile-major - 16 MMAs on the pair's A tiles, 16 on the B tiles - so
+// A's accumulator completes half a layer (2048 cycles) before B's: A's epilogue (tcgen05.ld -> +bias ->
+// ReLU -> bf16 -> swizzled st.shared) overlaps B's MMAs and B's epilogue overlaps A's MMAs of the next
+// layer.  Barriers that gate the MMA thread (weights landed, tile ready, accumulator drained) live in
+// the leader CTA and count both CTAs (TMA .cta_group::2 completion, remote mbarrier arrives); barriers
+// the MMA thread signals (accumulator full, weight stage free) are multicast to both CTAs by
+// tcgen05.commit.
 // When activations must be saved for the backward pass each epilogue warp TMA-stores the
 // 32-row x 64-column boxes it has just written (cp.async.bulk.tensor, bulk groups).
 // The last layer of the chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
 // written as fp32 with the reference's output activation.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..17 = epilogue (four warps per TMEM
-// lane quadrant, each draining a quarter of the columns of tile A, then of tile B, with one tcgen05.ld).
+// Warp roles per CTA: 0 = TMA producer, 1 = TMEM owner (+ MMA issuer in the leader), 2..17 = epilogue
+// (four warps per TMEM lane quadrant, each draining a quarter of the columns of tile A, then of tile B).
 #include "tc_common.cuh"
 
 namespace nfs {
@@ -33,8 +42,8 @@ constexpr int kFmThreads = 576;   // 18 warps
 constexpr int kFmMaxLayers = 12;
 constexpr int kActBytes = 128 * 256 * 2;
 constexpr int kActSlab = 128 * 128;
-constexpr int kWStage = 256 * 128;
-constexpr int kWStages = 3;
+constexpr int kWStage = 128 * 128;   // one weight stage: this CTA's half of the rows, [<= 128 x 64] bf16
+constexpr int kWStages = 6;
 
 struct FusedArgs {
   long long P;
@@ -62,6 +71,55 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- CTA-pair plumbing
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the pair
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Barriers signalled from the peer CTA / by multicast commits are waited on with the default
+// (.acquire.cta) try_wait like every other barrier: a cluster-scope acquire costs ~400 cycles per wait
+// (measured with the timeline tracer) and the data these barriers guard is read through the async
+// proxy (UMMA operands, TMEM), which the arriving side orders with fence.proxy.async / tcgen05 fences.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset): both CTAs of the
+// pair fill their own shared memory, one barrier in the leader counts all the bytes.
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all prior MMAs of this thread -> one arrive on `bar` (same offset) in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ float fm_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -150,7 +208,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s
   } while (0)
 
 template <bool kMasked>
-__global__ void __launch_bounds__(kFmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_save, const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -163,24 +221,29 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t *act_free = in_full + 2;              // [2] last layer's MMAs have read act[t]
   uint64_t *act_ready = act_free + 2;            // [2] epilogue wrote next layer's operand into act[t]
   uint64_t *acc_full = act_ready + 2;            // [2] accumulator of tile t complete
-  uint64_t *head_done = acc_full + 2;            // [2] head epilogue drained accumulator t
-  uint64_t *bias_full = head_done + 2;           // [2] bias of a layer landed in bias_s[slot] (bulk copy)
+  uint64_t *head_done = acc_full + 2;            // [2] this CTA's epilogue is done with act[t] / accumulator t (producer)
+  uint64_t *acc_free = head_done + 2;            // [2] leader: both CTAs' epilogues drained accumulator t (MMA thread)
+  uint64_t *bias_full = acc_free + 2;           // [2] bias of a layer landed in bias_s[slot] (bulk copy)
   uint64_t *bias_empty = bias_full + 2;          // [2] all 16 epilogue warps are done with bias_s[slot]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_empty + 2);
   float *bias_s = reinterpret_cast<float *>(bars + 32);   // [2][256] fp32: the current and the next layer's bias
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then treats it (and every branch on it) as warp-uniform and
+  // keeps the MMA / TMA operands in uniform registers instead of R2UR "waterfall" loops per instruction
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   unsigned trace_n = 0;
   const int L = a.n_layers;
   const long long n_tiles = (a.P + 127) / 128;
-  const long long n_pairs = (n_tiles + 1) / 2;
+  const long long n_quads = (n_tiles + 3) / 4;          // a CTA pair works on 4 tiles: tile = 4*quad + 2*rank + t
+  const uint32_t rank = cluster_ctarank();
+  const long long quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { printf("nfs_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 16);
-      mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16);
+      mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 32);
+      mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16); mbar_init(acc_free + t, 32);
       mbar_init(bias_full + t, 1); mbar_init(bias_empty + t, 16);
     }
     fence_barrier_init();
@@ -188,12 +251,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tma_prefetch_desc(&tmap_w);
     if (a.save) tma_prefetch_desc(&tmap_save);
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+  if (warp == 1) {                                 // the pair allocates together: warp 1 of both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                              // both CTAs' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -202,19 +266,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       uint32_t wit = 0, iter = 0;
       const int ks0 = a.K[0] >> 6;
-      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++iter) {
+      for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(act_free + t, (iter & 1) ^ 1);
-          mbar_wait(head_done + t, (iter & 1) ^ 1);
-          mbar_expect_tx(in_full + t, (uint32_t)(ks0 * kActSlab));
+          mbar_wait_relaxed(act_free + t, (iter & 1) ^ 1);
+          mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(in_full + t, (uint32_t)(2 * ks0 * kActSlab));     // both CTAs' tiles
           for (int s = 0; s < ks0; ++s)
-            tma_load_2d(act[t] + s * kActSlab, &tmap_x, in_full + t, s * 64, (int)((2 * pair + t) * 128));
+            tma_load_2d_pair(act[t] + s * kActSlab, &tmap_x, in_full + t, s * 64, (int)((4 * quad + 2 * rank + t) * 128));
         }
         for (int l = 0; l < L; ++l) {
-          const int ks = a.K[l] >> 6, nb = a.N[l] >> 6;
+          const int ks = a.K[l] >> 6, nh = a.N[l] >> 1;           // this CTA's half of the output rows
+          const int nb = (nh + 63) >> 6;                          // 64-row TMA boxes (a 32-row half loads a full box)
           if (a.bias != nullptr) {
             const uint32_t gl = iter * (uint32_t)L + (uint32_t)l, slot = gl & 1;
-            mbar_wait(bias_empty + slot, ((gl >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(bias_empty + slot, ((gl >> 1) & 1) ^ 1);
             mbar_expect_tx(bias_full + slot, (uint32_t)(a.N[l] * 4));
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(bias_s + slot * 256)), "l"(a.bias + a.row0[l]), "r"(a.N[l] * 4),
@@ -223,64 +288,68 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int s = 0; s < ks; ++s, ++wit) {
             const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
             if ((a.dbg & 2) && wit >= kWStages) continue;
-            mbar_wait(w_empty + stage, ph ^ 1);
-            mbar_expect_tx(w_full + stage, (uint32_t)(a.N[l] * 128));
+            mbar_wait_relaxed(w_empty + stage, ph ^ 1);
+            if (rank == 0) mbar_expect_tx(w_full + stage, (uint32_t)(2 * nb * 8192));
             for (int b = 0; b < nb; ++b)
-              tma_load_2d(wring + stage * kWStage + b * 8192, &tmap_w, w_full + stage, s * 64, a.row0[l] + b * 64);
+              tma_load_2d_pair(wring + stage * kWStage + b * 8192, &tmap_w, w_full + stage, s * 64,
+                               a.row0[l] + (int)rank * nh + b * 64);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {                 // all 32 lanes walk the (warp-uniform) schedule; one elected lane issues
       uint32_t wit = 0, iter = 0, n_ready[2] = {0, 0};
-      for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++iter) {
-        // Issue order per layer: K-half major, tile minor - A.(s0,s1) B.(s0,s1) A.(s2,s3) B.(s2,s3).
-        // Runs of 8 MMAs stay on one accumulator (switching the D operand between consecutive MMAs costs
-        // ~150-270 cycles, scripts/ubench/mma_modes.cu), each weight slab still serves both tiles while it
-        // is resident, and tile A's accumulator completes 8 MMAs before tile B's: A's epilogue overlaps B's
-        // last MMAs and B's epilogue overlaps A's first MMAs of the next layer.
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(wring), 16, 1024);
+      const bool no_mma = (a.dbg & 4) != 0;
+      for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
+        // Issue order per layer: tile major - 4*ks MMAs on the pair's A tiles, then 4*ks on the B tiles.
+        // Long runs on one accumulator (switching the D operand between consecutive MMAs costs
+        // ~150-270 cycles, scripts/ubench/mma_modes.cu); the layer's weights (ks stages of [N/2 x 64]
+        // per CTA) stay resident for both passes.
         for (int l = 0; l < L; ++l) {
           const int ks = a.K[l] >> 6;
-          const uint32_t idesc = umma_idesc_bf16(128, a.N[l], 0, 0);
-          const int n_ph = ks >= 2 ? 2 : 1, split = (ks + 1) >> 1;
-          for (int ph = 0; ph < n_ph; ++ph) {
-            const int s_lo = ph == 0 ? 0 : split, s_hi = ph == n_ph - 1 ? ks : split;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              if (ph == 0) {
-                if (l == 0) {
-                  mbar_wait(head_done + t, (iter & 1) ^ 1);    // accumulator t drained by the previous pair's head
-                  mbar_wait(in_full + t, iter & 1);
-                } else {
-                  mbar_wait(act_ready + t, n_ready[t] & 1);
-                  ++n_ready[t];
-                }
-                tc_fence_after();
-                NFS_TRACE(1, l, t);
-              }
-              const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
-              for (int s = s_lo; s < s_hi; ++s) {
-                const uint32_t w = wit + s, stage = w % kWStages, wph = (w / kWStages) & 1;
-                if (t == 0) {
-                  if (!((a.dbg & 2) && w >= kWStages)) mbar_wait(w_full + stage, wph);
-                  tc_fence_after();
-                }
-                const uint32_t wa = smem_u32(wring + stage * kWStage);
-                const uint32_t xa = smem_u32(act[t] + s * kActSlab);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (!(a.dbg & 4)) umma_bf16(d_tmem, umma_desc_sw128(xa + k * 32, 16, 1024), umma_desc_sw128(wa + k * 32, 16, 1024), idesc,
-                            (uint32_t)((s | k) != 0));
-                if (t == 1) umma_commit(w_empty + stage);
-              }
-              if (ph == n_ph - 1) {
-                NFS_TRACE(2, l, t);
-                umma_commit(acc_full + t);
-                if (l == L - 1) umma_commit(act_free + t);
-              }
+          const uint32_t idesc = umma_idesc_bf16(256, a.N[l], 0, 0);
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t) {
+            if (l == 0) {
+              mbar_wait_cluster(acc_free + t, (iter & 1) ^ 1);   // accumulators t drained by the previous quad's last layer
+              mbar_wait_cluster(in_full + t, iter & 1);
+            } else {
+              mbar_wait_cluster(act_ready + t, n_ready[t] & 1);
+              ++n_ready[t];
             }
+            tc_fence_after();
+            NFS_TRACE(1, l, t);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+            // descriptors differ only in their 14-bit start-address field: +2 per 32-byte K step
+            const uint64_t a_desc0 = umma_desc_sw128(smem_u32(act[0]) + (uint32_t)t * kActBytes, 16, 1024);
+            for (int s = 0; s < ks; ++s) {
+              const uint32_t w = wit + s, stage = w % kWStages, wph = (w / kWStages) & 1;
+              if (t == 0) {
+                if (!((a.dbg & 2) && w >= kWStages)) mbar_wait_cluster(w_full + stage, wph);
+                tc_fence_after();
+              }
+              const uint64_t ad = a_desc0 + (uint64_t)((s * kActSlab) >> 4);
+              const uint64_t bd = b_desc0 + (uint64_t)((stage * kWStage) >> 4);
+              if (elect_one()) {
+                if (!no_mma) {
+                  umma_bf16_pair(d_tmem, ad, bd, idesc, (uint32_t)(s != 0));
+                  umma_bf16_pair(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                  umma_bf16_pair(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                  umma_bf16_pair(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                }
+                if (t == 1) umma_commit_pair(w_empty + stage);
+              }
+              __syncwarp();
+            }
+            NFS_TRACE(2, l, t);
+            if (elect_one()) {
+              umma_commit_pair(acc_full + t);
+              if (l == L - 1) umma_commit_pair(act_free + t);
+            }
+            __syncwarp();
           }
           wit += ks;
         }
@@ -295,7 +364,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int r_in = q * 32 + lane;
     uint32_t n_full[2] = {0, 0}, gl = 0;
     bool store_pending = false;
-    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    const uint32_t ready_bar[2] = {map_to_cta(act_ready, 0), map_to_cta(act_ready + 1, 0)};   // in the leader CTA
+    const uint32_t free_bar[2] = {map_to_cta(acc_free, 0), map_to_cta(acc_free + 1, 0)};
+    for (long long quad = quad0; quad < n_quads; quad += quad_step) {
       for (int l = 0; l < L; ++l, ++gl) {
         const bool last = (l == L - 1);
         const bool is_head = last && a.head != 0;
@@ -303,12 +374,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int act_l = a.act[l];
         const float *bias = nullptr;                // this warp's columns of the layer's bias, in shared memory
         if (a.bias != nullptr) {
-          mbar_wait(bias_full + (gl & 1), (gl >> 1) & 1);
+          mbar_wait_relaxed(bias_full + (gl & 1), (gl >> 1) & 1);
           bias = bias_s + (gl & 1) * 256 + c0;
         }
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-          const long long tile = 2 * pair + t;
+          const long long tile = 4 * quad + 2 * rank + t;
           const long long row = tile * 128 + r_in;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
           uint8_t *act_t = smem + t * kActBytes;
@@ -324,7 +395,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               for (int g = 0; g < 4; ++g) mk[g] = __ldg(mp + g);
             }
           }
-          mbar_wait(acc_full + t, n_full[t] & 1);
+          mbar_wait_relaxed(acc_full + t, n_full[t] & 1);
           ++n_full[t];
           tc_fence_after();
           NFS_TRACE(3, l, t);
@@ -365,7 +436,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             NFS_TRACE(5, l, t);
             if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             if (lane == 0) {
-              if (!last) mbar_arrive(act_ready + t);
+              if (!last) mbar_arrive_cluster(ready_bar[t]);
               if (a.save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
                 tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
                              (int)(l * a.save_rows + tile * 128 + q * 32));
@@ -376,7 +447,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (last) {                          // chain ends in a regular layer: tile t is finished once the
               if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
               __syncwarp();
-              if (lane == 0) mbar_arrive(head_done + t);
+              if (lane == 0) { mbar_arrive(head_done + t); mbar_arrive_cluster(free_bar[t]); }
             }
           } else {
             // head: first out_cols (<= 16) columns, fp32, reference output activation; quarter 0 only
@@ -405,7 +476,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             tc_fence_before();
             if (store_pending && lane == 0) bulk_wait_read0();
             __syncwarp();
-            if (lane == 0) mbar_arrive(head_done + t);
+            if (lane == 0) { mbar_arrive(head_done + t); mbar_arrive_cluster(free_bar[t]); }
           }
         }
         if (last) store_pending = false;
@@ -420,9 +491,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // the peer may still be signalling this CTA's barriers / reading its operands
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -501,8 +573,9 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_pairs = ((n_points + 127) / 128 + 1) / 2;
-  const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
+  const long long n_quads = ((n_points + 127) / 128 + 3) / 4;
+  const long long max_pairs = sms / 2;
+  const unsigned grid = 2u * (unsigned)(n_quads < max_pairs ? n_quads : max_pairs);   // whole CTA pairs
   if (mask_bf16 != nullptr)
     fused_mlp_kernel<true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
   else

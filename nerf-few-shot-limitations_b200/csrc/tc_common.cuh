@@ -44,6 +44,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Same, for warps whose wake-up latency is not critical (epilogue / producer warps that share a
+// scheduler with the single MMA-issuing thread): back off between polls so that the pollers do not
+// take issue slots from the MMA thread.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(40);
+    if (spin > (1u << 24)) {
+      printf("nfs_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {

@@ -29,23 +29,23 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(576, 1)
+mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles, int rotate) {
   extern __shared__ uint8_t raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *sa = smem, *sb = smem + 16384;           // A: [128 x 64], B half: [N/2 x 64]
-  uint64_t *bar = (uint64_t *)(sb + 16384);
-  uint32_t *slot = (uint32_t *)(bar + 1);
+  uint8_t *sa = smem, *sb = smem + 131072;          // A: [128 x 64], B half: [N/2 x 64]
+  uint64_t *bar = (uint64_t *)(smem + 131072 + 98304);
+  uint32_t *slot = (uint32_t *)(bar + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = cluster_rank();
   const int nh = N / 2;
-  for (int i = tid; i < 128 * 8; i += 128) {
+  for (int i = tid; i < 128 * 8; i += blockDim.x) {
     const int r = i >> 3, c = i & 7;
     __nv_bfloat16 v[8];
     for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(a_val(r + 128 * (int)rank, c * 8 + j));
     *(uint4 *)(sa + r * 128 + ((c ^ (r & 7)) << 4)) = *(uint4 *)v;
   }
-  for (int i = tid; i < nh * 8; i += 128) {
+  for (int i = tid; i < nh * 8; i += blockDim.x) {
     const int r = i >> 3, c = i & 7;
     __nv_bfloat16 v[8];
     for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(b_val(r + nh * (int)rank, c * 8 + j));
@@ -54,6 +54,8 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 2)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 3)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -73,13 +75,35 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles) {
     for (int it = 0; it < iters; ++it)
       for (int k = 0; k < 4; ++k) {
         const uint32_t acc = (uint32_t)((it | k) != 0);
+        if (rotate == 3 && k == 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (rotate == 4 && k == 0) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(smem_u32(bar + 3)), "r"(1) : "memory");
+          if (!ok) __trap();
+        }
+        const uint32_t a_off = rotate == 1 ? (uint32_t)(it % 8) * 16384u : 0u;
+        const uint32_t b_off = rotate == 1 ? (uint32_t)(it % 6) * 16384u : 0u;
+        const uint32_t d_off = rotate == 1 ? (uint32_t)((it / 4) & 1) * 256u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(tbase), "l"(desc_sw128(smem_u32(sa) + k * 32)), "l"(desc_sw128(smem_u32(sb) + k * 32)), "r"(idesc), "r"(acc)
+                     ::"r"(tbase + d_off), "l"(desc_sw128(smem_u32(smem) + a_off + k * 32)), "l"(desc_sw128(smem_u32(smem) + 131072u + b_off + k * 32)), "r"(idesc), "r"(acc)
                      : "memory");
+        if (rotate == 2 && k == 3)
+          asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                       ::"r"(smem_u32(bar + 2)), "h"((uint16_t)3) : "memory");
       }
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  }
+  if (rotate >= 5 && warp >= 4) {   // pollers: spin on the local barrier like the chain kernel's epilogue warps
+    uint32_t ok = 0; unsigned spin = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(bar)), "r"(0) : "memory");
+      if (rotate == 6 && !ok) __nanosleep(40);
+      if (++spin > (1u << 26)) { __trap(); }
+    }
   }
   if (tid == 0) {        // both CTAs: wait for the multicast commit on the local barrier
     uint32_t ok = 0; unsigned spin = 0;
@@ -92,7 +116,7 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles) {
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (d_out != nullptr && blockIdx.x < 2) {
+  if (d_out != nullptr && blockIdx.x < 2 && warp < 4) {
     for (int c0 = 0; c0 < N; c0 += 8) {
       uint32_t r[8];
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -111,12 +135,12 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles) {
 int main() {
   float *d_out; unsigned long long *cyc;
   cudaMalloc(&d_out, 256 * 256 * 4); cudaMalloc(&cyc, 148 * 8);
-  const int smem = 1024 + 16384 + 16384 + 64;
+  const int smem = 1024 + 131072 + 98304 + 64;
   cudaFuncSetAttribute(mma2_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   float *h = (float *)malloc(256 * 256 * 4);
   for (int N : {256, 128, 64}) {
     cudaMemset(d_out, 0, 256 * 256 * 4);
-    mma2_bench<<<2, 128, smem>>>(N, 1, d_out, cyc);
+    mma2_bench<<<2, 576, smem>>>(N, 1, d_out, cyc, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("N %d: error %s\n", N, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, d_out, 256 * 256 * 4, cudaMemcpyDeviceToHost);
@@ -130,14 +154,16 @@ int main() {
         if (err > 1e-3 && bad++ < 4) printf("   mismatch r %d n %d got %f ref %f\n", r, n, h[r * 256 + n], ref);
       }
     const int iters = 4000;
-    mma2_bench<<<148, 128, smem>>>(N, iters, nullptr, cyc);
+  for (int rotate : {0, 5, 6}) {
+    mma2_bench<<<148, 576, smem>>>(N, iters, nullptr, cyc, rotate);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("N %d: error %s\n", N, cudaGetErrorString(e)); return 1; }
     unsigned long long hc[74];
     cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
     unsigned long long mx = 0; for (int i = 0; i < 74; ++i) if (hc[i] > mx) mx = hc[i];
-    printf("2-CTA SS N=%3d: max|D-ref| = %g (%d bad); %.1f cycles per MMA (M256 x N x K16), %.0f flop/cyc/SM\n", N, maxerr, bad,
+    printf("2-CTA SS N=%3d rotate=%d: max|D-ref| = %g (%d bad); %.1f cycles per MMA (M256 x N x K16), %.0f flop/cyc/SM\n", N, rotate, maxerr, bad,
            (double)mx / (iters * 4.0), 2.0 * 256 * N * 16 * iters * 4.0 / (double)mx / 2.0);
+  }
   }
   return 0;
 }
