@@ -216,11 +216,14 @@ int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
  *   the per-point attention gates of dino_feature_model.py:191-192, read at scale_*[p*scale_stride]
  *   (stride 2 = the two columns of the (P,2) softmax output).  Rows are written at
  *   out + p*out_pitch (0 = k_pad), so the block can be a column range of a wider operand.
+ *   pow2_bands != 0 asserts freqs[k] == freqs[0] * 2^k (the log-sampled bands both reference encoders
+ *   use by default): sin/cos of the higher octaves then come from the double-angle recurrence
+ *   (error <= ~2e-4 at 12 octaves, below the bf16 rounding of the output) instead of 2L sincosf.
  * ------------------------------------------------------------------------- */
 int nfs_posenc_bf16(const float *x, const float *freqs, const float *extra,
                     const float *scale_enc, const float *scale_extra, int32_t scale_stride,
                     int64_t n_points, int32_t dim, int32_t n_freqs, int32_t extra_dim,
-                    int32_t k_pad, int64_t out_pitch, void *out_bf16, void *stream);
+                    int32_t k_pad, int64_t out_pitch, int32_t pow2_bands, void *out_bf16, void *stream);
 
 /* Backward of that gate: dc_bf16 (P rows, pitch dc_pitch) = dL/dc' for c' = [enc(x) g0 | extra g1],
  * gate (P,2) = softmax output -> dlogits_bf16 [P,n_pad] (columns 0..1, rest zero):

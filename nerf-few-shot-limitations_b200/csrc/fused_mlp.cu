@@ -130,13 +130,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return r;
 }
 // ReLU backward on a packed pair: keep v where the saved activation h (>= 0, output of a ReLU) is
-// non-zero.  min(h * 2^126, 1) is exactly 1.0 for every positive bf16 and 0 for +0.
+// non-zero: set.gt yields {1.0, 0.0} per half, one multiply applies it.
 __device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t v, uint32_t h) {
-  const uint32_t big = 0x7E807E80u;   // bf16x2 {2^126, 2^126}
-  const uint32_t one = 0x3F803F80u;   // bf16x2 {1, 1}
   uint32_t m, r;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(big));
-  asm("min.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(m), "r"(one));
+  asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(0u));
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(m));
   return r;
 }
@@ -386,14 +383,16 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           // ReLU-backward mask row (straight from HBM): issue the loads before blocking on the accumulator
           uint4 mk[8] = {};
           if (kMasked && act_l == 4 && tile < n_tiles) {
+            // this thread's 64 (or 32) mask values = 128 (64) contiguous bytes: 256-bit loads, one 32-byte sector each,
+            // not allocated in the (tiny, 228 KB of it is shared memory) L1
             const uint4 *mp = reinterpret_cast<const uint4 *>(a.mask + ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl + c0);
-            if (quarter == 64) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) mk[g] = __ldg(mp + g);
-            } else {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) mk[g] = __ldg(mp + g);
-            }
+            for (int g = 0; g < 4; ++g)
+              if (g < (quarter >> 4))
+                asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(mk[2 * g].x), "=r"(mk[2 * g].y), "=r"(mk[2 * g].z), "=r"(mk[2 * g].w),
+                               "=r"(mk[2 * g + 1].x), "=r"(mk[2 * g + 1].y), "=r"(mk[2 * g + 1].z), "=r"(mk[2 * g + 1].w)
+                             : "l"(mp + 2 * g));
           }
           mbar_wait_relaxed(acc_full + t, n_full[t] & 1);
           ++n_full[t];

@@ -21,7 +21,7 @@ constexpr int kEncTile = 64;   // points per CTA
 __global__ void __launch_bounds__(kEncThreads)
 posenc_bf16_kernel(const float *__restrict__ x, const float *__restrict__ freqs, const float *__restrict__ extra,
                    const float *__restrict__ scale_enc, const float *__restrict__ scale_extra, int scale_stride,
-                   long long n_points, int D, int L, int E, int k_pad, long long out_pitch,
+                   long long n_points, int D, int L, int E, int k_pad, long long out_pitch, int pow2_bands,
                    __nv_bfloat16 *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(s_raw);     // [kEncTile][k_pad]
@@ -34,6 +34,24 @@ posenc_bf16_kernel(const float *__restrict__ x, const float *__restrict__ freqs,
   __syncthreads();
 
   const int per_pt = L * D;
+  if (pow2_bands) {
+    // bands f_k = f_0 * 2^k (log sampling, positional_encoding.py:14 / nerf_mlp.py:14): one accurate sincosf per
+    // coordinate, then the double-angle recurrence.  Its error doubles per octave (~1e-7 * 2^k <= 2e-4 at
+    // L = 12), far below the bf16 rounding (4e-3) of the operand this kernel writes.
+    for (int t = threadIdx.x; t < np * D; t += kEncThreads) {
+      const int p = t / D, d = t - p * D;
+      float s, c;
+      sincosf(__fmul_rn(__ldg(x + (p0 + p) * D + d), __ldg(freqs)), &s, &c);
+      const float g = scale_enc ? __ldg(scale_enc + (p0 + p) * scale_stride) : 1.f;
+      __nv_bfloat16 *row = tile + p * k_pad + D + d;
+      for (int k = 0; k < L; ++k) {
+        row[2 * k * D] = __float2bfloat16_rn(s * g);
+        row[2 * k * D + D] = __float2bfloat16_rn(c * g);
+        const float s2 = 2.f * s * c, c2 = 1.f - 2.f * s * s;
+        s = s2; c = c2;
+      }
+    }
+  } else
   for (int t = threadIdx.x; t < np * per_pt; t += kEncThreads) {
     const int p = t / per_pt, r = t - p * per_pt;
     const int k = r / D, d = r - k * D;
@@ -180,8 +198,8 @@ using namespace nfs;
 
 extern "C" int nfs_posenc_bf16(const float *x, const float *freqs, const float *extra, const float *scale_enc,
                                const float *scale_extra, int32_t scale_stride, int64_t n_points, int32_t dim,
-                               int32_t n_freqs, int32_t extra_dim, int32_t k_pad, int64_t out_pitch, void *out_bf16,
-                               void *stream) {
+                               int32_t n_freqs, int32_t extra_dim, int32_t k_pad, int64_t out_pitch,
+                               int32_t pow2_bands, void *out_bf16, void *stream) {
   const char *fn = "nfs_posenc_bf16";
   if (n_points < 0 || dim <= 0 || n_freqs < 0 || extra_dim < 0) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
   if (n_points == 0) return 0;
@@ -199,7 +217,7 @@ extern "C" int nfs_posenc_bf16(const float *x, const float *freqs, const float *
   if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
   posenc_bf16_kernel<<<(unsigned)blocks, kEncThreads, smem, (cudaStream_t)stream>>>(
       x, freqs, extra_dim > 0 ? extra : nullptr, scale_enc, scale_extra, scale_stride, n_points, dim, n_freqs,
-      extra_dim, k_pad, out_pitch, (__nv_bfloat16 *)out_bf16);
+      extra_dim, k_pad, out_pitch, (pow2_bands != 0 && n_freqs > 1) ? 1 : 0, (__nv_bfloat16 *)out_bf16);
   return check_launch(fn);
 }
 

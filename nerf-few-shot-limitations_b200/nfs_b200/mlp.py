@@ -85,6 +85,21 @@ class PackedLinear:
 
 
 _freq_cache = {}
+_pow2_cache = {}
+
+
+def bands_are_octaves(freqs):
+    """True when freqs[k] == freqs[0] * 2^k exactly (decided once per table on the host; a table that lives
+    on the GPU is read back once)."""
+    key = (freqs.data_ptr(), freqs._version, int(freqs.numel()), str(freqs.device))
+    hit = _pow2_cache.get(key)
+    if hit is None:
+        f = freqs.detach().double().cpu()
+        hit = bool(f.numel() > 1 and torch.equal(f, f[0] * 2.0 ** torch.arange(f.numel(), dtype=torch.float64)))
+        if len(_pow2_cache) > 64:
+            _pow2_cache.clear()
+        _pow2_cache[key] = hit
+    return hit
 
 
 def freqs_on(device, freqs):
@@ -118,13 +133,14 @@ def encode_operand(x, freqs, k_pad, extra=None, gate=None, out=None):
         pitch = out.stride(0)
     if P:
         fr = None if freqs is None else freqs_on(x.device, freqs)
+        octaves = freqs is not None and bands_are_octaves(freqs)
         g0 = g1 = None
         if gate is not None:
             gate = ops._f32c(gate)
             g0, g1 = ptr(gate), ctypes.c_void_p(gate.data_ptr() + 4)
         with torch.cuda.device(x.device):
             _lib.call("nfs_posenc_bf16", ptr(x), ptr(fr), ptr(ops._f32c(extra)) if E else None, g0, g1, 2, P, D, L, E,
-                      k_pad, int(pitch), ptr(out), _stream())
+                      k_pad, int(pitch), int(octaves), ptr(out), _stream())
     return out
 
 
