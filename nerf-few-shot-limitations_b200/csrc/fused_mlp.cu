@@ -394,6 +394,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                "=r"(mk[2 * g + 1].x), "=r"(mk[2 * g + 1].y), "=r"(mk[2 * g + 1].z), "=r"(mk[2 * g + 1].w)
                              : "l"(mp + 2 * g));
           }
+          if (kMasked && l + 1 < L && a.act[l + 1] == 4 && tile < n_tiles) {
+            // the mask row of this tile's NEXT layer (two epilogue steps ahead): pull it from HBM into L2 now,
+            // so that the register loads above see L2 latency instead of DRAM latency
+            const __nv_bfloat16 *np = a.mask + ((long long)a.mask_idx[l + 1] * a.mask_rows + row) * a.N[l + 1] + cq * (a.N[l + 1] >> 2);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+          }
           mbar_wait_relaxed(acc_full + t, n_full[t] & 1);
           ++n_full[t];
           tc_fence_after();

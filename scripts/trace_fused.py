@@ -17,10 +17,17 @@ lib = _lib.load()
 keep = len(sys.argv) > 1 and sys.argv[1] == "save"
 flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 lib.nfs_set_debug_flags(flags)
-for _ in range(3): plan.run_forward_fused(x16, keep)
+bwd = len(sys.argv) > 1 and sys.argv[1] == "bwd"
+if bwd:
+    out, acts, save = plan.run_forward_fused(x16, True)
+    dy = torch.randn(P, 64, device=dev).to(torch.bfloat16)
+    run = lambda: plan.dgrad_chain_fused(dy, save, P)
+else:
+    run = lambda: plan.run_forward_fused(x16, keep)
+for _ in range(3): run()
 buf = torch.zeros(18 * 1024, dtype=torch.int64, device=dev)
 lib.nfs_set_debug_trace(buf.data_ptr())
-plan.run_forward_fused(x16, keep)
+run()
 torch.cuda.synchronize()
 lib.nfs_set_debug_trace(None)
 lib.nfs_set_debug_flags(0)
@@ -33,7 +40,7 @@ for w in range(18):
         ev.append((v >> 16, w, (v >> 12) & 15, (v >> 4) & 255, v & 15))
 ev.sort()
 t0 = ev[0][0]
-names = {6: "mma: slab 0 issued", 7: "mma: slab 1 issued", 8: "mma: slab 2 issued", 9: "mma: slab 3 issued", 10: "mma: w_full 0", 11: "mma: w_full 1", 12: "mma: w_full 2", 13: "mma: w_full 3", 1: "mma: tile ready", 2: "mma: commit acc", 3: "epi: acc_full seen", 4: "epi: math+sts done", 5: "epi: fenced"}
+names = {14: "epi: store-read wait done", 15: "epi: step begins (mask loads issued next)", 6: "mma: slab 0 issued", 7: "mma: slab 1 issued", 8: "mma: slab 2 issued", 9: "mma: slab 3 issued", 10: "mma: w_full 0", 11: "mma: w_full 1", 12: "mma: w_full 2", 13: "mma: w_full 3", 1: "mma: tile ready", 2: "mma: commit acc", 3: "epi: acc_full seen", 4: "epi: math+sts done", 5: "epi: fenced"}
 # second pair iteration (steady state): find the 2nd occurrence of (code 1, layer 0, tile 0)
 starts = [e for e in ev if e[2] == 1 and e[3] == 0 and e[4] == 0]
 lo = starts[2][0] if len(starts) > 3 else t0
