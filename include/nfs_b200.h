@@ -143,6 +143,22 @@ int nfs_sample_hierarchical(const float *rays_o, const float *rays_d,
                             void *stream);
 
 /* ------------------------------------------------------------------------- *
+ * K5 — feature-conditioning gather (the step before the conditioned MLP)
+ *   replaces utils.ray_utils.project_points_to_image           src/utils/ray_utils.py:176-210
+ *        and SpatialDINOFeatures.sample_features_at_points     src/models/dino_feature_model.py:114-148
+ *   points (P,3) world coordinates; pose_inv (4,4) row-major = inverse of the camera-to-world pose
+ *   (ray_utils.py:192); features (Hp,Wp,C) fp32 = the (1,Hp,Wp,C) feature map | NULL.
+ *     cam = [p,1] . pose_inv^T; x = cam_x / (cam_z + 1e-8) * focal + W/2 (y likewise with H);
+ *     points_2d = (x / W) * 2 - 1 ; depths = cam_z ; valid = cam_z > 0
+ *     sampled = F.grid_sample(features, points_2d, bilinear, zeros padding, align_corners=False)
+ *   Outputs (each optional): points_2d (P,2), depths (P), valid (P) bytes, sampled (P,C).
+ *   pose_inv == NULL: `points` already holds normalised image coordinates (P,2); only `sampled` is produced.
+ * ------------------------------------------------------------------------- */
+int nfs_project_gather(const float *points, const float *pose_inv, float focal, int32_t H, int32_t W,
+                       const float *features, int32_t Hp, int32_t Wp, int32_t C, int64_t n_points,
+                       float *points_2d, float *depths, unsigned char *valid, float *sampled, void *stream);
+
+/* ------------------------------------------------------------------------- *
  * K3 — NeRF MLP dense layers on tcgen05 tensor cores
  *   replaces the nn.Linear(+ReLU / sigmoid) chains of
  *     nerf_model.NeRFMLP.forward               src/models/nerf_model.py:16-24

@@ -11,6 +11,15 @@ import torch
 import torch.nn as nn
 
 from nfs_b200 import mlp_g3 as _g3
+from nfs_b200 import ops as _ops
+
+
+def sample_features_at_points(features, points_2d):
+    """The body of SpatialDINOFeatures.sample_features_at_points (dino_feature_model.py:114-148): bilinear
+    F.grid_sample (zeros padding, align_corners=False) of a (1, Hp, Wp, C) feature map at normalised points
+    (N,2) -> (N,C), as one kernel.  The class itself (a HuggingFace Dinov2 backbone, out of scope) can
+    forward its method here."""
+    return _ops.sample_features(features, points_2d)
 
 
 class NeRFDINOFusion(nn.Module):

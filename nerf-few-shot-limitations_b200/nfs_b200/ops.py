@@ -254,6 +254,65 @@ def sample_hierarchical(rays_o, rays_d, z_vals, weights, n_importance, u=None, c
     return pts, z_out
 
 
+# --------------------------------------------------------------------------- K5
+def project_gather(points_3d, pose, focal, H, W, features=None, want_projection=True):
+    """World points (...,3) -> (points_2d (...,2), depths (...), valid (...) bool[, sampled (...,C)]):
+    project_points_to_image (ray_utils.py:176-210) and, when `features` (1|B=1,Hp,Wp,C) is given, the
+    bilinear feature lookup of sample_features_at_points (dino_feature_model.py:114-148) in the same
+    kernel.  The 4x4 inverse is torch.inverse on the device, like the reference (ray_utils.py:192)."""
+    _need_cuda("project_gather", points_3d, pose, features)
+    lead = points_3d.shape[:-1]
+    if points_3d.shape[-1] != 3 or pose.shape != (4, 4):
+        raise RuntimeError("project_gather: points must be (...,3) and pose (4,4)")
+    pts = _f32c(points_3d).reshape(-1, 3)
+    P = pts.shape[0]
+    dev = pts.device
+    pose_inv = torch.inverse(_f32c(pose)).contiguous()
+    feat = None
+    Hp = Wp = C = 0
+    if features is not None:
+        if features.dim() == 4:
+            if features.shape[0] != 1:
+                raise RuntimeError("project_gather: one feature map per call (batch 1), got %s" % (tuple(features.shape),))
+            features = features[0]
+        if features.dim() != 3:
+            raise RuntimeError("project_gather: features must be (1,Hp,Wp,C) or (Hp,Wp,C)")
+        feat = _f32c(features)
+        Hp, Wp, C = feat.shape
+    p2d = torch.empty((P, 2), device=dev, dtype=torch.float32) if want_projection else None
+    depth = torch.empty((P,), device=dev, dtype=torch.float32) if want_projection else None
+    valid = torch.empty((P,), device=dev, dtype=torch.uint8)
+    sampled = torch.empty((P, C), device=dev, dtype=torch.float32) if feat is not None else None
+    if P:
+        with torch.cuda.device(dev):
+            _lib.call("nfs_project_gather", ptr(pts), ptr(pose_inv), float(focal), int(H), int(W), ptr(feat), Hp, Wp, C,
+                      P, ptr(p2d), ptr(depth), ptr(valid), ptr(sampled), _stream())
+    out = (p2d.reshape(*lead, 2) if want_projection else None, depth.reshape(lead) if want_projection else None,
+           valid.bool().reshape(lead))
+    if feat is not None:
+        out = out + (sampled.reshape(*lead, C),)
+    return out
+
+
+def sample_features(features, points_2d):
+    """F.grid_sample(bilinear, zeros, align_corners=False) of a (1,Hp,Wp,C) map at normalised points (N,2)
+    (dino_feature_model.py:114-148) -> (N,C): the lookup half of project_gather for callers that already
+    hold points_2d."""
+    _need_cuda("sample_features", features, points_2d)
+    if features.dim() != 4 or features.shape[0] != 1 or points_2d.dim() != 2 or points_2d.shape[-1] != 2:
+        raise RuntimeError("sample_features: features (1,Hp,Wp,C), points_2d (N,2)")
+    N = points_2d.shape[0]
+    pts = _f32c(points_2d)
+    feat = _f32c(features[0])
+    Hp, Wp, C = feat.shape
+    sampled = torch.empty((N, C), device=pts.device, dtype=torch.float32)
+    if N:
+        with torch.cuda.device(pts.device):
+            _lib.call("nfs_project_gather", ptr(pts), None, 1.0, 2, 2, ptr(feat), Hp, Wp, C, N, None, None, None,
+                      ptr(sampled), _stream())
+    return sampled
+
+
 # --------------------------------------------------------------------------- K3 building blocks
 def _bf16c(t):
     if t is None:

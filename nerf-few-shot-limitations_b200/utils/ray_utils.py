@@ -61,14 +61,6 @@ def get_ray_batch(rays_o, rays_d, batch_size=1024):
 
 def project_points_to_image(points_3d, pose, focal, H, W):
     """World points -> normalised [-1,1] image coordinates, camera depth, in-front mask
-    (ray_utils.py:176-210).  Section 8f rank-1 'next' row: kept as the reference's torch
-    arithmetic until it is fused into the feature-gather producer of the G3 MLP."""
-    pose_inv = torch.inverse(pose)
-    points_homo = torch.cat([points_3d, torch.ones_like(points_3d[..., :1])], dim=-1)
-    points_cam = torch.matmul(points_homo, pose_inv.T)[..., :3]
-    valid_mask = points_cam[..., 2] > 0
-    x = points_cam[..., 0] / (points_cam[..., 2] + 1e-8) * focal + W / 2
-    y = points_cam[..., 1] / (points_cam[..., 2] + 1e-8) * focal + H / 2
-    x_norm = (x / W) * 2 - 1
-    y_norm = (y / H) * 2 - 1
-    return torch.stack([x_norm, y_norm], dim=-1), points_cam[..., 2], valid_mask
+    (ray_utils.py:176-210) as one kernel (nfs_project_gather); nfs_b200.ops.project_gather also does the
+    bilinear feature lookup that follows it in the callers (train.py:212-221) in the same pass."""
+    return _ops.project_gather(points_3d, pose, focal, H, W)

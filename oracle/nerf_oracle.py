@@ -271,6 +271,29 @@ def nerf_loss(pred, target, rgb_weight=1.0, depth_weight=0.1, reg_weight=0.01):
     return out
 
 
+# ----------------------------------------------------------------------------- 8f rank 1
+def project_points(points_3d, pose, focal, H, W):
+    """utils.ray_utils.project_points_to_image, src/utils/ray_utils.py:176-210."""
+    pose_inv = torch.inverse(pose)                                                         # :192
+    homo = torch.cat([points_3d, torch.ones_like(points_3d[..., :1])], dim=-1)             # :193
+    cam = torch.matmul(homo, pose_inv.T)[..., :3]                                          # :194
+    valid = cam[..., 2] > 0                                                                # :198
+    x = cam[..., 0] / (cam[..., 2] + 1e-8) * focal + W / 2                                 # :201
+    y = cam[..., 1] / (cam[..., 2] + 1e-8) * focal + H / 2                                 # :202
+    return torch.stack([(x / W) * 2 - 1, (y / H) * 2 - 1], dim=-1), cam[..., 2], valid     # :205-210
+
+
+def sample_features(features, points_2d):
+    """SpatialDINOFeatures.sample_features_at_points, src/models/dino_feature_model.py:114-148:
+    features (B,Hp,Wp,C), points_2d (N,2) -> (N,C) for B == 1."""
+    B = features.shape[0]
+    grid = points_2d.unsqueeze(0).unsqueeze(2).expand(B, -1, 1, -1)                        # :131-132
+    out = F.grid_sample(features.permute(0, 3, 1, 2), grid, mode="bilinear", padding_mode="zeros",
+                        align_corners=False)                                               # :135-140
+    out = out.squeeze(-1).permute(0, 2, 1)                                                 # :143
+    return out.squeeze(0) if B == 1 else out                                               # :145-148
+
+
 # ----------------------------------------------------------------------------- synthetic rays
 def pose_spherical(theta_deg, phi_deg, radius):
     """Blender-style camera-to-world looking at the origin."""

@@ -201,6 +201,33 @@ def mlp_cases():
     save("mlp", cases)
 
 
+def gather_cases():
+    """project_points_to_image + SpatialDINOFeatures.sample_features_at_points (the method body is pure
+    torch; it is called unbound on a stand-in object so that no Dinov2 weights are needed)."""
+    from models.dino_feature_model import SpatialDINOFeatures
+    gen = torch.Generator().manual_seed(707)
+    import math
+
+    class _Self:
+        pass
+
+    cases = []
+    for (n, hw, hp, c, spread) in [(257, 128, 9, 64, 1.0), (100, 100, 7, 32, 3.0), (64, 800, 16, 128, 0.5)]:
+        th = float(torch.rand((), generator=gen)) * 2 * math.pi
+        pose = torch.eye(4)
+        pose[:3, :3] = torch.tensor([[math.cos(th), 0, math.sin(th)], [0, 1, 0], [-math.sin(th), 0, math.cos(th)]])
+        pose[:3, 3] = torch.tensor([0.3, -0.2, 4.0])
+        focal = 0.5 * hw / math.tan(0.5 * 0.6911112)
+        pts = (torch.rand(n, 3, generator=gen) - 0.5) * 2 * spread
+        pts[::7] += torch.tensor([0.0, 0.0, 9.0])          # some points behind the camera / far outside the image
+        feats = torch.randn(1, hp, hp, c, generator=gen)
+        p2d, depth, valid = ray_utils.project_points_to_image(pts, pose, focal, hw, hw)
+        sampled = SpatialDINOFeatures.sample_features_at_points(_Self(), feats, p2d)
+        cases.append(dict(points=pts, pose=pose, focal=focal, H=hw, W=hw, features=feats, points_2d=p2d, depths=depth,
+                          valid=valid, sampled=sampled))
+    save("gather", cases)
+
+
 def loss_cases():
     gen = torch.Generator().manual_seed(707)
     pred = dict(rgb=torch.rand(50, 3, generator=gen), depth=torch.rand(50, generator=gen) * 6,
@@ -220,3 +247,4 @@ if __name__ == "__main__":
     hierarchical_cases()
     mlp_cases()
     loss_cases()
+    gather_cases()

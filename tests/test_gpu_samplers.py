@@ -150,3 +150,43 @@ def test_posenc_golden_and_live(golden, cuda):
     assert bit_equal(out[:, :3], x)
     assert PE3(10)(x[:0].to(cuda)).shape == (0, 63)
     assert "freq_bands" in PE4(4).state_dict() and "freq_bands" not in PE3(4).state_dict()
+
+
+def test_project_gather_golden_and_live(golden, cuda):
+    """K5 (8f rank 1): world points -> image coordinates -> bilinear feature lookup in one kernel, against the
+    reference-generated fixture and the oracle on a larger live case.  Tolerances: coordinates / depths
+    1e-5 relative to the coordinate scale (the reference's matmul sums in another order), the in-front mask
+    exact away from cam_z = 0, sampled features 1e-4 absolute (a coordinate error of 1e-6 moves a bilinear
+    tap weight by the same amount; feature values are O(1))."""
+    from nfs_b200 import ops
+    from models.dino_feature_model import sample_features_at_points
+    from utils.ray_utils import project_points_to_image
+    from oracle import nerf_oracle as O
+    for c in golden("gather"):
+        p2d, depth, valid, sampled = ops.project_gather(c["points"].to(cuda), c["pose"].to(cuda), c["focal"], c["H"],
+                                                        c["W"], features=c["features"].to(cuda))
+        scale = max(1.0, float(c["points_2d"].abs().max()))
+        assert float((p2d.cpu() - c["points_2d"]).abs().max()) <= 1e-5 * scale
+        assert float((depth.cpu() - c["depths"]).abs().max()) <= 1e-5
+        safe = c["depths"].abs() > 1e-4
+        assert torch.equal(valid.cpu()[safe], c["valid"][safe])
+        assert float((sampled.cpu() - c["sampled"]).abs().max()) <= 1e-4 * max(1.0, scale)
+        # the two reference entry points separately
+        q2d, qd, qv = project_points_to_image(c["points"].to(cuda), c["pose"].to(cuda), c["focal"], c["H"], c["W"])
+        assert torch.equal(q2d, p2d) and torch.equal(qd, depth) and torch.equal(qv, valid)
+        s2 = sample_features_at_points(c["features"].to(cuda), c["points_2d"].to(cuda))
+        assert float((s2.cpu() - c["sampled"]).abs().max()) <= 1e-5
+    g = torch.Generator().manual_seed(5)
+    P = 40000
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 3
+    pose = torch.eye(4); pose[2, 3] = 4.0
+    feats = torch.randn(1, 9, 9, 64, generator=g)
+    r2d, rdp, rv = O.project_points(pts, pose, 180.0, 128, 128)
+    rs = O.sample_features(feats, r2d)
+    p2d, depth, valid, sampled = ops.project_gather(pts.to(cuda), pose.to(cuda), 180.0, 128, 128, features=feats.to(cuda))
+    assert float((p2d.cpu() - r2d).abs().max()) <= 1e-5 and torch.equal(valid.cpu(), rv)
+    assert float((sampled.cpu() - rs).abs().max()) <= 1e-4
+    e2d, ed, ev = ops.project_gather(torch.zeros(0, 3, device=cuda), pose.to(cuda), 180.0, 128, 128)
+    assert e2d.shape == (0, 2) and ev.shape == (0,)
+    with pytest.raises(RuntimeError):
+        ops.project_gather(pts, pose, 180.0, 128, 128)            # CPU tensors: no fallback

@@ -123,3 +123,14 @@ def test_loss(golden):
     only = O.nerf_loss({"rgb": c["pred"]["rgb"]}, {"rgb": c["target"]["rgb"]}, 2.0, 0.5, 0.1)
     for k, v in c["rgb_only"].items():
         assert close(only[k], v), k
+
+
+def test_project_and_sample_features(golden):
+    """8f rank 1: project_points_to_image + sample_features_at_points against the reference's outputs."""
+    for c in golden("gather"):
+        p2d, depth, valid = O.project_points(c["points"], c["pose"], c["focal"], c["H"], c["W"])
+        assert torch.equal(valid, c["valid"])
+        assert float((p2d - c["points_2d"]).abs().max()) <= 1e-5 * max(1.0, float(c["points_2d"].abs().max()))
+        assert float((depth - c["depths"]).abs().max()) <= 1e-6
+        sampled = O.sample_features(c["features"], c["points_2d"])
+        assert float((sampled - c["sampled"]).abs().max()) <= 1e-6
