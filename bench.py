@@ -245,6 +245,38 @@ def measure_extras(dev, rank, world, dist, quick):
         "frac_of_bf16_sustained_peak": n * flop_ray / (ms * 1e-3) / 1e12 / bf16_peak(),
         "allreduce": "nccl sum of %d fp32 gradients per step" % opt.flat.numel() if world > 1 else "none (1 GPU)",
         "launch": "CUDA graph replay"}}
+    # cfg 4: DINO-NeRF (experiments/dino_nerf.yaml): NeRFWithDINO, pos_freq 12, 64-d feature map (random values
+    # stand in for the frozen Dinov2 + projection head, which is per-view preprocessing), batch 512 rays x 64
+    # samples, projection + bilinear feature lookup + MLP + compositing, forward + backward + Adam, graph replay
+    try:
+        from models.nerf_mlp import NeRFWithDINO
+        torch.manual_seed(1)
+        g3 = NeRFWithDINO(pos_freq=12, dir_freq=4, dino_dim=64).to(dev).train()
+        opt3 = FusedAdam(g3.parameters(), lr=5e-4)
+        nb = 512
+        ro4, rd4 = lego_rays(nb, H=128, W=128, seed=200 + rank)
+        ro4, rd4 = ro4.to(dev), rd4.to(dev)
+        tgt4 = torch.rand(nb, 3, device=dev)
+        fmap = torch.randn(1, 9, 9, 64, device=dev)
+        pose4 = torch.eye(4, device=dev)
+        pose4[2, 3] = 4.0
+        focal4 = 0.5 * 128 / math.tan(0.5 * 0.6911112)
+        pose4_inv = torch.inverse(pose4)             # per view, outside the captured step
+
+        def loss4():
+            o = pipeline.render_rays_conditioned(g3, ro4, rd4, 2.0, 6.0, 64, pose4, focal4, 128, 128, fmap, perturb=True,
+                                                 pose_inv=pose4_inv)
+            return torch.mean((o["rgb"] - tgt4) ** 2)
+
+        step4 = pipeline.GraphedStep(opt3, loss4, loss_scale=1.0 / world, allreduce=allreduce)
+        ms4 = timed(step4.replay, reps, 3)
+        flop4 = 64 * 5.51e6                          # ~5.51 MFLOP per point for G3 training
+        out["dino_nerf_cfg4"] = {
+            "rays_per_s": world * nb / (ms4 * 1e-3), "ms_per_step": ms4, "rays_per_gpu": nb, "points_per_step": nb * 64,
+            "tflops_per_gpu": nb * flop4 / (ms4 * 1e-3) / 1e12, "launch": "CUDA graph replay",
+            "note": "batch 512 x 64 samples = 32768 points per step: latency-bound, ~230 kernels per step"}
+    except Exception as e:
+        out["dino_nerf_cfg4"] = {"error": repr(e)[:300]}
     # render: this rank's contiguous share of the 640 000 rays of one 800 x 800 frame
     total = 640000
     lo, hi = nd.shard_range(total, rank, world)

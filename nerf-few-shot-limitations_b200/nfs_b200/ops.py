@@ -255,11 +255,12 @@ def sample_hierarchical(rays_o, rays_d, z_vals, weights, n_importance, u=None, c
 
 
 # --------------------------------------------------------------------------- K5
-def project_gather(points_3d, pose, focal, H, W, features=None, want_projection=True):
+def project_gather(points_3d, pose, focal, H, W, features=None, want_projection=True, pose_inv=None):
     """World points (...,3) -> (points_2d (...,2), depths (...), valid (...) bool[, sampled (...,C)]):
     project_points_to_image (ray_utils.py:176-210) and, when `features` (1|B=1,Hp,Wp,C) is given, the
     bilinear feature lookup of sample_features_at_points (dino_feature_model.py:114-148) in the same
-    kernel.  The 4x4 inverse is torch.inverse on the device, like the reference (ray_utils.py:192)."""
+    kernel.  The 4x4 inverse is torch.inverse on the device, like the reference (ray_utils.py:192); callers
+    that reuse a view pass `pose_inv` (torch.inverse synchronises, which a CUDA-graph capture cannot)."""
     _need_cuda("project_gather", points_3d, pose, features)
     lead = points_3d.shape[:-1]
     if points_3d.shape[-1] != 3 or pose.shape != (4, 4):
@@ -267,7 +268,7 @@ def project_gather(points_3d, pose, focal, H, W, features=None, want_projection=
     pts = _f32c(points_3d).reshape(-1, 3)
     P = pts.shape[0]
     dev = pts.device
-    pose_inv = torch.inverse(_f32c(pose)).contiguous()
+    pose_inv = torch.inverse(_f32c(pose)).contiguous() if pose_inv is None else _f32c(pose_inv)
     feat = None
     Hp = Wp = C = 0
     if features is not None:

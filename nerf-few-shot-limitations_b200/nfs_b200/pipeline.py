@@ -76,31 +76,44 @@ def render_image(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_im
     return torch.cat(outs, 0) if outs else rays_o.new_zeros((0, 3))
 
 
-class GraphedTrainStep:
-    """train_step captured once into CUDA graphs and replayed: ~140 kernel launches per step
-    (samplers, operand packing, MLP chains, wgrads, compositing, loss, fused Adam) become one
+def render_rays_conditioned(model, rays_o, rays_d, near, far, n_samples, pose, focal, H, W, feature_map,
+                            perturb=True, white_bkgd=False, t_rand=None, pose_inv=None):
+    """NeRFDINOTrainer.render_rays with use_dino (train.py:188-242, BASELINE config 4): stratified samples ->
+    projection onto the source view + bilinear feature lookup (one kernel) -> NeRFWithDINO -> compositing.
+    model: models.nerf_mlp.NeRFWithDINO; feature_map (1,Hp,Wp,C) precomputed for the view; pose (4,4)."""
+    N = rays_o.shape[0]
+    if perturb and t_rand is None:
+        t_rand = torch.rand(N, n_samples, device=rays_o.device)
+    pts, z = ops.sample_stratified(rays_o, rays_d, near, far, n_samples, t_rand=t_rand if perturb else None)
+    pts_flat = pts.reshape(-1, 3)
+    _, _, _, feats = ops.project_gather(pts_flat, pose, focal, H, W, features=feature_map, want_projection=False,
+                                        pose_inv=pose_inv)
+    dirs = rays_d.unsqueeze(1).expand(-1, n_samples, -1).reshape(-1, 3)          # train.py:225
+    rgb, density = model(pts_flat, dirs, feats)
+    rgb_map, depth, weights = ops.composite(rgb.reshape(N, n_samples, 3), density.reshape(N, n_samples, 1), z, rays_d,
+                                            white_bkgd=white_bkgd)
+    return {"rgb": rgb_map, "depth": depth, "weights": weights, "z_vals": z}
+
+
+class GraphedStep:
+    """An optimisation step captured once into CUDA graphs and replayed: every launch of
+    `loss_closure()` (render + loss), its backward, the gradient flattening and the fused Adam become one
     cudaGraphLaunch, so the step is paced by the GPU instead of by Python / launch latency.
 
-    Everything the step reads is static: rays and targets are copied into fixed buffers, the
-    Adam step count and learning rate live on the device (nfs_adam_step_dev), the uniform draws
-    come from torch's graph-safe generator.  With `allreduce` (data parallel) the step is two graphs
-    with the gradient all-reduce between them: [render + backward + gradient flattening] -> NCCL
-    all-reduce of the flat buffer -> [Adam]."""
+    Everything the step reads must be static: the closure reads fixed device buffers (the caller copies new
+    inputs into them before calling), the Adam step count and learning rate live on the device
+    (nfs_adam_step_dev), uniform draws come from torch's graph-safe generator.  With `allreduce` (data
+    parallel) the step is two graphs with the gradient all-reduce between them:
+    [render + backward + gradient flattening] -> NCCL all-reduce of the flat buffer -> [Adam]."""
 
-    def __init__(self, model, optimizer, freq_bands, n_rays, near, far, n_coarse=64, n_importance=128,
-                 perturb=True, loss_scale=1.0, allreduce=None, warmup=3):
+    def __init__(self, optimizer, loss_closure, loss_scale=1.0, allreduce=None, warmup=3):
         from . import mlp
         if not hasattr(optimizer, "gather_grads"):
-            raise RuntimeError("GraphedTrainStep needs nfs_b200.optim.FusedAdam (device-resident optimizer state)")
-        self.model, self.opt, self.bands = model, optimizer, mlp.freqs_on(optimizer.flat.device, freq_bands)
-        self.cfg = (near, far, n_coarse, n_importance, perturb)
+            raise RuntimeError("GraphedStep needs nfs_b200.optim.FusedAdam (device-resident optimizer state)")
+        self.opt, self.closure = optimizer, loss_closure
         self.loss_scale, self.allreduce = float(loss_scale), allreduce
-        dev = optimizer.flat.device
-        self.rays_o = torch.zeros(n_rays, 3, device=dev)
-        self.rays_d = torch.zeros(n_rays, 3, device=dev)
-        self.rays_d[:, 2] = -1.0
-        self.target = torch.zeros(n_rays, 3, device=dev)
         o = optimizer
+        dev = o.flat.device
         snap = [t.clone() for t in (o.flat, o.exp_avg, o.exp_avg_sq, o._step_dev, o._state)]
         rng = torch.cuda.get_rng_state(dev)
         side = torch.cuda.Stream(device=dev)
@@ -129,12 +142,8 @@ class GraphedTrainStep:
         mlp.bump_weight_epoch()
 
     def _forward_backward(self):
-        near, far, n_coarse, n_importance, perturb = self.cfg
         self.opt.zero_grad()
-        out = render_rays(self.model, self.bands, self.rays_o, self.rays_d, near, far, n_coarse, n_importance, perturb)
-        loss = torch.mean((out["rgb"] - self.target) ** 2)
-        if n_importance > 0:
-            loss = loss + torch.mean((out["rgb_coarse"] - self.target) ** 2)
+        loss = self.closure()
         (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         self.opt.gather_grads()
         return loss.detach()
@@ -142,15 +151,44 @@ class GraphedTrainStep:
     def _update(self):
         self.opt.step(gathered=True)
 
-    def __call__(self, rays_o, rays_d, target):
-        """One optimisation step; returns the loss tensor of this step (static buffer, no host sync)."""
+    def replay(self):
+        """One optimisation step on whatever the static input buffers hold; returns the loss tensor of this
+        step (a static buffer, no host sync)."""
         from . import mlp
-        self.rays_o.copy_(rays_o, non_blocking=True)
-        self.rays_d.copy_(rays_d, non_blocking=True)
-        self.target.copy_(target, non_blocking=True)
         self.g_step.replay()
         if self.g_update is not None:
             self.allreduce(self.opt.grad)
             self.g_update.replay()
         mlp.bump_weight_epoch()      # the graph changed the fp32 masters: eager callers must repack
         return self.loss
+
+
+class GraphedTrainStep(GraphedStep):
+    """train_step (BASELINE config 3: coarse + fine render of the G1 model, MSE on both passes) as a
+    GraphedStep; rays and targets are copied into fixed buffers before each replay."""
+
+    def __init__(self, model, optimizer, freq_bands, n_rays, near, far, n_coarse=64, n_importance=128,
+                 perturb=True, loss_scale=1.0, allreduce=None, warmup=3):
+        from . import mlp
+        dev = optimizer.flat.device
+        self.model, self.bands = model, mlp.freqs_on(dev, freq_bands)
+        self.cfg = (near, far, n_coarse, n_importance, perturb)
+        self.rays_o = torch.zeros(n_rays, 3, device=dev)
+        self.rays_d = torch.zeros(n_rays, 3, device=dev)
+        self.rays_d[:, 2] = -1.0
+        self.target = torch.zeros(n_rays, 3, device=dev)
+        super().__init__(optimizer, self._loss, loss_scale=loss_scale, allreduce=allreduce, warmup=warmup)
+
+    def _loss(self):
+        near, far, n_coarse, n_importance, perturb = self.cfg
+        out = render_rays(self.model, self.bands, self.rays_o, self.rays_d, near, far, n_coarse, n_importance, perturb)
+        loss = torch.mean((out["rgb"] - self.target) ** 2)
+        if n_importance > 0:
+            loss = loss + torch.mean((out["rgb_coarse"] - self.target) ** 2)
+        return loss
+
+    def __call__(self, rays_o, rays_d, target):
+        self.rays_o.copy_(rays_o, non_blocking=True)
+        self.rays_d.copy_(rays_d, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        return self.replay()

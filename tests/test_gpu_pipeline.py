@@ -124,3 +124,40 @@ def test_graphed_train_step_matches_eager(cuda):
         assert abs(a - b) <= 2e-3 * abs(a), (losses["eager"], losses["graph"])      # wgrad atomics reorder fp32 sums
     assert float((finals["eager"] - finals["graph"]).abs().max()) <= 5e-3
     assert losses["graph"][-1] < losses["graph"][0] * 1.5
+
+
+def test_conditioned_render_vs_oracle(cuda):
+    """BASELINE config 4 path (train.py:188-242 with use_dino): sampler -> projection + feature lookup ->
+    NeRFWithDINO (pos_freq 12, 64-d features) -> compositing against the oracle chain on the same draws."""
+    import math
+    import bench
+    from models.nerf_mlp import NeRFWithDINO
+    from nfs_b200 import pipeline
+    from oracle import nerf_oracle as O
+    from helpers import record
+    N, S = 512, 64
+    ro, rd = bench.lego_rays(N, H=128, W=128, seed=2)
+    g = torch.Generator().manual_seed(4)
+    t_rand = torch.rand(N, S, generator=g)
+    feats = torch.randn(1, 9, 9, 64, generator=g)
+    pose = torch.eye(4); pose[:3, 3] = torch.tensor([0.2, -0.1, 4.0])
+    focal = 0.5 * 128 / math.tan(0.5 * 0.6911112)
+    torch.manual_seed(21)
+    ref = O.ConditionedNeRF(pos_freq=12, dino_dim=64)
+    mod = NeRFWithDINO(pos_freq=12, dino_dim=64)
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.to(cuda).eval()
+    # oracle chain
+    pts, z = O.stratified(ro, rd, 2.0, 6.0, S, t_rand=t_rand)
+    p2d, _, _ = O.project_points(pts.reshape(-1, 3), pose, focal, 128, 128)
+    f = O.sample_features(feats, p2d)
+    rgb, den = ref(pts.reshape(-1, 3), rd.unsqueeze(1).expand(-1, S, -1).reshape(-1, 3), f)
+    ref_out = O.render(rgb.reshape(N, S, 3), den.reshape(N, S, 1), z, rd)
+    with torch.no_grad():
+        out = pipeline.render_rays_conditioned(mod, ro.to(cuda), rd.to(cuda), 2.0, 6.0, S, pose.to(cuda), focal, 128, 128,
+                                               feats.to(cuda), perturb=True, t_rand=t_rand.to(cuda))
+    e_rgb = float((out["rgb"].cpu() - ref_out[0].detach()).abs().max())
+    e_depth = float((out["depth"].cpu() - ref_out[1].detach()).abs().max())
+    record("conditioned_pipeline_vs_oracle", rgb_abs=e_rgb, depth_abs=e_depth)
+    assert torch.equal(out["z_vals"].cpu(), z)
+    assert e_rgb <= 1e-2 and e_depth <= 5e-2, (e_rgb, e_depth)
