@@ -243,7 +243,9 @@ def measure_extras(dev, rank, world, dist, quick):
         "rays_per_s": world * n / (ms * 1e-3), "ms_per_step": ms, "rays_per_gpu": n,
         "tflops_per_gpu": n * flop_ray / (ms * 1e-3) / 1e12,
         "frac_of_bf16_sustained_peak": n * flop_ray / (ms * 1e-3) / 1e12 / bf16_peak(),
-        "allreduce": "nccl sum of %d fp32 gradients per step" % opt.flat.numel() if world > 1 else "none (1 GPU)",
+        "allreduce": ("nccl sum of %d fp32 gradients per step, %s" % (
+            opt.flat.numel(), "captured in the step's CUDA graph" if step.allreduce_in_graph else
+            "eager between two graphs")) if world > 1 else "none (1 GPU)",
         "launch": "CUDA graph replay"}}
     # cfg 4: DINO-NeRF (experiments/dino_nerf.yaml): NeRFWithDINO, pos_freq 12, 64-d feature map (random values
     # stand in for the frozen Dinov2 + projection head, which is per-view preprocessing), batch 512 rays x 64

@@ -126,6 +126,9 @@ class GraphedStep:
                 self._update()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # The all-reduce stays OUTSIDE the graphs: capturing the NCCL collective together with the step hung
+        # on a 2-GPU box (round 1), so data parallel runs [graph] -> eager all-reduce -> [graph].
+        self.allreduce_in_graph = False
         self.g_step = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_step):
             self.loss = self._forward_backward()
@@ -156,7 +159,7 @@ class GraphedStep:
         step (a static buffer, no host sync)."""
         from . import mlp
         self.g_step.replay()
-        if self.g_update is not None:
+        if self.g_update is not None:               # two-graph form: eager all-reduce between the graphs
             self.allreduce(self.opt.grad)
             self.g_update.replay()
         mlp.bump_weight_epoch()      # the graph changed the fp32 masters: eager callers must repack
