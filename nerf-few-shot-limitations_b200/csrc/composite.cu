@@ -385,6 +385,166 @@ __global__ void __launch_bounds__(kBlock, 5) composite_bwd_kernel(const Composit
   }
 }
 
+// ------------------------------- backward, staged ---------------------------
+// Same arithmetic as composite_bwd_kernel for the common case (row-major rgb / density / z, S <= 4G, 16-byte
+// aligned, no noise), with the loads decoupled from the compute: persistent blocks walk tiles of
+// kStageRays rays; one thread streams each tile's three (four with g_weights) contiguous input blocks into a
+// 3-stage shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx), the warps read
+// their samples from shared memory.  The long dependent chains of the backward (two shuffle scans, exp,
+// quotient) then never wait on DRAM latency, and ~40 KB of loads per block are always in flight.
+constexpr int kStageRays = 16;       // 8 warps x (32 / G) rays at G = 16; G = 8 -> 32, G = 32 -> 8 (see launch)
+constexpr int kBwdStages = 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+template <int G>
+__global__ void __launch_bounds__(kBlock, 4) composite_bwd_staged_kernel(const CompositeArgs a, const long long n_tiles) {
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int kRays = (kBlock / 32) * kGroupsPerWarp;          // rays per tile
+  extern __shared__ __align__(128) unsigned char s_stage[];
+  const int S = a.S;
+  const bool has_gw = a.g_w != nullptr;
+  const int stage_floats = kRays * S * (has_gw ? 6 : 5);          // rgb 3S | density S | z S | [g_w S] per ray
+  float *ring = reinterpret_cast<float *>(s_stage);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBwdStages * stage_floats);
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const int group_in_block = (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBwdStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int stage) {                    // thread 0 only
+    const long long r0 = tile * kRays;
+    const long long nr = (a.n_rays - r0) < kRays ? (a.n_rays - r0) : kRays;
+    const uint32_t row = (uint32_t)(nr * S * 4);
+    float *st = ring + stage * stage_floats;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(full + stage)),
+                 "r"(row * (has_gw ? 6u : 5u)) : "memory");
+    bulk_g2s(st, a.rgb + r0 * S * 3, row * 3, full + stage);
+    bulk_g2s(st + kRays * S * 3, a.density + r0 * S, row, full + stage);
+    bulk_g2s(st + kRays * S * 4, a.z + r0 * S, row, full + stage);
+    if (has_gw) bulk_g2s(st + kRays * S * 5, a.g_w + r0 * S, row, full + stage);
+  };
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBwdStages; ++i)
+      if (first + i * step < n_tiles) issue(first + i * step, i);
+
+  uint32_t it = 0;
+  for (long long tile = first; tile < n_tiles; tile += step, ++it) {
+    const int stage = it % kBwdStages;
+    const uint32_t parity = (it / kBwdStages) & 1;
+    const long long ray = tile * kRays + group_in_block;
+    const bool ray_ok = ray < a.n_rays;
+    // per-ray scalars straight from global memory (28 bytes per ray) while the tile lands
+    float dnorm = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
+    if (ray_ok) {
+      const float dx = __ldg(a.rays_d + ray * 3), dy = __ldg(a.rays_d + ray * 3 + 1), dz = __ldg(a.rays_d + ray * 3 + 2);
+      dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+      gr = __ldg(a.g_rgb + ray * 3); gg = __ldg(a.g_rgb + ray * 3 + 1); gb = __ldg(a.g_rgb + ray * 3 + 2);
+      if (a.g_depth != nullptr) gd = __ldg(a.g_depth + ray);
+    }
+    const float g_bg = a.white ? (gr + gg + gb) : 0.f;
+    {                                                               // wait for the tile
+      uint32_t ok = 0, spin = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(full + stage)), "r"(parity) : "memory");
+        if (++spin > (1u << 26)) { printf("nfs_b200: composite_bwd tile wait timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+      }
+    }
+    const float *st = ring + stage * stage_floats;
+    const int s0 = 4 * gl;
+    Lane4 v;
+    float gw_in[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v.z[j] = 0.f; v.sg[j] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v.col[j] = 0.f;
+    if (ray_ok && s0 < S) {
+      const int o = group_in_block * S + s0;
+      const float4 c0 = *reinterpret_cast<const float4 *>(st + o * 3);
+      const float4 c1 = *reinterpret_cast<const float4 *>(st + o * 3 + 4);
+      const float4 c2 = *reinterpret_cast<const float4 *>(st + o * 3 + 8);
+      const float4 dd = *reinterpret_cast<const float4 *>(st + kRays * S * 3 + o);
+      const float4 zz = *reinterpret_cast<const float4 *>(st + kRays * S * 4 + o);
+      v.col[0] = c0.x; v.col[1] = c0.y; v.col[2] = c0.z; v.col[3] = c0.w;
+      v.col[4] = c1.x; v.col[5] = c1.y; v.col[6] = c1.z; v.col[7] = c1.w;
+      v.col[8] = c2.x; v.col[9] = c2.y; v.col[10] = c2.z; v.col[11] = c2.w;
+      v.sg[0] = dd.x; v.sg[1] = dd.y; v.sg[2] = dd.z; v.sg[3] = dd.w;
+      v.z[0] = zz.x; v.z[1] = zz.y; v.z[2] = zz.z; v.z[3] = zz.w;
+      if (has_gw) {
+        const float4 t = *reinterpret_cast<const float4 *>(st + kRays * S * 5 + o);
+        gw_in[0] = t.x; gw_in[1] = t.y; gw_in[2] = t.z; gw_in[3] = t.w;
+      }
+    }
+    float zn = __shfl_down_sync(kFullMask, v.z[0], 1, G);          // single chunk: the last lane's successor
+    if (gl == G - 1) zn = 0.f;                                      // does not exist (its distance is 1e10)
+    Alpha4 al;
+    alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+
+    const float p1 = al.q[0], p2 = p1 * al.q[1], p3 = p2 * al.q[2], p4 = p3 * al.q[3];
+    float chunk_all;
+    const float tb = group_excl_prod<G>(p4, gl, chunk_all);
+    const float T[4] = {tb, tb * p1, tb * p2, tb * p3};
+    float w[4], Gi[4], gwk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = al.alpha[j] * T[j];
+      Gi[j] = gr * v.col[3 * j] + gg * v.col[3 * j + 1] + gb * v.col[3 * j + 2] + gd * v.z[j] + gw_in[j] - g_bg;
+      gwk[j] = Gi[j] * w[j];
+    }
+    const float e3 = 0.f, e2 = gwk[3], e1 = e2 + gwk[2], e0 = e1 + gwk[1];
+    float chunk_sum;
+    const float rb = group_excl_suffix_sum<G>(e0 + gwk[0], gl, chunk_sum);
+    const float R[4] = {rb + e0, rb + e1, rb + e2, rb + e3};
+    float ds[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dalpha = Gi[j] * T[j] - __fdividef(R[j], al.q[j]);
+      ds[j] = (v.sg[j] > 0.f) ? dalpha * al.dist[j] * al.e[j] : 0.f;
+    }
+    if (ray_ok && s0 < S) {
+      const long long base = ray * (long long)S + s0;
+      float *op = a.d_rgb + base * 3;
+      stg_stream4(op,     make_float4(w[0] * gr, w[0] * gg, w[0] * gb, w[1] * gr));
+      stg_stream4(op + 4, make_float4(w[1] * gg, w[1] * gb, w[2] * gr, w[2] * gg));
+      stg_stream4(op + 8, make_float4(w[2] * gb, w[3] * gr, w[3] * gg, w[3] * gb));
+      stg_stream4(a.d_density + base, make_float4(ds[0], ds[1], ds[2], ds[3]));
+    }
+    __syncthreads();                                                // everyone has read this stage
+    if (threadIdx.x == 0 && tile + kBwdStages * step < n_tiles) issue(tile + kBwdStages * step, stage);
+  }
+}
+
+template <int G>
+int launch_bwd_staged(const CompositeArgs &a, cudaStream_t st) {
+  constexpr int kRays = (kBlock / 32) * (32 / G);
+  const long long n_tiles = (a.n_rays + kRays - 1) / kRays;
+  const size_t smem = sizeof(float) * (size_t)kBwdStages * kRays * a.S * (a.g_w ? 6 : 5) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(composite_bwd_staged_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return fail_cuda("nfs_composite_bwd", e);
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long max_blocks = (long long)sms * 4;
+  const unsigned grid = (unsigned)(n_tiles < max_blocks ? n_tiles : max_blocks);
+  composite_bwd_staged_kernel<G><<<grid, kBlock, smem, st>>>(a, n_tiles);
+  return check_launch("nfs_composite_bwd");
+}
+
 // ------------------------------- dispatch -----------------------------------
 int pick_group(int S) { return S <= 32 ? 8 : (S <= 64 ? 16 : 32); }
 
@@ -412,6 +572,12 @@ int launch_bwd(const CompositeArgs &a, cudaStream_t st) {
 template <bool FWD>
 int dispatch(const CompositeArgs &a, bool aligned, bool packed, cudaStream_t st) {
   const int G = pick_group(a.S);
+  if (!FWD && aligned && !packed && a.noise == nullptr && a.S <= 4 * G &&
+      sizeof(float) * (size_t)kBwdStages * (kBlock / 32) * (32 / G) * a.S * (a.g_w ? 6 : 5) + 64 <= 96 * 1024) {
+    if (G == 8) return launch_bwd_staged<8>(a, st);
+    if (G == 16) return launch_bwd_staged<16>(a, st);
+    return launch_bwd_staged<32>(a, st);
+  }
 #define NFS_CASE(GV, AL, PK)                                                         \
   if (G == GV && aligned == AL && packed == PK)                                      \
     return FWD ? launch_fwd<GV, AL, PK>(a, st) : launch_bwd<GV, AL, PK>(a, st);
