@@ -194,6 +194,13 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s
   *reinterpret_cast<uint4 *>(srow + (((ch + 1) ^ r7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
+// Developer tools (bisection switches + timeline) are compiled in only with -DNFS_DEVTOOLS
+// (NFS_DEVTOOLS=1 python -m nfs_b200.build): they cost registers in a kernel that is short of them.
+#ifndef NFS_DEVTOOLS
+#define NFS_TRACE(code, l, t) do { } while (0)
+#define NFS_DBG(a) 0
+#else
+#define NFS_DBG(a) ((a).dbg)
 // Developer timeline: CTA 0 appends (clock << 16 | code << 12 | layer << 4 | tile) per warp.
 #define NFS_TRACE(code, l, t)                                                                       \
   do {                                                                                              \
@@ -203,6 +210,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s
       a.trace[warp * 1024] = trace_n;                                                               \
     }                                                                                               \
   } while (0)
+#endif
 
 template <bool kMasked>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFmThreads, 1)
@@ -284,7 +292,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
           for (int s = 0; s < ks; ++s, ++wit) {
             const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
-            if ((a.dbg & 2) && wit >= kWStages) continue;
+            if ((NFS_DBG(a) & 2) && wit >= kWStages) continue;
             mbar_wait_relaxed(w_empty + stage, ph ^ 1);
             if (rank == 0) mbar_expect_tx(w_full + stage, (uint32_t)(2 * nb * 8192));
             for (int b = 0; b < nb; ++b)
@@ -299,7 +307,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (rank == 0) {                 // all 32 lanes walk the (warp-uniform) schedule; one elected lane issues
       uint32_t wit = 0, iter = 0, n_ready[2] = {0, 0};
       const uint64_t b_desc0 = umma_desc_sw128(smem_u32(wring), 16, 1024);
-      const bool no_mma = (a.dbg & 4) != 0;
+      const bool no_mma = (NFS_DBG(a) & 4) != 0;
       for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
         // Issue order per layer: tile major - 4*ks MMAs on the pair's A tiles, then 4*ks on the B tiles.
         // Long runs on one accumulator (switching the D operand between consecutive MMAs costs
@@ -325,7 +333,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int s = 0; s < ks; ++s) {
               const uint32_t w = wit + s, stage = w % kWStages, wph = (w / kWStages) & 1;
               if (t == 0) {
-                if (!((a.dbg & 2) && w >= kWStages)) mbar_wait_cluster(w_full + stage, wph);
+                if (!((NFS_DBG(a) & 2) && w >= kWStages)) mbar_wait_cluster(w_full + stage, wph);
                 tc_fence_after();
               }
               const uint64_t ad = a_desc0 + (uint64_t)((s * kActSlab) >> 4);
@@ -417,7 +425,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             uint8_t *srow = act_t + (c0 >> 6) * kActSlab + r_in * 128;
             const int ch0 = (c0 & 63) >> 3;
-            if (a.dbg & 1) {
+            if (NFS_DBG(a) & 1) {
               // bisection: no TMEM drain, no math, no smem writes
             } else {
               // `quarter` (64 or 32) columns in chunks of 16 (small chunks leave registers for a whole chunk of
@@ -430,13 +438,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                   tmem_ld16_async(taddr + c0 + 16 * c, va);
                   tmem_ld_wait();
                   epi_chunk<kMasked>(va, bias ? bias + 16 * c : nullptr, act_l, mk[2 * c], mk[2 * c + 1],
-                                     srow, ch0 + 2 * c, r_in & 7, a.dbg);
+                                     srow, ch0 + 2 * c, r_in & 7, NFS_DBG(a));
                 }
               }
             }
             NFS_TRACE(4, l, t);
             tc_fence_before();
-            if (!(a.dbg & 16)) fence_proxy_async();   // generic-proxy smem writes -> visible to UMMA / TMA
+            if (!(NFS_DBG(a) & 16)) fence_proxy_async();   // generic-proxy smem writes -> visible to UMMA / TMA
             __syncwarp();
             NFS_TRACE(5, l, t);
             if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");

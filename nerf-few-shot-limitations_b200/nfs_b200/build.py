@@ -56,6 +56,8 @@ def build(force=False, verbose=False):
                "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if os.environ.get("NFS_DEVTOOLS", "0") not in ("", "0"):
+            cmd.insert(1, "-DNFS_DEVTOOLS")          # bisection switches + timeline tracer in the fused MLP kernel
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

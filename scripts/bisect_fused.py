@@ -2,6 +2,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "nerf-few-shot-limitations_b200")]
 import torch
+# needs the developer build of the library:  NFS_DEVTOOLS=1 python -m nfs_b200.build --force  (then rebuild
+# without it: the production kernel compiles the bisection switches and the tracer out)
 from nfs_b200 import _lib
 from models.nerf_model import NeRFMLP
 dev = torch.device("cuda:0")
