@@ -389,19 +389,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
           uint8_t *act_t = smem + t * kActBytes;
           // ReLU-backward mask row (straight from HBM): issue the loads before blocking on the accumulator
-          uint4 mk[8] = {};
-          if (kMasked && act_l == 4 && tile < n_tiles) {
-            // this thread's 64 (or 32) mask values = 128 (64) contiguous bytes: 256-bit loads, one 32-byte sector each,
-            // not allocated in the (tiny, 228 KB of it is shared memory) L1
-            const uint4 *mp = reinterpret_cast<const uint4 *>(a.mask + ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g < (quarter >> 4))
-                asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=r"(mk[2 * g].x), "=r"(mk[2 * g].y), "=r"(mk[2 * g].z), "=r"(mk[2 * g].w),
-                               "=r"(mk[2 * g + 1].x), "=r"(mk[2 * g + 1].y), "=r"(mk[2 * g + 1].z), "=r"(mk[2 * g + 1].w)
-                             : "l"(mp + 2 * g));
-          }
+          // ReLU-backward mask: this thread's row of the saved activation, 16 columns (32 bytes) per chunk, loaded
+          // one chunk ahead of its use with 256-bit no-allocate loads (the row was prefetched into L2 two epilogue
+          // steps ago); holding only two chunks keeps the kernel within its 96 registers
+          uint4 mk_cur[2] = {}, mk_nxt[2] = {};
+          const bool use_mask = kMasked && act_l == 4 && tile < n_tiles;
+          const uint4 *mp = reinterpret_cast<const uint4 *>(
+              a.mask + (use_mask ? ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl + c0 : 0));
+          auto load_mask = [&](uint4 (&dst)[2], int chunk) {
+            asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(dst[0].x), "=r"(dst[0].y), "=r"(dst[0].z), "=r"(dst[0].w),
+                           "=r"(dst[1].x), "=r"(dst[1].y), "=r"(dst[1].z), "=r"(dst[1].w)
+                         : "l"(mp + 2 * chunk));
+          };
+          if (use_mask) load_mask(mk_cur, 0);
           if (kMasked && l + 1 < L && a.act[l + 1] == 4 && tile < n_tiles) {
             // the mask row of this tile's NEXT layer (two epilogue steps ahead): pull it from HBM into L2 now,
             // so that the register loads above see L2 latency instead of DRAM latency
@@ -435,10 +436,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 if (c < n_chunks) {
+                  if (use_mask && c + 1 < n_chunks) load_mask(mk_nxt, c + 1);
                   tmem_ld16_async(taddr + c0 + 16 * c, va);
                   tmem_ld_wait();
-                  epi_chunk<kMasked>(va, bias ? bias + 16 * c : nullptr, act_l, mk[2 * c], mk[2 * c + 1],
+                  epi_chunk<kMasked>(va, bias ? bias + 16 * c : nullptr, act_l, mk_cur[0], mk_cur[1],
                                      srow, ch0 + 2 * c, r_in & 7, NFS_DBG(a));
+                  mk_cur[0] = mk_nxt[0]; mk_cur[1] = mk_nxt[1];
                 }
               }
             }
