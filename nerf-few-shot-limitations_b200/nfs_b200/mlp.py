@@ -17,6 +17,15 @@ from .ops import _stream
 
 
 _WEIGHT_EPOCH = 0
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One auxiliary stream per device for launches that may overlap the current stream's."""
+    key = str(dev)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def bump_weight_epoch():
@@ -308,12 +317,20 @@ class G1Plan:
         if save_fwd is not None and n_layers >= 2 and os.environ.get("NFS_MLP_FUSED_BWD", "1") != "0":
             P = out.shape[0]
             dys = self.dgrad_chain_fused(dy, save_fwd, P)
-            for i in range(n_layers - 1, 0, -1):
+            # the wgrad launches are independent of each other: alternate them between two streams so that one
+            # kernel's tail (SMs draining 256 KB of fp32 red.add each) overlaps the next kernel's ramp-up
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(main)
+            for n, i in enumerate(range(n_layers - 1, 0, -1)):
                 dyi = dys[n_layers - 1 - i, :P]
-                ops.wgrad_bf16(acts[i], dyi, views[2 * i], 1, hd, colsum=views[2 * i + 1], colsum_of_v=True,
-                               m_valid=hd, n_valid=hd)
-            ops.wgrad_bf16(dys[n_layers - 1, :P], acts[0], views[0], self.in_dim, 1, colsum=views[1],
-                           colsum_of_v=False, m_valid=hd, n_valid=self.in_dim)
+                with torch.cuda.stream(side if n & 1 else main):
+                    ops.wgrad_bf16(acts[i], dyi, views[2 * i], 1, hd, colsum=views[2 * i + 1], colsum_of_v=True,
+                                   m_valid=hd, n_valid=hd)
+            with torch.cuda.stream(side):
+                ops.wgrad_bf16(dys[n_layers - 1, :P], acts[0], views[0], self.in_dim, 1, colsum=views[1],
+                               colsum_of_v=False, m_valid=hd, n_valid=self.in_dim)
+            main.wait_stream(side)
             return views
         dh, _ = ops.linear_bf16(dy, self.head.w16t, None, act=0, relu_mask_src=h_last)
         for i in range(n_layers - 1, 0, -1):
