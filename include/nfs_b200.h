@@ -223,6 +223,16 @@ int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
                   void *save_bf16, int64_t save_rows_per_layer,
                   float *out_f32, int32_t out_cols, void *stream);
 
+/* nfs_mlp_chain_points: the same chain with K2 fused in (inference): the chain input is the positional encoding
+ *   of points (P,3) fp32 - [x, sin(x f_0), cos(x f_0), ..., cos(x f_{L-1}), 0], f_k = freq0 * 2^k, L = n_octaves
+ *   <= 10 - computed by the epilogue warps straight into the first layer's shared-memory operand (K_0 must be
+ *   64), so neither the fp32 encoding (positional_encoding.py:27-33) nor its bf16 copy ever exists in HBM.
+ *   The last layer is the fp32 output head (out_f32 [P,out_cols]); nothing is saved. */
+int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
+                         int32_t n_layers, const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
+                         const int32_t *row0, const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                         float *out_f32, int32_t out_cols, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * K2 fused with the operand cast of the first dense layer
  *   (positional_encoding.py:27-33 / nerf_mlp.py:24-33, the torch.cat with DINO features of

@@ -58,6 +58,9 @@ struct FusedArgs {
   const __nv_bfloat16 *mask;           // act 4: [n, mask_rows, N] bf16, result *= [mask[mask_idx[l]][row][col] > 0]
   long long mask_rows;
   int mask_idx[kFmMaxLayers];
+  const float *points;                 // in-kernel encoding mode: [P,3] fp32 sample positions (x_bf16 unused) | NULL
+  float freq0;                         // first frequency band; band k = freq0 * 2^k
+  int n_octaves;                       // number of bands (3 * (2 * n_octaves + 1) <= 64)
   int dbg;                             // developer bisection switches (nfs_set_debug_flags), 0 in production
   unsigned long long *trace;           // developer timeline of CTA 0 (nfs_set_debug_trace), NULL in production
 };
@@ -228,15 +231,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t *acc_full = act_ready + 2;            // [2] accumulator of tile t complete
   uint64_t *head_done = acc_full + 2;            // [2] this CTA's epilogue is done with act[t] / accumulator t (producer)
   uint64_t *acc_free = head_done + 2;            // [2] leader: both CTAs' epilogues drained accumulator t (MMA thread)
-  uint64_t *bias_full = acc_free + 2;           // [2] bias of a layer landed in bias_s[slot] (bulk copy)
+  uint64_t *in_ready = acc_free + 2;             // [2] leader: both CTAs' encoding warps wrote the chain input of tile t
+  uint64_t *bias_full = in_ready + 2;           // [2] bias of a layer landed in bias_s[slot] (bulk copy)
   uint64_t *bias_empty = bias_full + 2;          // [2] all 16 epilogue warps are done with bias_s[slot]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_empty + 2);
-  float *bias_s = reinterpret_cast<float *>(bars + 32);   // [2][256] fp32: the current and the next layer's bias
+  float *bias_s = reinterpret_cast<float *>(bars + 32);   // 30 barriers + the TMEM slot fit in 256 bytes;   // [2][256] fp32: the current and the next layer's bias
 
   // warp index through a shuffle: the compiler then treats it (and every branch on it) as warp-uniform and
   // keeps the MMA / TMA operands in uniform registers instead of R2UR "waterfall" loops per instruction
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   unsigned trace_n = 0;
+  (void)trace_n;
   const int L = a.n_layers;
   const long long n_tiles = (a.P + 127) / 128;
   const long long n_quads = (n_tiles + 3) / 4;          // a CTA pair works on 4 tiles: tile = 4*quad + 2*rank + t
@@ -249,6 +254,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     for (int t = 0; t < 2; ++t) {
       mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 32);
       mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16); mbar_init(acc_free + t, 32);
+      mbar_init(in_ready + t, 8);
       mbar_init(bias_full + t, 1); mbar_init(bias_empty + t, 16);
     }
     fence_barrier_init();
@@ -272,7 +278,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       uint32_t wit = 0, iter = 0;
       const int ks0 = a.K[0] >> 6;
       for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < 2 && a.points == nullptr; ++t) {
           mbar_wait_relaxed(act_free + t, (iter & 1) ^ 1);
           mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);
           if (rank == 0) mbar_expect_tx(in_full + t, (uint32_t)(2 * ks0 * kActSlab));     // both CTAs' tiles
@@ -320,7 +326,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           for (int t = 0; t < 2; ++t) {
             if (l == 0) {
               mbar_wait_cluster(acc_free + t, (iter & 1) ^ 1);   // accumulators t drained by the previous quad's last layer
-              mbar_wait_cluster(in_full + t, iter & 1);
+              mbar_wait_cluster((a.points != nullptr ? in_ready : in_full) + t, iter & 1);
             } else {
               mbar_wait_cluster(act_ready + t, n_ready[t] & 1);
               ++n_ready[t];
@@ -371,7 +377,54 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     bool store_pending = false;
     const uint32_t ready_bar[2] = {map_to_cta(act_ready, 0), map_to_cta(act_ready + 1, 0)};   // in the leader CTA
     const uint32_t free_bar[2] = {map_to_cta(acc_free, 0), map_to_cta(acc_free + 1, 0)};
-    for (long long quad = quad0; quad < n_quads; quad += quad_step) {
+    const uint32_t in_bar[2] = {map_to_cta(in_ready, 0), map_to_cta(in_ready + 1, 0)};
+    uint32_t iter = 0;
+    for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
+      if (a.points != nullptr && cq < 2) {
+        // K2 fused in: the warps with cq == t write the positional encoding of tile t (thread = point) straight
+        // into slab 0 of act[t] - [x | sin(x f_0) | cos(x f_0) | sin(x f_1) | ...], one accurate sincosf per
+        // coordinate and the double-angle recurrence for the higher octaves (identical arithmetic to
+        // posenc_bf16_kernel's octave path, so the result is bit-identical to the two-kernel route)
+        const int t = cq;
+        mbar_wait_relaxed(act_free + t, (iter & 1) ^ 1);       // the previous quad's last MMAs have read act[t]
+        mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);      // and every epilogue warp is done with it
+        const long long row = (4 * quad + 2 * rank + t) * 128 + r_in;
+        float x[3] = {0.f, 0.f, 0.f}, sn[3], cs[3];
+        if (row < a.P) { x[0] = __ldg(a.points + row * 3); x[1] = __ldg(a.points + row * 3 + 1); x[2] = __ldg(a.points + row * 3 + 2); }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sincosf(__fmul_rn(x[d], a.freq0), &sn[d], &cs[d]);
+        uint8_t *srow = smem + t * kActBytes + r_in * 128;
+        float buf[8];
+        int nb = 0, chunk = 0;
+        auto push = [&](float v) {
+          buf[nb++] = v;
+          if (nb == 8) {
+            *reinterpret_cast<uint4 *>(srow + ((chunk ^ (r_in & 7)) << 4)) =
+                make_uint4(pack_bf16x2(buf[0], buf[1]), pack_bf16x2(buf[2], buf[3]), pack_bf16x2(buf[4], buf[5]),
+                           pack_bf16x2(buf[6], buf[7]));
+            nb = 0; ++chunk;
+          }
+        };
+        push(x[0]); push(x[1]); push(x[2]);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+          if (k < a.n_octaves) {
+            push(sn[0]); push(sn[1]); push(sn[2]); push(cs[0]); push(cs[1]); push(cs[2]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float s2 = 2.f * sn[d] * cs[d], c2 = 1.f - 2.f * sn[d] * sn[d];
+              sn[d] = s2; cs[d] = c2;
+            }
+          } else {
+            push(0.f); push(0.f); push(0.f); push(0.f); push(0.f); push(0.f);
+          }
+        }
+        push(0.f);                                            // column 63: zero padding
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(in_bar[t]);
+      }
       for (int l = 0; l < L; ++l, ++gl) {
         const bool last = (l == L - 1);
         const bool is_head = last && a.head != 0;
@@ -526,21 +579,22 @@ extern "C" void nfs_set_debug_trace(void *buf) { g_fm_trace = (unsigned long lon
 
 // Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
 // default only in their row count (64 resp. 32).
-extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
-                             const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
-                             const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
-                             const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
-                             void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
-                             void *stream) {
-  const char *fn = "nfs_mlp_chain";
+static int launch_chain(const char *fn, const void *x_bf16, const float *points, float freq0, int n_octaves,
+                        int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                        const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                        const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                        const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
+                        void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
+                        void *stream) {
   if (n_points < 0 || n_layers < 2 || n_layers > kFmMaxLayers) return fail_arg(fn, NFS_E_BADARG, "need 2..12 layers");
   if (n_points == 0) return 0;
-  if (!x_bf16 || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || (!out_f32 && !save_bf16))
+  if ((!x_bf16 && !points) || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || (!out_f32 && !save_bf16))
     return fail_arg(fn, NFS_E_BADARG, "null pointer");
   FusedArgs a{};
   a.P = n_points; a.n_layers = n_layers; a.bias = bias_stack; a.out = out_f32; a.out_cols = out_cols;
   a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
   a.head = out_f32 != nullptr;
+  a.points = points; a.freq0 = freq0; a.n_octaves = n_octaves;
   a.dbg = g_fm_debug;
   a.trace = g_fm_trace;
   a.mask = (const __nv_bfloat16 *)mask_bf16; a.mask_rows = mask_rows_per_layer;
@@ -566,17 +620,21 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
     for (int l = 0; l < n_saved; ++l)
       if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal layer widths");
 
-  CUtensorMap tx, tw, ts;
-  int rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)n_points, (uint64_t)a.K[0], (uint64_t)a.K[0], 128, fn);
-  if (rc) return rc;
+  CUtensorMap tx{}, tw{}, ts{};
+  int rc = 0;
+  if (points != nullptr) {
+    if (a.K[0] != 64 || n_octaves < 1 || n_octaves > 10)
+      return fail_arg(fn, NFS_E_UNSUPPORTED, "in-kernel encoding needs a 64-wide first layer and 1..10 octaves");
+  } else {
+    rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)n_points, (uint64_t)a.K[0], (uint64_t)a.K[0], 128, fn);
+    if (rc) return rc;
+  }
   rc = tc::make_tmap_bf16(&tw, w_stack_bf16, (uint64_t)w_rows, 256, 256, 64, fn);
   if (rc) return rc;
   if (a.save) {
     rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * n_saved), (uint64_t)a.N[0],
                             (uint64_t)a.N[0], 32, fn);
     if (rc) return rc;
-  } else {
-    ts = tx;
   }
   const size_t smem = 2 * kActBytes + kWStages * kWStage + 256 + 2 * 256 * sizeof(float);
   static bool attr_set = false;
@@ -597,4 +655,24 @@ extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_lay
   else
     fused_mlp_kernel<false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
   return check_launch(fn);
+}
+
+extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                             const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                             const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                             const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
+                             void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
+                             void *stream) {
+  return launch_chain("nfs_mlp_chain", x_bf16, nullptr, 0.f, 0, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
+                      w_rows, bias_stack, mask_bf16, mask_rows_per_layer, mask_idx, save_bf16, save_rows_per_layer, out_f32,
+                      out_cols, stream);
+}
+
+extern "C" int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
+                                    int32_t n_layers, const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
+                                    const int32_t *row0, const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                                    float *out_f32, int32_t out_cols, void *stream) {
+  if (!points || !out_f32) return fail_arg("nfs_mlp_chain_points", NFS_E_BADARG, "null pointer");
+  return launch_chain("nfs_mlp_chain_points", nullptr, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0,
+                      w_stack_bf16, w_rows, bias_stack, nullptr, 0, nullptr, nullptr, 0, out_f32, out_cols, stream);
 }

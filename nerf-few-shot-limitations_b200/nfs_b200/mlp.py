@@ -97,6 +97,12 @@ _freq_cache = {}
 _pow2_cache = {}
 
 
+def first_band(freqs):
+    """freqs[0] as a Python float (cached with the octave test: one read-back for a table on the GPU)."""
+    bands_are_octaves(freqs)
+    return _pow2_cache[(freqs.data_ptr(), freqs._version, int(freqs.numel()), str(freqs.device), "f0")]
+
+
 def bands_are_octaves(freqs):
     """True when freqs[k] == freqs[0] * 2^k exactly (decided once per table on the host; a table that lives
     on the GPU is read back once)."""
@@ -108,6 +114,7 @@ def bands_are_octaves(freqs):
         if len(_pow2_cache) > 64:
             _pow2_cache.clear()
         _pow2_cache[key] = hit
+        _pow2_cache[key + ("f0",)] = float(f[0]) if f.numel() else 1.0
     return hit
 
 
@@ -262,6 +269,18 @@ class G1Plan:
         acts = [x16] + ([save[i, :P] for i in range(n_hidden)] if keep else [])
         return out, acts, save
 
+    def run_forward_points(self, pts, freqs):
+        """nfs_mlp_chain_points: encoding + all layers in one launch (inference only; nothing saved)."""
+        P = pts.shape[0]
+        out = torch.empty((P, 4), device=pts.device, dtype=torch.float32)
+        if P:
+            n_hidden = len(self.packed)
+            with torch.cuda.device(pts.device):
+                _lib.call("nfs_mlp_chain_points", ptr(pts), float(first_band(freqs)), int(freqs.numel()), P, n_hidden + 1,
+                          self.c_k, self.c_n, self.c_act, self.c_row0, ptr(self.w_stack), self.w_rows, ptr(self.b_stack),
+                          ptr(out), 4, _stream())
+        return out
+
     def dgrad_chain_fused(self, dy, save_fwd, P):
         """All dgrad GEMMs of the backward pass in one launch (nfs_mlp_chain with act 4): returns
         [n_hidden, rows, h_pad] bf16 whose slice j is dL/d(pre-activation of layer n_hidden-1-j)."""
@@ -392,6 +411,13 @@ def g1_forward(plan, x=None, points=None, freqs=None):
         width = flat.shape[-1] * (2 * int(freqs.numel()) + 1)
         if width != plan.in_dim:
             raise RuntimeError("NeRFMLP: encoding width %d does not match the first layer (%d)" % (width, plan.in_dim))
+        params = plan.params()
+        keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if (not keep and getattr(plan, "fusable", False) and plan.k0 == 64 and flat.shape[-1] == 3
+                and 1 <= int(freqs.numel()) <= 10 and bands_are_octaves(freqs)
+                and os.environ.get("NFS_MLP_FUSED", "1") != "0" and os.environ.get("NFS_MLP_FUSED_ENC", "1") != "0"):
+            # inference: the encoding is produced inside the chain kernel (no operand tensor in HBM)
+            return plan.run_forward_points(ops._f32c(flat), freqs).reshape(*lead, 4)
         x16 = encode_operand(flat, freqs, plan.k0)
     params = plan.params()
     keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)

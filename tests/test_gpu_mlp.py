@@ -174,3 +174,28 @@ def test_fused_chain_matches_layerwise(cuda, P, monkeypatch):
     grads_f = plan.run_backward(acts_f, out_f, g_out, save_fwd=save_f)
     for a, b in zip(grads_f, grads_l):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max() + 1e-12) + 1e-7
+
+
+@pytest.mark.parametrize("P", [1, 129, 5000, 70001])
+def test_in_kernel_encoding_matches_two_kernel_route(cuda, P, monkeypatch):
+    """nfs_mlp_chain_points (K2 fused into the chain) against posenc_bf16 -> nfs_mlp_chain: identical
+    arithmetic, so bit-identical outputs; both within tolerance of the fp32 oracle."""
+    from models.nerf_model import NeRFMLP
+    from oracle import nerf_oracle as O
+    torch.manual_seed(3)
+    ref = O.PlainNeRF()
+    mod = NeRFMLP()
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.to(cuda)
+    g = torch.Generator().manual_seed(P)
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 8
+    bands = O.frequency_bands(10)
+    with torch.no_grad():
+        fused = mod.forward_points(pts.to(cuda), bands)
+        monkeypatch.setenv("NFS_MLP_FUSED_ENC", "0")
+        two = mod.forward_points(pts.to(cuda), bands)
+        monkeypatch.delenv("NFS_MLP_FUSED_ENC")
+        out_ref = ref(O.encode(pts, bands))
+    assert torch.equal(fused, two)
+    assert float((fused.cpu()[:, :3] - out_ref[:, :3]).abs().max()) <= 2e-2
+    assert float(((fused.cpu()[:, 3] - out_ref[:, 3]).abs() / (3e-2 * out_ref[:, 3].abs() + 1e-2)).max()) <= 1.0
