@@ -201,16 +201,19 @@ int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int6
 
 /* nfs_mlp_chain: a whole chain of dense layers in ONE launch (fused multi-layer MLP):
  *   h_0 = X;  h_{l+1} = act_l( h_l . W_l^T + b_l ),  l = 0 .. n_layers-1
- *   Forward use: replaces nerf_model.NeRFMLP.forward (src/models/nerf_model.py:16-24).
- *   Backward use: the dgrad chain of its autograd backward (X = dL/d(head pre-activation),
- *   W_l = transposed weights in reverse order, act 4 = ReLU backward).
- *   Activations stay in shared memory / TMEM between layers; weights are TMA-streamed from one
- *   stacked bf16 tensor w_stack [w_rows, 256] (layer l = rows row0[l] .. row0[l]+N_l, columns
- *   0..K_l, zero padded); biases stacked the same way (bias_stack[row0[l] + n]) or NULL.
+ *   Forward use: replaces nerf_model.NeRFMLP.forward (src/models/nerf_model.py:16-24) and the equal-width
+ *   sub-chains of NeRFWithDINO (nerf_mlp.py:134-158).  Backward use: the dgrad chain of their autograd
+ *   backward (X = dL/d(last pre-activation), W_l = transposed weights in reverse order, act 4 = ReLU backward).
+ *   Runs on CTA pairs (tcgen05 cta_group::2); activations stay in shared memory / TMEM between layers; weights
+ *   are TMA-streamed from one stacked bf16 tensor w_stack [w_rows, 256] (layer l = rows row0[l] .. row0[l]+N_l,
+ *   columns 0..K_l, zero padded); biases stacked the same way (bias_stack[row0[l] + n]) or NULL.
  *   K_l, N_l multiples of 64 in [64,256], K_l == N_{l-1}.
- *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 4 multiply by
- *   [mask[mask_idx[l]][p][n] > 0] with mask_bf16 = [*, mask_rows_per_layer, N_l] bf16 (the
- *   activations saved by the forward chain).
+ *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 4 ReLU backward: multiply by the sign bit
+ *   relu_bits_in[mask_idx[l]][p][n] (layers >= 128 wide).
+ *   ReLU sign bits: uint32 [layers, rows_per_layer, 8] = 256 bits per point; in word w bit j (j < 16) is column
+ *   32w + 2j and bit 16 + j is column 32w + 2j + 1.  relu_bits_out (forward chain of a training step, NULL
+ *   otherwise) receives the bits of every act-1 layer's output, 32 bytes per point instead of the 512-byte
+ *   activation row the backward would otherwise re-read; rows per layer = save_rows_per_layer.
  *   out_f32 != NULL: the LAST layer is an output head whose first out_cols columns are written
  *   as fp32 [P,out_cols].  save_bf16 != NULL: [n_saved, save_rows_per_layer, N_0] bf16 receives
  *   every non-head layer's output by TMA store (n_saved = n_layers - 1 with a head, else
@@ -219,8 +222,8 @@ int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
                   const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
                   const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
                   const float *bias_stack,
-                  const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
-                  void *save_bf16, int64_t save_rows_per_layer,
+                  const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
+                  void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer,
                   float *out_f32, int32_t out_cols, void *stream);
 
 /* nfs_mlp_chain_points: the same chain with K2 fused in (inference): the chain input is the positional encoding

@@ -55,8 +55,13 @@ struct FusedArgs {
   int out_cols;
   int save;
   int head;                            // 1: last layer is the fp32 output head; 0: it is a regular (saved) layer
-  const __nv_bfloat16 *mask;           // act 4: [n, mask_rows, N] bf16, result *= [mask[mask_idx[l]][row][col] > 0]
-  long long mask_rows;
+  // ReLU sign bits, 256 per row = 8 words [layer][row][8]; in word w bit j (j < 16) is column 32w + 2j, bit 16 + j is
+  // column 32w + 2j + 1 (the two halves of packed pair j), so (word >> j) & 0x10001 times 0x3F80 is the pair's
+  // bf16x2 {1.0 | 0.0} multiplier.  bits_out: written by layers with act 1 (the forward chain of a training step);
+  // bits_in: read by layers with act 4 (the dgrad chain): result *= bit(mask_idx[l], row, col).
+  uint32_t *bits_out;
+  const uint32_t *bits_in;
+  long long bits_rows;                 // rows per layer of bits_in
   int mask_idx[kFmMaxLayers];
   const float *points;                 // in-kernel encoding mode: [P,3] fp32 sample positions (x_bf16 unused) | NULL
   float freq0;                         // first frequency band; band k = freq0 * 2^k
@@ -132,13 +137,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// ReLU backward on a packed pair: keep v where the saved activation h (>= 0, output of a ReLU) is
-// non-zero: set.gt yields {1.0, 0.0} per half, one multiply applies it.
-__device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t v, uint32_t h) {
-  uint32_t m, r;
-  asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(0u));
+// ReLU backward on packed pair j of a 32-column word of sign bits (layout above)
+__device__ __forceinline__ uint32_t relu_bits_bf16x2(uint32_t v, uint32_t word, int j) {
+  const uint32_t m = ((word >> j) & 0x00010001u) * 0x3F80u;     // bf16x2 {1.0 | 0.0, 1.0 | 0.0}
+  uint32_t r;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(m));
   return r;
+}
+// sign bits of a post-ReLU packed pair (both halves are non-negative bf16: adding 0x7FFF carries into bit 15 / 31
+// exactly when the half is non-zero), placed at bit j and bit 16 + j
+__device__ __forceinline__ uint32_t relu_bits_of(uint32_t pk, int j) {
+  return (((pk + 0x7FFF7FFFu) >> 15) & 0x00010001u) << j;
 }
 
 // TMEM -> registers, 16 consecutive fp32 columns of this thread's lane, WITHOUT waiting: the
@@ -158,9 +167,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // One epilogue chunk: 16 accumulator columns of one row -> (+bias, read from shared memory: every
 // lane reads the same address = broadcast; packed fp32x2 adds) -> ReLU | ReLU-backward mask | none
 // -> bf16 -> two 16-byte chunks of the row in the SWIZZLE_128B operand layout.
-template <bool kMasked>
-__device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s, int act, uint4 mk0, uint4 mk1,
-                                          uint8_t *srow, int ch, int r7, int dbg) {
+template <bool kMasked, bool kTrain>
+__device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s, int act, uint32_t bits_word, int j0,
+                                          uint32_t &bits_acc, uint8_t *srow, int ch, int r7, int dbg) {
   if (bias_s != nullptr && !(dbg & 8)) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -181,10 +190,12 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s
     for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
   }
   if (kMasked && act == 4) {
-    pk[0] = relu_mask_bf16x2(pk[0], mk0.x); pk[1] = relu_mask_bf16x2(pk[1], mk0.y);
-    pk[2] = relu_mask_bf16x2(pk[2], mk0.z); pk[3] = relu_mask_bf16x2(pk[3], mk0.w);
-    pk[4] = relu_mask_bf16x2(pk[4], mk1.x); pk[5] = relu_mask_bf16x2(pk[5], mk1.y);
-    pk[6] = relu_mask_bf16x2(pk[6], mk1.z); pk[7] = relu_mask_bf16x2(pk[7], mk1.w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = relu_bits_bf16x2(pk[j], bits_word, j0 + j);
+  }
+  if (kTrain && act == 1) {              // sign bits for the backward pass
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bits_acc |= relu_bits_of(pk[j], j0 + j);
   }
   if (dbg & 32) {                       // bisection: keep the values alive without the shared-memory stores
     uint32_t x = 0;
@@ -215,7 +226,9 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s
   } while (0)
 #endif
 
-template <bool kMasked>
+// kMasked: dgrad chain (ReLU backward from sign bits).  kTrain: forward chain of a training step (saves activations
+// and sign bits).  Neither: inference forward (optionally with the positional encoding computed in-kernel).
+template <bool kMasked, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_save, const FusedArgs a) {
@@ -374,13 +387,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int cq = (warp - 2) >> 2;
     const int r_in = q * 32 + lane;
     uint32_t n_full[2] = {0, 0}, gl = 0;
+    uint2 b_n1 = make_uint2(0u, 0u), b_n2 = make_uint2(0u, 0u);   // sign bits of the next two epilogue steps
     bool store_pending = false;
     const uint32_t ready_bar[2] = {map_to_cta(act_ready, 0), map_to_cta(act_ready + 1, 0)};   // in the leader CTA
     const uint32_t free_bar[2] = {map_to_cta(acc_free, 0), map_to_cta(acc_free + 1, 0)};
     const uint32_t in_bar[2] = {map_to_cta(in_ready, 0), map_to_cta(in_ready + 1, 0)};
     uint32_t iter = 0;
     for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
-      if (a.points != nullptr && cq < 2) {
+      if (!kMasked && !kTrain && a.points != nullptr && cq < 2) {
         // K2 fused in: the warps with cq == t write the positional encoding of tile t (thread = point) straight
         // into slab 0 of act[t] - [x | sin(x f_0) | cos(x f_0) | sin(x f_1) | ...], one accurate sincosf per
         // coordinate and the double-angle recurrence for the higher octaves (identical arithmetic to
@@ -442,26 +456,24 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
           uint8_t *act_t = smem + t * kActBytes;
           // ReLU-backward mask row (straight from HBM): issue the loads before blocking on the accumulator
-          // ReLU-backward mask: this thread's row of the saved activation, 16 columns (32 bytes) per chunk, loaded
-          // one chunk ahead of its use with 256-bit no-allocate loads (the row was prefetched into L2 two epilogue
-          // steps ago); holding only two chunks keeps the kernel within its 96 registers
-          uint4 mk_cur[2] = {}, mk_nxt[2] = {};
-          const bool use_mask = kMasked && act_l == 4 && tile < n_tiles;
-          const uint4 *mp = reinterpret_cast<const uint4 *>(
-              a.mask + (use_mask ? ((long long)a.mask_idx[l] * a.mask_rows + row) * Nl + c0 : 0));
-          auto load_mask = [&](uint4 (&dst)[2], int chunk) {
-            asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(dst[0].x), "=r"(dst[0].y), "=r"(dst[0].z), "=r"(dst[0].w),
-                           "=r"(dst[1].x), "=r"(dst[1].y), "=r"(dst[1].z), "=r"(dst[1].w)
-                         : "l"(mp + 2 * chunk));
+          // ReLU-backward sign bits of this thread's `quarter` columns (8 or 4 bytes per tile step): loaded two epilogue
+          // steps ahead (same tile, previous layer's step), so their latency never shows
+          const bool use_bits = kMasked && act_l == 4 && tile < n_tiles;
+          const int words = quarter >> 5;                       // 2 (256-wide layers) or 1 (128-wide)
+          auto load_bits = [&](int layer) -> uint2 {
+            const uint32_t *bp = a.bits_in + ((long long)a.mask_idx[layer] * a.bits_rows + row) * 8 + (c0 >> 5);
+            uint2 v = make_uint2(0u, 0u);
+            if (words == 2) v = __ldg(reinterpret_cast<const uint2 *>(bp));
+            else v.x = __ldg(bp);
+            return v;
           };
-          if (use_mask) load_mask(mk_cur, 0);
-          if (kMasked && l + 1 < L && a.act[l + 1] == 4 && tile < n_tiles) {
-            // the mask row of this tile's NEXT layer (two epilogue steps ahead): pull it from HBM into L2 now,
-            // so that the register loads above see L2 latency instead of DRAM latency
-            const __nv_bfloat16 *np = a.mask + ((long long)a.mask_idx[l + 1] * a.mask_rows + row) * a.N[l + 1] + cq * (a.N[l + 1] >> 2);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+          uint2 b_cur = make_uint2(0u, 0u);
+          if (kMasked) {
+            if (use_bits) b_cur = (l == 0) ? load_bits(0) : b_n1;
+            b_n1 = b_n2;
+            if (l + 1 < L && a.act[l + 1] == 4 && tile < n_tiles) b_n2 = load_bits(l + 1);
           }
+          uint32_t bits_acc[2] = {0u, 0u};
           mbar_wait_relaxed(acc_full + t, n_full[t] & 1);
           ++n_full[t];
           tc_fence_after();
@@ -470,7 +482,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // the TMA store this warp issued from act[t] one layer ago has finished READING the block that is
             // overwritten below (the store issued for the other tile a moment ago may still be in flight)
             // 128-wide layers: two warps (cq, cq^1) share one 64-column TMA-store box -> pair barriers
-            const bool paired = a.save && quarter == 32;
+            const bool do_save = (kTrain || kMasked) && a.save != 0;
+            const bool paired = do_save && quarter == 32;
             const uint32_t pair_bar = 1u + (uint32_t)(q * 2 + (cq >> 1));
             if (store_pending) {
               if (lane == 0 && (!paired || (cq & 1) == 0)) bulk_wait_read1();
@@ -489,14 +502,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 if (c < n_chunks) {
-                  if (use_mask && c + 1 < n_chunks) load_mask(mk_nxt, c + 1);
                   tmem_ld16_async(taddr + c0 + 16 * c, va);
                   tmem_ld_wait();
-                  epi_chunk<kMasked>(va, bias ? bias + 16 * c : nullptr, act_l, mk_cur[0], mk_cur[1],
-                                     srow, ch0 + 2 * c, r_in & 7, NFS_DBG(a));
-                  mk_cur[0] = mk_nxt[0]; mk_cur[1] = mk_nxt[1];
+                  epi_chunk<kMasked, kTrain>(va, bias ? bias + 16 * c : nullptr, act_l, (c >> 1) ? b_cur.y : b_cur.x, 8 * (c & 1),
+                                     bits_acc[c >> 1], srow, ch0 + 2 * c, r_in & 7, NFS_DBG(a));
                 }
               }
+            }
+            if (kTrain && a.bits_out != nullptr && act_l == 1 && tile < n_tiles) {
+              uint32_t *bp = a.bits_out + ((long long)l * a.save_rows + row) * 8 + (c0 >> 5);
+              if (words == 2) *reinterpret_cast<uint2 *>(bp) = make_uint2(bits_acc[0], bits_acc[1]);
+              else *bp = bits_acc[0];
             }
             NFS_TRACE(4, l, t);
             tc_fence_before();
@@ -506,13 +522,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             if (lane == 0) {
               if (!last) mbar_arrive_cluster(ready_bar[t]);
-              if (a.save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
+              if (do_save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
                 tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
                              (int)(l * a.save_rows + tile * 128 + q * 32));
                 bulk_commit();
               }
             }
-            store_pending = a.save != 0;
+            store_pending = do_save;
             if (last) {                          // chain ends in a regular layer: tile t is finished once the
               if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
               __syncwarp();
@@ -583,9 +599,9 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
                         int64_t n_points, int32_t n_layers, const int32_t *k_dims,
                         const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
                         const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
-                        const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
-                        void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
-                        void *stream) {
+                        const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
+                        void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                        int32_t out_cols, void *stream) {
   if (n_points < 0 || n_layers < 2 || n_layers > kFmMaxLayers) return fail_arg(fn, NFS_E_BADARG, "need 2..12 layers");
   if (n_points == 0) return 0;
   if ((!x_bf16 && !points) || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || (!out_f32 && !save_bf16))
@@ -597,12 +613,15 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   a.points = points; a.freq0 = freq0; a.n_octaves = n_octaves;
   a.dbg = g_fm_debug;
   a.trace = g_fm_trace;
-  a.mask = (const __nv_bfloat16 *)mask_bf16; a.mask_rows = mask_rows_per_layer;
+  a.bits_in = (const uint32_t *)relu_bits_in; a.bits_rows = bits_rows_per_layer;
+  a.bits_out = (uint32_t *)relu_bits_out;
   for (int l = 0; l < n_layers; ++l) {
     a.K[l] = k_dims[l]; a.N[l] = n_dims[l]; a.act[l] = acts[l]; a.row0[l] = row0[l];
     a.mask_idx[l] = mask_idx ? mask_idx[l] : 0;
-    if (a.act[l] == 4 && (!mask_bf16 || !mask_idx || a.mask_idx[l] < 0))
-      return fail_arg(fn, NFS_E_BADARG, "act 4 (ReLU-backward mask) needs mask_bf16 and mask_idx");
+    if (a.act[l] == 4 && (!relu_bits_in || !mask_idx || a.mask_idx[l] < 0))
+      return fail_arg(fn, NFS_E_BADARG, "act 4 (ReLU backward) needs relu_bits_in and mask_idx");
+    if ((a.act[l] == 4 || (a.act[l] == 1 && relu_bits_out)) && a.N[l] < 128 && !(out_f32 && l == n_layers - 1))
+      return fail_arg(fn, NFS_E_UNSUPPORTED, "ReLU sign bits need layers at least 128 wide");
     if (a.act[l] < 0 || a.act[l] > 4) return fail_arg(fn, NFS_E_BADARG, "act must be 0..4");
     if (a.K[l] % 64 || a.K[l] <= 0 || a.K[l] > 256 || a.N[l] % 64 || a.N[l] <= 0 || a.N[l] > 256 ||
         a.row0[l] < 0 || a.row0[l] + a.N[l] > w_rows)
@@ -613,8 +632,10 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   const long long rows128 = ((n_points + 127) / 128) * 128;
   if (a.save && save_rows_per_layer < rows128)
     return fail_arg(fn, NFS_E_BADARG, "save_rows_per_layer must be >= n_points rounded up to 128");
-  if (mask_bf16 && mask_rows_per_layer < rows128)
-    return fail_arg(fn, NFS_E_BADARG, "mask_rows_per_layer must be >= n_points rounded up to 128");
+  if (relu_bits_in && bits_rows_per_layer < rows128)
+    return fail_arg(fn, NFS_E_BADARG, "bits_rows_per_layer must be >= n_points rounded up to 128");
+  if (relu_bits_out && (relu_bits_in || save_rows_per_layer < rows128))
+    return fail_arg(fn, NFS_E_BADARG, "relu_bits_out belongs to a forward chain (no relu_bits_in) with save_rows_per_layer >= rows");
   const int n_saved = a.head ? n_layers - 1 : n_layers;
   if (a.save)
     for (int l = 0; l < n_saved; ++l)
@@ -639,9 +660,11 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   const size_t smem = 2 * kActBytes + kWStages * kWStage + 256 + 2 * 256 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(fused_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail_cuda(fn, e);
     attr_set = true;
   }
@@ -650,22 +673,24 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   const long long n_quads = ((n_points + 127) / 128 + 3) / 4;
   const long long max_pairs = sms / 2;
   const unsigned grid = 2u * (unsigned)(n_quads < max_pairs ? n_quads : max_pairs);   // whole CTA pairs
-  if (mask_bf16 != nullptr)
-    fused_mlp_kernel<true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+  if (relu_bits_in != nullptr)
+    fused_mlp_kernel<true, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+  else if (a.save || relu_bits_out)
+    fused_mlp_kernel<false, true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
   else
-    fused_mlp_kernel<false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+    fused_mlp_kernel<false, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
   return check_launch(fn);
 }
 
 extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
                              const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
                              const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
-                             const void *mask_bf16, int64_t mask_rows_per_layer, const int32_t *mask_idx,
-                             void *save_bf16, int64_t save_rows_per_layer, float *out_f32, int32_t out_cols,
-                             void *stream) {
+                             const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
+                             void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                             int32_t out_cols, void *stream) {
   return launch_chain("nfs_mlp_chain", x_bf16, nullptr, 0.f, 0, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
-                      w_rows, bias_stack, mask_bf16, mask_rows_per_layer, mask_idx, save_bf16, save_rows_per_layer, out_f32,
-                      out_cols, stream);
+                      w_rows, bias_stack, relu_bits_in, bits_rows_per_layer, mask_idx, save_bf16, relu_bits_out,
+                      save_rows_per_layer, out_f32, out_cols, stream);
 }
 
 extern "C" int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
@@ -674,5 +699,5 @@ extern "C" int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_
                                     float *out_f32, int32_t out_cols, void *stream) {
   if (!points || !out_f32) return fail_arg("nfs_mlp_chain_points", NFS_E_BADARG, "null pointer");
   return launch_chain("nfs_mlp_chain_points", nullptr, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0,
-                      w_stack_bf16, w_rows, bias_stack, nullptr, 0, nullptr, nullptr, 0, out_f32, out_cols, stream);
+                      w_stack_bf16, w_rows, bias_stack, nullptr, 0, nullptr, nullptr, nullptr, 0, out_f32, out_cols, stream);
 }

@@ -251,23 +251,24 @@ class G1Plan:
         self.cb_mask = arr_b(*[nh - 1 - j for j in range(nh)])      # h_{nh-j} = forward save[nh-1-j]
 
     def run_forward_fused(self, x16, keep):
-        """nfs_mlp_chain: all layers in one launch; hidden activations are written to HBM only
-        when the backward pass will need them."""
+        """nfs_mlp_chain: all layers in one launch; hidden activations (for wgrad) and their ReLU sign bits
+        (for the dgrad chain) are written to HBM only when the backward pass will need them."""
         P = x16.shape[0]
         dev = x16.device
         n_hidden = len(self.packed)
         out = torch.empty((P, 4), device=dev, dtype=torch.float32)
-        save, rows = None, 0
+        save, bits, rows = None, None, 0
         if keep:
             rows = _ceil_to(P, 128)
             save = torch.empty((n_hidden, rows, self.h_pad), device=dev, dtype=torch.bfloat16)
+            bits = torch.empty((n_hidden, rows, 8), device=dev, dtype=torch.int32)
         if P:
             with torch.cuda.device(dev):
                 _lib.call("nfs_mlp_chain", ptr(x16), P, n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0,
-                          ptr(self.w_stack), self.w_rows, ptr(self.b_stack), None, 0, None, ptr(save), rows,
+                          ptr(self.w_stack), self.w_rows, ptr(self.b_stack), None, 0, None, ptr(save), ptr(bits), rows,
                           ptr(out), 4, _stream())
         acts = [x16] + ([save[i, :P] for i in range(n_hidden)] if keep else [])
-        return out, acts, save
+        return out, acts, (save, bits) if keep else None
 
     def run_forward_points(self, pts, freqs):
         """nfs_mlp_chain_points: encoding + all layers in one launch (inference only; nothing saved)."""
@@ -281,15 +282,16 @@ class G1Plan:
                           ptr(out), 4, _stream())
         return out
 
-    def dgrad_chain_fused(self, dy, save_fwd, P):
-        """All dgrad GEMMs of the backward pass in one launch (nfs_mlp_chain with act 4): returns
-        [n_hidden, rows, h_pad] bf16 whose slice j is dL/d(pre-activation of layer n_hidden-1-j)."""
+    def dgrad_chain_fused(self, dy, bits, P):
+        """All dgrad GEMMs of the backward pass in one launch (nfs_mlp_chain with act 4 reading the forward
+        chain's ReLU sign bits): returns [n_hidden, rows, h_pad] bf16 whose slice j is
+        dL/d(pre-activation of layer n_hidden-1-j)."""
         n_hidden = len(self.packed)
-        rows = save_fwd.shape[1]
+        rows = bits.shape[1]
         out = torch.empty((n_hidden, rows, self.h_pad), device=dy.device, dtype=torch.bfloat16)
         with torch.cuda.device(dy.device):
             _lib.call("nfs_mlp_chain", ptr(dy), P, n_hidden, self.cb_k, self.cb_n, self.cb_act, self.cb_row0,
-                      ptr(self.wt_stack), self.wt_rows, None, ptr(save_fwd), rows, self.cb_mask, ptr(out), rows,
+                      ptr(self.wt_stack), self.wt_rows, None, ptr(bits), rows, self.cb_mask, ptr(out), None, rows,
                       None, 0, _stream())
         return out
 
@@ -335,7 +337,7 @@ class G1Plan:
         views[2 * n_layers + 3].copy_(tmp_b[0:3])
         if save_fwd is not None and n_layers >= 2 and os.environ.get("NFS_MLP_FUSED_BWD", "1") != "0":
             P = out.shape[0]
-            dys = self.dgrad_chain_fused(dy, save_fwd, P)
+            dys = self.dgrad_chain_fused(dy, save_fwd[1], P)
             # the wgrad launches are independent of each other: alternate them between two streams so that one
             # kernel's tail (SMs draining 256 KB of fp32 red.add each) overlaps the next kernel's ramp-up
             main = torch.cuda.current_stream(dev)
@@ -374,7 +376,7 @@ class _G1Fn(torch.autograd.Function):
         ctx.fused = save is not None
         if keep:
             if ctx.fused:
-                ctx.save_for_backward(out, x16, save)
+                ctx.save_for_backward(out, x16, save[0], save[1])
             else:
                 ctx.save_for_backward(out, *acts)
         return out
@@ -382,9 +384,10 @@ class _G1Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         if ctx.fused:
-            out, x16, save = ctx.saved_tensors
+            out, x16, sv, bits = ctx.saved_tensors
             P = out.shape[0]
-            acts = [x16] + [save[i, :P] for i in range(save.shape[0])]
+            acts = [x16] + [sv[i, :P] for i in range(sv.shape[0])]
+            save = (sv, bits)
         else:
             out, *acts = ctx.saved_tensors
             save = None

@@ -219,15 +219,17 @@ class G3Plan:
         self.chain_b.refresh()
         self.chain_b_bwd.refresh()
 
-    def _chain(self, x16, stack, n_layers, acts, P, mask=None, mask_idx=None):
-        """nfs_mlp_chain without an output head: every layer's output is saved -> [n_layers, rows, hp]."""
+    def _chain(self, x16, stack, n_layers, acts, P, bits_in=None, mask_idx=None, want_bits=False):
+        """nfs_mlp_chain without an output head: every layer's output is saved -> [n_layers, rows, hp]
+        (+ the ReLU sign bits [n_layers, rows, 8] of a forward chain when want_bits)."""
         rows = _ceil_to(P, 128)
         save = torch.empty((n_layers, rows, self.hp), device=x16.device, dtype=torch.bfloat16)
+        bits = torch.empty((n_layers, rows, 8), device=x16.device, dtype=torch.int32) if want_bits else None
         with torch.cuda.device(x16.device):
             _lib.call("nfs_mlp_chain", ptr(x16), P, n_layers, stack.c_k, stack.c_n, acts, stack.c_row0, ptr(stack.w),
-                      stack.rows, ptr(stack.b), ptr(mask), 0 if mask is None else mask.shape[1], mask_idx, ptr(save), rows,
-                      None, 0, _stream())
-        return save
+                      stack.rows, ptr(stack.b), ptr(bits_in), 0 if bits_in is None else bits_in.shape[1], mask_idx,
+                      ptr(save), ptr(bits), rows, None, 0, _stream())
+        return (save, bits) if want_bits else save
 
     def run_forward(self, x, d, f, freqs_pos, freqs_dir):
         P = x.shape[0]
@@ -238,7 +240,7 @@ class G3Plan:
         a16, _ = ops.linear_bf16(h2, self.pa.w16, self.pa.bias, act=1)
         _, gate = ops.linear_bf16(a16, self.pb.w16, self.pb.bias, act=5, out_bf16=False, out_f32_cols=2)
         c2 = encode_operand(x, freqs_pos, self.k0, extra=f, gate=gate)
-        sb = self._chain(c2, self.chain_b, self.nb, self.cbf_act, P)
+        sb, sb_bits = self._chain(c2, self.chain_b, self.nb, self.cbf_act, P, want_bits=True)
         hn = sb[self.nb - 1, :P]
         _, density = ops.linear_bf16(hn, self.pdh.w16, self.pdh.bias, act=1, out_bf16=False, out_f32_cols=1)
         cat16 = torch.empty((P, self.cat_k), device=x.device, dtype=torch.bfloat16)
@@ -247,11 +249,11 @@ class G3Plan:
         k1, _ = ops.linear_bf16(cat16, self.pc1.w16, self.pc1.bias, act=1)
         k2, _ = ops.linear_bf16(k1, self.pc2.w16, self.pc2.bias, act=1)
         _, rgb = ops.linear_bf16(k2, self.pc3.w16, self.pc3.bias, act=3, out_bf16=False, out_f32_cols=3)
-        saved = (c16, sa, a16, gate, c2, sb, density, cat16, k1, k2, rgb)
+        saved = (c16, sa, a16, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits)
         return rgb, density, saved
 
     def run_backward(self, x, f, freqs_pos, saved, g_rgb, g_density):
-        c16, sa, a16, gate, c2, sb, density, cat16, k1, k2, rgb = saved
+        c16, sa, a16, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits = saved
         P = x.shape[0]
         dev = x.device
         hp, H, nb = self.hp, self.H, self.nb
@@ -294,7 +296,7 @@ class G3Plan:
             dcat[:, hp:].zero_()
         g_top, _ = ops.linear_bf16(dcat, self.pheads.w16t, None, act=0, relu_mask_src=hn)
         # ---- density layers, output_proj, second use of fusion[2] (dgrad chain)
-        dys = self._chain(g_top, self.chain_b_bwd, nb - 1, self.cb_act, P, mask=sb, mask_idx=self.cb_mask)
+        dys = self._chain(g_top, self.chain_b_bwd, nb - 1, self.cb_act, P, bits_in=sb_bits, mask_idx=self.cb_mask)
 
         def grad_pre(j):          # dL/d(pre-activation of chain-B layer j)
             return g_top if j == nb - 1 else dys[nb - 2 - j, :P]
