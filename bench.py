@@ -451,7 +451,7 @@ def main():
         return
 
     peak, peak_src = peaks()
-    dom_ms, dom_bytes, dom = (bwd_ms, BWD_BYTES, "composite_bwd_kernel") if bwd_ms >= fwd_ms else \
+    dom_ms, dom_bytes, dom = (bwd_ms, BWD_BYTES, "composite_bwd_staged_kernel") if bwd_ms >= fwd_ms else \
         (fwd_ms, FWD_BYTES, "composite_fwd_kernel")
     achieved = dom_bytes * N_RAYS / (dom_ms * 1e-3) / 1e9
     line = {
