@@ -1,0 +1,113 @@
+"""Trainer shell: the repaired NeRFDINOTrainer consumes the reference's baseline.yaml schema
+unchanged, trains on the CUDA path and writes checkpoints with the reference's keys."""
+import copy
+import os
+
+import pytest
+import torch
+
+BASELINE = {   # experiments/baseline.yaml of the reference, verbatim values (only the sizes under test are reduced below)
+    "experiment": {"name": "NeRF-Baseline-Lego"},
+    "data": {"dataset": "nerf_synthetic", "scene": "lego", "num_views": 5, "resolution": 128, "near": 2.0, "far": 6.0},
+    "model": {"use_dino": False},
+    "nerf_model": {"pos_freq": 10, "dir_freq": 4, "hidden_dim": 256, "num_layers": 8},
+    "dino_model": {"name": "facebook/dinov2-base", "use_lora": False, "lora_rank": 4, "lora_alpha": 4},
+    "training": {"epochs": 200, "batch_size": 1024,
+                 "progressive_schedule": {"epochs_0_50": [32, 32, 32], "epochs_50_100": [64, 64, 48],
+                                          "epochs_100_plus": [128, 128, 64]}},
+    "optimizer": {"lr": 5.0e-4, "weight_decay": 1.0e-6, "lr_milestones": [100, 150], "lr_gamma": 0.5},
+    "loss": {"rgb_weight": 1.0, "depth_weight": 0.0, "reg_weight": 0.0},
+    "rendering": {"near": 2.0, "far": 6.0, "chunk_size": 2048, "noise_std": 0.0, "white_bkgd": False},
+    "output": {"save_dir": "results/baseline_lego", "val_freq": 10, "save_freq": 50},
+}
+
+
+def test_config_helpers():
+    from training.train import multistep_lr, near_far
+    assert near_far(BASELINE) == (2.0, 6.0)                        # B4: no top-level near/far in baseline.yaml
+    cfg = copy.deepcopy(BASELINE); cfg["near"], cfg["far"] = 1.0, 3.0
+    assert near_far(cfg) == (1.0, 3.0)
+    with pytest.raises(KeyError):
+        near_far({"rendering": {}, "data": {}})
+    sched = torch.optim.lr_scheduler.MultiStepLR(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=5e-4),
+                                                 milestones=[3, 5], gamma=0.5)
+    for epoch in range(1, 8):
+        sched.optimizer.step(); sched.step()
+        assert abs(multistep_lr(5e-4, [3, 5], 0.5, epoch) - sched.get_last_lr()[0]) < 1e-12
+
+
+def test_blender_loader_roundtrip(tmp_path):
+    """models.data_loader.load_blender_data on a two-frame dataset written to disk."""
+    import json
+    import numpy as np
+    from PIL import Image
+    from models.data_loader import load_blender_data
+    os.makedirs(tmp_path / "train")
+    frames = []
+    for i in range(2):
+        Image.fromarray((np.random.RandomState(i).rand(16, 16, 4) * 255).astype("uint8")).save(tmp_path / "train" / ("r_%d.png" % i))
+        frames.append({"file_path": "./train/r_%d" % i, "transform_matrix": np.eye(4).tolist()})
+    json.dump({"camera_angle_x": 0.6911112, "frames": frames}, open(tmp_path / "transforms_train.json", "w"))
+    images, poses, (H, W, focal) = load_blender_data(str(tmp_path), "train", img_size=8)
+    assert images.shape == (2, 3, 8, 8) and poses.shape == (2, 4, 4) and (H, W) == (8, 8)
+    assert abs(focal - 0.5 * 8 / np.tan(0.5 * 0.6911112) * (8 / 16)) < 1e-4     # data_loader.py:40,62
+
+
+@pytest.mark.gpu
+def test_trainer_runs_baseline_config(cuda, tmp_path):
+    from training.train import NeRFDINOTrainer
+    cfg = copy.deepcopy(BASELINE)
+    cfg["data"]["resolution"] = 32
+    cfg["data"]["num_views"] = 3
+    cfg["training"]["batch_size"] = 256
+    cfg["output"] = {"save_dir": str(tmp_path), "val_freq": 2, "save_freq": 3}
+    # NeRFWithDINO's density is relu(linear): at many random inits it is zero everywhere in the scene, the render
+    # is black and no gradient flows (a property of the reference architecture, nerf_mlp.py:61-62) - pick a seed
+    # whose initial density is alive so that "the loss goes down" is a meaningful check
+    for seed in range(40):
+        torch.manual_seed(seed)
+        tr = NeRFDINOTrainer(cfg, device=cuda)
+        probe = (torch.rand(4096, 3, device=cuda) - 0.5) * 2.5
+        with torch.no_grad():
+            _, den = tr.nerf_model(probe, torch.randn(4096, 3, device=cuda), None)
+        if float((den > 0).float().mean()) > 0.2:
+            break
+    else:
+        pytest.skip("no seed with a live initial density in 40 tries")
+    tr.load_synthetic(n_test=1)
+    l0 = tr.train_step(0)
+    for e in range(1, 4):
+        l1 = tr.train_step(e)
+    assert l1 == l1 and l1 < l0, (l0, l1)
+    tr.epoch = 0
+    tr.train(3)
+    ck = torch.load(os.path.join(str(tmp_path), "epoch_3.pth"), weights_only=False)
+    assert set(ck) == {"epoch", "best_psnr", "nerf_model_state_dict", "optimizer_state_dict", "scheduler_state_dict",
+                       "config"}                                                    # train.py:375-382
+    assert os.path.exists(os.path.join(str(tmp_path), "best_%s.pth" % cfg["experiment"]["name"]))
+    m = tr.evaluate(0)
+    assert m["psnr"] > 5.0 and 0.0 < m["ssim"] <= 1.0
+    # the state dict loads into the oracle's restatement of the reference model (names / shapes interchange)
+    from oracle import nerf_oracle as O
+    ref = O.ConditionedNeRF(dino_dim=0)
+    ref.load_state_dict(ck["nerf_model_state_dict"])
+
+
+@pytest.mark.gpu
+def test_trainer_with_feature_maps(cuda, tmp_path):
+    from training.train import NeRFDINOTrainer
+    cfg = copy.deepcopy(BASELINE)
+    cfg["model"]["use_dino"] = True
+    cfg["data"]["resolution"] = 32
+    cfg["data"]["num_views"] = 2
+    cfg["nerf_model"]["pos_freq"] = 12
+    cfg["training"]["batch_size"] = 256
+    cfg["output"] = {"save_dir": str(tmp_path), "val_freq": 100, "save_freq": 100}
+    tr = NeRFDINOTrainer(cfg, device=cuda)
+    tr.load_synthetic(n_test=1)
+    with pytest.raises(RuntimeError):
+        tr.train_step(0)
+    tr.set_feature_maps([torch.randn(1, 9, 9, 64) for _ in range(2)])
+    l0 = tr.train_step(0)
+    l1 = tr.train_step(1)
+    assert l1 == l1 and l1 < l0 * 1.5
