@@ -531,11 +531,12 @@ int launch_bwd_staged(const CompositeArgs &a, cudaStream_t st) {
   constexpr int kRays = (kBlock / 32) * (32 / G);
   const long long n_tiles = (a.n_rays + kRays - 1) / kRays;
   const size_t smem = sizeof(float) * (size_t)kBwdStages * kRays * a.S * (a.g_w ? 6 : 5) + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.need(&attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(composite_bwd_staged_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return fail_cuda("nfs_composite_bwd", e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

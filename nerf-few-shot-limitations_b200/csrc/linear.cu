@@ -248,11 +248,12 @@ extern "C" int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const flo
   while (cols < 2 * n_dim) cols <<= 1;
   a.tmem_cols = cols;
   const size_t smem = 1024 + (size_t)w_bytes + (size_t)stages * kSlabBytesX + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.need(&attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(fn, e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
   const long long n_tiles = (n_points + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());

@@ -23,6 +23,19 @@ static inline int check_launch(const char *where) {
   return 0;
 }
 
+// cudaFuncSetAttribute is per device: remember per (call site, device) whether the opt-in shared-memory size has
+// been set, so that a process driving several GPUs configures the kernel on each of them.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};          // bit d = done on device d (d < 64)
+  bool need(int *dev_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    *dev_out = dev;
+    return dev >= 64 || !((done.load(std::memory_order_acquire) >> dev) & 1ull);
+  }
+  void mark(int dev) { if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release); }
+};
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned8(const void *p)  { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 

@@ -199,11 +199,12 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   while (cols < (m_dim / 128) * n_dim) cols <<= 1;
   a.tmem_cols = cols;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.need(&attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(fn, e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -199,3 +199,28 @@ def test_in_kernel_encoding_matches_two_kernel_route(cuda, P, monkeypatch):
     assert torch.equal(fused, two)
     assert float((fused.cpu()[:, :3] - out_ref[:, :3]).abs().max()) <= 2e-2
     assert float(((fused.cpu()[:, 3] - out_ref[:, 3]).abs() / (3e-2 * out_ref[:, 3].abs() + 1e-2)).max()) <= 1.0
+
+
+def test_chain_stress_repeatable(cuda):
+    """The CTA-pair chain hands tiles between two SMs through mbarriers and remote arrives: a protocol race would
+    show up as run-to-run differences.  Repeat inference, training forward (activations + sign bits) and the dgrad
+    chain on many sizes and demand bit-identical results every time."""
+    from models.nerf_model import NeRFMLP
+    torch.manual_seed(4)
+    mod = NeRFMLP().to(cuda)
+    plan = mod._get_plan()
+    plan.refresh()
+    g = torch.Generator().manual_seed(0)
+    for P in (3, 500, 513, 9999, 74 * 512 + 1, 148 * 512 * 2 + 77):
+        x16 = torch.randn(P, 64, generator=g).to(torch.bfloat16).to(cuda)
+        dy = torch.randn(P, 64, generator=g).to(torch.bfloat16).to(cuda)
+        ref_out, _, ref_save = plan.run_forward_fused(x16, keep=True)
+        ref_dys = plan.dgrad_chain_fused(dy, ref_save[1], P)
+        ref_inf = plan.run_forward_fused(x16, keep=False)[0]
+        assert torch.equal(ref_inf, ref_out)
+        for _ in range(12):
+            out, _, save = plan.run_forward_fused(x16, keep=True)
+            assert torch.equal(out, ref_out)
+            assert torch.equal(save[0][:, :P], ref_save[0][:, :P]) and torch.equal(save[1][:, :P], ref_save[1][:, :P])
+            assert torch.equal(plan.dgrad_chain_fused(dy, save[1], P)[:, :P], ref_dys[:, :P])
+            assert torch.equal(plan.run_forward_fused(x16, keep=False)[0], ref_out)
