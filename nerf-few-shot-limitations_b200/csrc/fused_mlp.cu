@@ -1,4 +1,4 @@
-// K3 (fused multi-layer MLP forward) — a whole chain of dense layers per launch, activations
+// K3 (fused multi-layer MLP, forward and dgrad) — a whole chain of dense layers per launch, activations
 // kept in shared memory / TMEM, weights streamed by TMA, every layer on tcgen05 tensor cores.
 //
 // Replaces the Linear(+ReLU) chain + heads of
@@ -25,9 +25,11 @@
 // the leader CTA and count both CTAs (TMA .cta_group::2 completion, remote mbarrier arrives); barriers
 // the MMA thread signals (accumulator full, weight stage free) are multicast to both CTAs by
 // tcgen05.commit.
-// When activations must be saved for the backward pass each epilogue warp TMA-stores the
-// 32-row x 64-column boxes it has just written (cp.async.bulk.tensor, bulk groups).
-// The last layer of the chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
+// Three instantiations: inference forward (optionally computing the positional encoding of the points
+// in-kernel, K2 fused in), the forward of a training step (each epilogue warp TMA-stores the 32-row x
+// 64-column boxes it has just written, for wgrad, and writes one ReLU sign bit per activation, for the
+// backward), and the dgrad chain (ReLU backward from those sign bits).
+// The last layer of a forward chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
 // written as fp32 with the reference's output activation.
 // Warp roles per CTA: 0 = TMA producer, 1 = TMEM owner (+ MMA issuer in the leader), 2..17 = epilogue
 // (four warps per TMEM lane quadrant, each draining a quarter of the columns of tile A, then of tile B).

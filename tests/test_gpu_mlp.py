@@ -148,7 +148,7 @@ def test_g1_training_tracks_fp32(cuda):
 
 @pytest.mark.parametrize("P", [1, 127, 128, 129, 256, 257, 40000, 148 * 256 * 3 + 5])
 def test_fused_chain_matches_layerwise(cuda, P, monkeypatch):
-    """nfs_mlp_chain_fwd (one launch, activations on chip) == the layer-by-layer launches: same bf16
+    """nfs_mlp_chain (one launch, activations on chip) == the layer-by-layer launches: same bf16
     operands, same fp32 accumulation order per layer -> identical saved activations and outputs."""
     from models.nerf_model import NeRFMLP
     torch.manual_seed(2)
