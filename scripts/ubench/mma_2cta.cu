@@ -23,6 +23,15 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
 }
 __host__ __device__ inline float a_val(int r, int k) { return (float)((r * 7 + k * 3) % 13 - 6); }
 __host__ __device__ inline float b_val(int n, int k) { return (float)((n * 5 + k) % 11 - 5); }
+__host__ __device__ inline float bias_val(int n) { return 0.1234f * (float)n - 7.7f + 1e-3f * (float)(n % 7); }
+__device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                       // layout_type 0 = no swizzle
+}
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -34,7 +43,7 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles, int rotat
   extern __shared__ uint8_t raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint8_t *sa = smem, *sb = smem + 131072;          // A: [128 x 64], B half: [N/2 x 64]
-  uint64_t *bar = (uint64_t *)(smem + 131072 + 98304);
+  uint64_t *bar = (uint64_t *)(smem + 131072 + 81920);
   uint32_t *slot = (uint32_t *)(bar + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = cluster_rank();
@@ -50,6 +59,24 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles, int rotat
     __nv_bfloat16 v[8];
     for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(b_val(r + nh * (int)rank, c * 8 + j));
     *(uint4 *)(sb + r * 128 + ((c ^ (r & 7)) << 4)) = *(uint4 *)v;
+  }
+  // bias operands (no swizzle, K-major core matrices of 8 rows x 16 bytes):
+  //   ones: core matrix 0 = rows of [1,1,1,0,0,0,0,0], core matrix 1 (k = 8..15) = zeros; every 8-row group aliases it (SBO = 0)
+  //   bias: row n = [hi, mid, lo, 0...] (three bf16 terms of the fp32 bias), groups of 8 rows 128 bytes apart
+  uint8_t *s_ones = smem + 131072 + 81920 + 64, *s_bias = s_ones + 256;
+  if (tid < 16) {
+    __nv_bfloat16 v[8];
+    for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16((tid < 8 && j < 3) ? 1.f : 0.f);
+    *(uint4 *)(s_ones + tid * 16) = *(uint4 *)v;
+  }
+  for (int i = tid; i < nh; i += blockDim.x) {
+    const float b = bias_val(i + nh * (int)rank);
+    const __nv_bfloat16 hi = __float2bfloat16(b);
+    const float r1 = b - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16(r1);
+    const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
+    __nv_bfloat16 v[8] = {hi, mid, lo, __float2bfloat16(0.f), __float2bfloat16(0.f), __float2bfloat16(0.f), __float2bfloat16(0.f), __float2bfloat16(0.f)};
+    *(uint4 *)(s_bias + i * 16) = *(uint4 *)v;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (tid == 0) {
@@ -83,7 +110,7 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles, int rotat
           if (!ok) __trap();
         }
         const uint32_t a_off = rotate == 1 ? (uint32_t)(it % 8) * 16384u : 0u;
-        const uint32_t b_off = rotate == 1 ? (uint32_t)(it % 6) * 16384u : 0u;
+        const uint32_t b_off = rotate == 1 ? (uint32_t)(it % 5) * 16384u : 0u;
         const uint32_t d_off = rotate == 1 ? (uint32_t)((it / 4) & 1) * 256u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -93,10 +120,15 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles, int rotat
           asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                        ::"r"(smem_u32(bar + 2)), "h"((uint16_t)3) : "memory");
       }
+    if (rotate == 7)      // D += ones . bias^T
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(tbase), "l"(desc_noswz(smem_u32(s_ones), 128, 0)), "l"(desc_noswz(smem_u32(s_bias), 0, 128)), "r"(idesc), "r"(1u)
+                   : "memory");
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
   }
-  if (rotate >= 5 && warp >= 4) {   // pollers: spin on the local barrier like the chain kernel's epilogue warps
+  if (rotate >= 5 && rotate < 7 && warp >= 4) {   // pollers: spin on the local barrier like the chain kernel's epilogue warps
     uint32_t ok = 0; unsigned spin = 0;
     while (!ok) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -135,7 +167,7 @@ mma2_bench(int N, int iters, float *d_out, unsigned long long *cycles, int rotat
 int main() {
   float *d_out; unsigned long long *cyc;
   cudaMalloc(&d_out, 256 * 256 * 4); cudaMalloc(&cyc, 148 * 8);
-  const int smem = 1024 + 131072 + 98304 + 64;
+  const int smem = 1024 + 131072 + 81920 + 64 + 256 + 2048 + 64;
   cudaFuncSetAttribute(mma2_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   float *h = (float *)malloc(256 * 256 * 4);
   for (int N : {256, 128, 64}) {
@@ -153,6 +185,24 @@ int main() {
         if (err > maxerr) maxerr = err;
         if (err > 1e-3 && bad++ < 4) printf("   mismatch r %d n %d got %f ref %f\n", r, n, h[r * 256 + n], ref);
       }
+    {   // bias MMA check
+      cudaMemset(d_out, 0, 256 * 256 * 4);
+      mma2_bench<<<2, 576, smem>>>(N, 1, d_out, cyc, 7);
+      cudaError_t e2 = cudaDeviceSynchronize();
+      if (e2 != cudaSuccess) { printf("bias MMA N %d: error %s\n", N, cudaGetErrorString(e2)); return 1; }
+      cudaMemcpy(h, d_out, 256 * 256 * 4, cudaMemcpyDeviceToHost);
+      double me = 0; int nbad = 0;
+      for (int r = 0; r < 256; ++r)
+        for (int n = 0; n < N; ++n) {
+          float ref = 0;
+          for (int k = 0; k < 64; ++k) ref += a_val(r, k) * b_val(n, k);
+          ref += bias_val(n);
+          double err = fabs((double)h[r * 256 + n] - ref);
+          if (err > me) me = err;
+          if (err > 1e-3 && nbad++ < 4) printf("   bias mismatch r %d n %d got %f ref %f\n", r, n, h[r * 256 + n], ref);
+        }
+      printf("2-CTA N=%3d + bias MMA (ones x [hi mid lo]): max|D-ref| = %g (%d bad)\n", N, me, nbad);
+    }
     const int iters = 4000;
   for (int rotate : {0, 5, 6}) {
     mma2_bench<<<148, 576, smem>>>(N, iters, nullptr, cyc, rotate);
