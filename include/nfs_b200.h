@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NFS_B200_ABI_VERSION 2
+#define NFS_B200_ABI_VERSION 3
 
 /* negative return codes (argument errors) */
 #define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
@@ -206,7 +206,8 @@ int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int6
  *   backward (X = dL/d(last pre-activation), W_l = transposed weights in reverse order, act 4 = ReLU backward).
  *   Runs on CTA pairs (tcgen05 cta_group::2); activations stay in shared memory / TMEM between layers; weights
  *   are TMA-streamed from one stacked bf16 tensor w_stack [w_rows, 256] (layer l = rows row0[l] .. row0[l]+N_l,
- *   columns 0..K_l, zero padded); biases stacked the same way (bias_stack[row0[l] + n]) or NULL.
+ *   columns 0..K_l, zero padded); biases stacked the same way as bias_terms_bf16 [w_rows, 8] (row row0[l] + n =
+ *   nfs_bias_terms_bf16 of b_l[n]: the bias is added by the tensor core, one K = 16 MMA per tile and layer) or NULL.
  *   K_l, N_l multiples of 64 in [64,256], K_l == N_{l-1}.
  *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 4 ReLU backward: multiply by the sign bit
  *   relu_bits_in[mask_idx[l]][p][n] (layers >= 128 wide).
@@ -221,7 +222,7 @@ int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int6
 int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
                   const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
                   const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
-                  const float *bias_stack,
+                  const void *bias_terms_bf16,
                   const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
                   void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer,
                   float *out_f32, int32_t out_cols, void *stream);
@@ -233,8 +234,8 @@ int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,
  *   The last layer is the fp32 output head (out_f32 [P,out_cols]); nothing is saved. */
 int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
                          int32_t n_layers, const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
-                         const int32_t *row0, const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
-                         float *out_f32, int32_t out_cols, void *stream);
+                         const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
+                         const void *bias_terms_bf16, float *out_f32, int32_t out_cols, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * K2 fused with the operand cast of the first dense layer
@@ -268,6 +269,11 @@ int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float *extra, co
  * these are the cached operand copies refreshed after an optimizer step. */
 int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n_pad, int32_t k_pad,
                          int32_t row0, int32_t col0, void *w_bf16, void *wt_bf16, void *stream);
+
+/* fp32 bias[n] -> terms_bf16 [n, 8] bf16, row i = [hi, mid, lo, 0, 0, 0, 0, 0] with hi + mid + lo = bias[i] to
+ * ~2^-24 relative: the bias operand of nfs_mlp_chain (nn.Linear's "+ b", nerf_model.py:16-24, added on the
+ * tensor core as ones[128x16] . terms^T).  Refreshed with the packed weights after an optimizer step. */
+int nfs_bias_terms_bf16(const float *bias, int32_t n, void *terms_bf16, void *stream);
 
 /* dY (bf16 [P,n_pad], zero padded) = g_out * act'(out) for the fp32 network outputs
  * out, g_out [P,n_cols]: act 0 identity, 1 relu, 2 sigmoid on columns 0..2 (nerf_model.py:22-24),

@@ -52,7 +52,7 @@ struct FusedArgs {
   long long save_rows;                 // rows per layer in the saved-activation tensor (P rounded up to 128)
   int n_layers;
   int K[kFmMaxLayers], N[kFmMaxLayers], act[kFmMaxLayers], row0[kFmMaxLayers];
-  const float *bias;                   // stacked like the weights: bias[row0[l] + n]
+  int has_bias;                        // the biases arrive as a tensor-core operand (tmap_b), see below
   float *out;                          // [P, out_cols] fp32
   int out_cols;
   int save;
@@ -166,23 +166,12 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One epilogue chunk: 16 accumulator columns of one row -> (+bias, read from shared memory: every
-// lane reads the same address = broadcast; packed fp32x2 adds) -> ReLU | ReLU-backward mask | none
+// One epilogue chunk: 16 accumulator columns of one row (the bias is already in the accumulator, see the bias
+// MMA) -> ReLU | ReLU-backward mask | none
 // -> bf16 -> two 16-byte chunks of the row in the SWIZZLE_128B operand layout.
 template <bool kMasked, bool kTrain>
-__device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s, int act, uint32_t bits_word, int j0,
+__device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], int act, uint32_t bits_word, int j0,
                                           uint32_t &bits_acc, uint8_t *srow, int ch, int r7, int dbg) {
-  if (bias_s != nullptr && !(dbg & 8)) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + 4 * g);
-      asm("{\n\t.reg .b64 a, b;\n\t"
-          "mov.b64 a, {%0, %1};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t"
-          "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%6, %7};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%2, %3}, a;\n\t}"
-          : "+r"(r[4 * g]), "+r"(r[4 * g + 1]), "+r"(r[4 * g + 2]), "+r"(r[4 * g + 3])
-          : "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w));
-    }
-  }
   uint32_t pk[8];
   if (act == 1) {
 #pragma unroll
@@ -233,7 +222,8 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], const float *bias_s
 template <bool kMasked, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_save, const FusedArgs a) {
+                 const __grid_constant__ CUtensorMap tmap_save, const __grid_constant__ CUtensorMap tmap_b,
+                 const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw;                      // SWIZZLE_128B operands need 1024-byte alignment (checked below)
   uint8_t *act[2] = {smem, smem + kActBytes};
@@ -247,10 +237,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t *head_done = acc_full + 2;            // [2] this CTA's epilogue is done with act[t] / accumulator t (producer)
   uint64_t *acc_free = head_done + 2;            // [2] leader: both CTAs' epilogues drained accumulator t (MMA thread)
   uint64_t *in_ready = acc_free + 2;             // [2] leader: both CTAs' encoding warps wrote the chain input of tile t
-  uint64_t *bias_full = in_ready + 2;           // [2] bias of a layer landed in bias_s[slot] (bulk copy)
-  uint64_t *bias_empty = bias_full + 2;          // [2] all 16 epilogue warps are done with bias_s[slot]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_empty + 2);
-  float *bias_s = reinterpret_cast<float *>(bars + 32);   // 30 barriers + the TMEM slot fit in 256 bytes;   // [2][256] fp32: the current and the next layer's bias
+  uint64_t *bias_full = in_ready + 2;            // [1] leader: both CTAs' bias operands of the current layer landed (TMA)
+  uint64_t *bias_empty = bias_full + 1;          // [1] both bias MMAs of the layer have read the operand (commit, multicast)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_empty + 1);
+  // The bias enters the accumulator through the tensor core: one extra K = 16 MMA per tile and layer multiplies a
+  // constant "ones" operand (rows of [1,1,1,0,...]) by the layer's bias operand (row n = [hi, mid, lo, 0, ...], the
+  // fp32 bias split into three bf16 terms, exact to ~2^-24).  Both are un-swizzled K-major core matrices; every 8-row
+  // group of the ones operand aliases the same 128 bytes (SBO = 0) and the bias operand's second K core matrix
+  // aliases its first (LBO = 0: it only meets the zero half of the ones rows).  This takes 16 shared-memory loads and
+  // 32 adds per thread and tile out of the epilogue, which is the critical path (scripts/ubench/mma_2cta.cu).
+  uint8_t *s_ones = reinterpret_cast<uint8_t *>(bars + 32);          // 256 B
+  uint8_t *s_bias = s_ones + 256;                                    // [N/2 <= 128 rows x 16 B] of this CTA
 
   // warp index through a shuffle: the compiler then treats it (and every branch on it) as warp-uniform and
   // keeps the MMA / TMA operands in uniform registers instead of R2UR "waterfall" loops per instruction
@@ -270,12 +267,18 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 32);
       mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16); mbar_init(acc_free + t, 32);
       mbar_init(in_ready + t, 8);
-      mbar_init(bias_full + t, 1); mbar_init(bias_empty + t, 16);
     }
+    mbar_init(bias_full, 1); mbar_init(bias_empty, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     if (a.save) tma_prefetch_desc(&tmap_save);
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 80) {      // the "ones" operand: core matrix 0 = rows of [1,1,1,0,...], core matrix 1 = 0
+    const int i = threadIdx.x - 64;
+    const uint32_t one2 = 0x3F803F80u, one1 = 0x00003F80u;           // bf16 {1,1}, {1,0}
+    *reinterpret_cast<uint4 *>(s_ones + i * 16) = i < 8 ? make_uint4(one2, one1, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
   }
   if (warp == 1) {                                 // the pair allocates together: warp 1 of both CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -303,14 +306,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int l = 0; l < L; ++l) {
           const int ks = a.K[l] >> 6, nh = a.N[l] >> 1;           // this CTA's half of the output rows
           const int nb = (nh + 63) >> 6;                          // 64-row TMA boxes (a 32-row half loads a full box)
-          if (a.bias != nullptr) {
-            const uint32_t gl = iter * (uint32_t)L + (uint32_t)l, slot = gl & 1;
-            mbar_wait_relaxed(bias_empty + slot, ((gl >> 1) & 1) ^ 1);
-            mbar_expect_tx(bias_full + slot, (uint32_t)(a.N[l] * 4));
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(bias_s + slot * 256)), "l"(a.bias + a.row0[l]), "r"(a.N[l] * 4),
-                           "r"(smem_u32(bias_full + slot)) : "memory");
-          }
           for (int s = 0; s < ks; ++s, ++wit) {
             const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
             if ((NFS_DBG(a) & 2) && wit >= kWStages) continue;
@@ -319,6 +314,15 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int b = 0; b < nb; ++b)
               tma_load_2d_pair(wring + stage * kWStage + b * 8192, &tmap_w, w_full + stage, s * 64,
                                a.row0[l] + (int)rank * nh + b * 64);
+            // The bias operand (single buffer) is released when the previous layer's B pass STARTS (its bias MMA
+            // is issued first), about when that layer's first weight stages come free: loading it here, between
+            // the weight stages, keeps the weight prefetch running ahead.
+            if (s == (ks > 1 ? 1 : 0) && a.has_bias && !(NFS_DBG(a) & 8)) {
+              const uint32_t gl = iter * (uint32_t)L + (uint32_t)l;
+              mbar_wait_relaxed(bias_empty, (gl & 1) ^ 1);
+              if (rank == 0) mbar_expect_tx(bias_full, 2u * 2048u);
+              tma_load_2d_pair(s_bias, &tmap_b, bias_full, 0, a.row0[l] + (int)rank * nh);
+            }
           }
         }
       }
@@ -329,6 +333,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       uint32_t wit = 0, iter = 0, n_ready[2] = {0, 0};
       const uint64_t b_desc0 = umma_desc_sw128(smem_u32(wring), 16, 1024);
       const bool no_mma = (NFS_DBG(a) & 4) != 0;
+      const bool use_bias = a.has_bias && !(NFS_DBG(a) & 8);
+      const uint64_t ones_desc = umma_desc_noswizzle(smem_u32(s_ones), 128, 0);
+      const uint64_t bias_desc = umma_desc_noswizzle(smem_u32(s_bias), 0, 128);
       for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
         // Issue order per layer: tile major - 4*ks MMAs on the pair's A tiles, then 4*ks on the B tiles.
         // Long runs on one accumulator (switching the D operand between consecutive MMAs costs
@@ -351,6 +358,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
             // descriptors differ only in their 14-bit start-address field: +2 per 32-byte K step
             const uint64_t a_desc0 = umma_desc_sw128(smem_u32(act[0]) + (uint32_t)t * kActBytes, 16, 1024);
+            if (t == 1 && use_bias) {           // tile B: bias first, which frees the operand for the next layer
+              if (elect_one()) {
+                umma_bf16_pair(d_tmem, ones_desc, bias_desc, idesc, 0u);
+                umma_commit_pair(bias_empty);
+              }
+              __syncwarp();
+            }
             for (int s = 0; s < ks; ++s) {
               const uint32_t w = wit + s, stage = w % kWStages, wph = (w / kWStages) & 1;
               if (t == 0) {
@@ -361,13 +375,19 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               const uint64_t bd = b_desc0 + (uint64_t)((stage * kWStage) >> 4);
               if (elect_one()) {
                 if (!no_mma) {
-                  umma_bf16_pair(d_tmem, ad, bd, idesc, (uint32_t)(s != 0));
+                  umma_bf16_pair(d_tmem, ad, bd, idesc, (uint32_t)(s != 0 || (t == 1 && use_bias)));
                   umma_bf16_pair(d_tmem, ad + 2, bd + 2, idesc, 1u);
                   umma_bf16_pair(d_tmem, ad + 4, bd + 4, idesc, 1u);
                   umma_bf16_pair(d_tmem, ad + 6, bd + 6, idesc, 1u);
                 }
                 if (t == 1) umma_commit_pair(w_empty + stage);
               }
+              __syncwarp();
+            }
+            if (t == 0 && use_bias) {           // tile A: bias last (its operand has had the whole pass to land)
+              mbar_wait_cluster(bias_full, (iter * (uint32_t)L + (uint32_t)l) & 1);
+              tc_fence_after();
+              if (elect_one()) umma_bf16_pair(d_tmem, ones_desc, bias_desc, idesc, 1u);
               __syncwarp();
             }
             NFS_TRACE(2, l, t);
@@ -446,11 +466,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bool is_head = last && a.head != 0;
         const int Nl = a.N[l], quarter = Nl >> 2, c0 = cq * quarter;
         const int act_l = a.act[l];
-        const float *bias = nullptr;                // this warp's columns of the layer's bias, in shared memory
-        if (a.bias != nullptr) {
-          mbar_wait_relaxed(bias_full + (gl & 1), (gl >> 1) & 1);
-          bias = bias_s + (gl & 1) * 256 + c0;
-        }
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
           const long long tile = 4 * quad + 2 * rank + t;
@@ -506,7 +521,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (c < n_chunks) {
                   tmem_ld16_async(taddr + c0 + 16 * c, va);
                   tmem_ld_wait();
-                  epi_chunk<kMasked, kTrain>(va, bias ? bias + 16 * c : nullptr, act_l, (c >> 1) ? b_cur.y : b_cur.x, 8 * (c & 1),
+                  epi_chunk<kMasked, kTrain>(va, act_l, (c >> 1) ? b_cur.y : b_cur.x, 8 * (c & 1),
                                      bits_acc[c >> 1], srow, ch0 + 2 * c, r_in & 7, NFS_DBG(a));
                 }
               }
@@ -545,7 +560,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   if (j < a.out_cols) {
-                    float x = v[j] + (bias ? bias[j] : 0.f);
+                    float x = v[j];
                     if (act_l == 1) x = fmaxf(x, 0.f);
                     else if (act_l == 3 || (act_l == 2 && j < 3)) x = fm_sigmoid(x);
                     v[j] = x;
@@ -567,10 +582,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
         }
         if (last) store_pending = false;
-        if (a.bias != nullptr) {                    // both tiles have consumed this layer's bias
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bias_empty + (gl & 1));
-        }
       }
     }
     if (lane == 0) bulk_wait0();               // all saved activations are in global memory
@@ -600,7 +611,7 @@ extern "C" void nfs_set_debug_trace(void *buf) { g_fm_trace = (unsigned long lon
 static int launch_chain(const char *fn, const void *x_bf16, const float *points, float freq0, int n_octaves,
                         int64_t n_points, int32_t n_layers, const int32_t *k_dims,
                         const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
-                        const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                        const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16,
                         const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
                         void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
                         int32_t out_cols, void *stream) {
@@ -609,7 +620,7 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   if ((!x_bf16 && !points) || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || (!out_f32 && !save_bf16))
     return fail_arg(fn, NFS_E_BADARG, "null pointer");
   FusedArgs a{};
-  a.P = n_points; a.n_layers = n_layers; a.bias = bias_stack; a.out = out_f32; a.out_cols = out_cols;
+  a.P = n_points; a.n_layers = n_layers; a.has_bias = bias_terms_bf16 != nullptr; a.out = out_f32; a.out_cols = out_cols;
   a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
   a.head = out_f32 != nullptr;
   a.points = points; a.freq0 = freq0; a.n_octaves = n_octaves;
@@ -643,7 +654,7 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
     for (int l = 0; l < n_saved; ++l)
       if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal layer widths");
 
-  CUtensorMap tx{}, tw{}, ts{};
+  CUtensorMap tx{}, tw{}, ts{}, tb{};
   int rc = 0;
   if (points != nullptr) {
     if (a.K[0] != 64 || n_octaves < 1 || n_octaves > 10)
@@ -654,12 +665,16 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   }
   rc = tc::make_tmap_bf16(&tw, w_stack_bf16, (uint64_t)w_rows, 256, 256, 64, fn);
   if (rc) return rc;
+  if (bias_terms_bf16 != nullptr) {
+    rc = tc::make_tmap_rows16(&tb, bias_terms_bf16, (uint64_t)w_rows, 128, fn);
+    if (rc) return rc;
+  }
   if (a.save) {
     rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * n_saved), (uint64_t)a.N[0],
                             (uint64_t)a.N[0], 32, fn);
     if (rc) return rc;
   }
-  const size_t smem = 2 * kActBytes + kWStages * kWStage + 256 + 2 * 256 * sizeof(float);
+  const size_t smem = 2 * kActBytes + kWStages * kWStage + 256 + 256 + 128 * 16;   // tiles, weight ring, barriers, ones, bias operand
   static PerDeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.need(&attr_dev)) {
@@ -677,30 +692,30 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   const long long max_pairs = sms / 2;
   const unsigned grid = 2u * (unsigned)(n_quads < max_pairs ? n_quads : max_pairs);   // whole CTA pairs
   if (relu_bits_in != nullptr)
-    fused_mlp_kernel<true, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+    fused_mlp_kernel<true, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
   else if (a.save || relu_bits_out)
-    fused_mlp_kernel<false, true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+    fused_mlp_kernel<false, true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
   else
-    fused_mlp_kernel<false, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, a);
+    fused_mlp_kernel<false, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
   return check_launch(fn);
 }
 
 extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
                              const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
-                             const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                             const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16,
                              const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
                              void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
                              int32_t out_cols, void *stream) {
   return launch_chain("nfs_mlp_chain", x_bf16, nullptr, 0.f, 0, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
-                      w_rows, bias_stack, relu_bits_in, bits_rows_per_layer, mask_idx, save_bf16, relu_bits_out,
+                      w_rows, bias_terms_bf16, relu_bits_in, bits_rows_per_layer, mask_idx, save_bf16, relu_bits_out,
                       save_rows_per_layer, out_f32, out_cols, stream);
 }
 
 extern "C" int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
                                     int32_t n_layers, const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
-                                    const int32_t *row0, const void *w_stack_bf16, int32_t w_rows, const float *bias_stack,
+                                    const int32_t *row0, const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16,
                                     float *out_f32, int32_t out_cols, void *stream) {
   if (!points || !out_f32) return fail_arg("nfs_mlp_chain_points", NFS_E_BADARG, "null pointer");
   return launch_chain("nfs_mlp_chain_points", nullptr, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0,
-                      w_stack_bf16, w_rows, bias_stack, nullptr, 0, nullptr, nullptr, nullptr, 0, out_f32, out_cols, stream);
+                      w_stack_bf16, w_rows, bias_terms_bf16, nullptr, 0, nullptr, nullptr, nullptr, 0, out_f32, out_cols, stream);
 }

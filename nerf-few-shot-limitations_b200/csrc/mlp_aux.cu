@@ -233,6 +233,30 @@ extern "C" int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim
   return check_launch(fn);
 }
 
+// fp32 bias -> the [n, 8] bf16 operand of the chain kernel's bias MMA: row i = [hi, mid, lo, 0, 0, 0, 0, 0] with
+// hi + mid + lo == bias[i] to ~2^-24 relative (three round-to-nearest bf16 terms).
+__global__ void bias_terms_kernel(const float *__restrict__ bias, int n, uint4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float b = bias[i];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const float r1 = b - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  out[i] = make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                      (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+}
+
+extern "C" int nfs_bias_terms_bf16(const float *bias, int32_t n, void *terms_bf16, void *stream) {
+  const char *fn = "nfs_bias_terms_bf16";
+  if (n < 0) return fail_arg(fn, NFS_E_BADARG, "negative size");
+  if (n == 0) return 0;
+  if (!bias || !terms_bf16) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  if (!aligned16(terms_bf16)) return fail_arg(fn, NFS_E_ALIGN, "terms_bf16 must be 16-byte aligned");
+  bias_terms_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bias, n, (uint4 *)terms_bf16);
+  return check_launch(fn);
+}
+
 extern "C" int nfs_act_grad_bf16(const float *out, const float *g_out, int64_t n_points, int32_t n_cols, int32_t act,
                                  int32_t n_pad, int64_t dy_pitch, void *dy_bf16, void *stream) {
   const char *fn = "nfs_act_grad_bf16";

@@ -18,6 +18,10 @@ namespace tc {
 int make_tmap_bf16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                    uint32_t box_rows, const char *where);
 
+// [rows, 8] bf16 tensor (16-byte rows, e.g. the three-term bias operand), box = [box_rows, 8] with no swizzle: the
+// shared-memory image is box_rows x 16 bytes, contiguous = K-major core matrices of 8 rows x 16 bytes.
+int make_tmap_rows16(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, const char *where);
+
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -155,6 +159,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;   // layout_type = SWIZZLE_128B
+  return d;
+}
+
+// Shared-memory matrix descriptor without swizzle: K-major core matrices (8 rows x 16 bytes = 128 contiguous bytes);
+// LBO = bytes between core matrices adjacent in K, SBO = bytes between 8-row groups (0 = every group aliases the first).
+__device__ __forceinline__ uint64_t umma_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell); layout_type 0 = no swizzle
   return d;
 }
 

@@ -49,8 +49,9 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        if (not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))):
+        newest = max([os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)] + [os.path.getmtime(
+            os.path.join(os.path.dirname(PKG_ROOT), "include", "nfs_b200.h"))])
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > newest:
             continue
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "-c", src, "-o", obj]

@@ -93,6 +93,14 @@ class PackedLinear:
         return self
 
 
+def bias_terms(b):
+    """fp32 bias vector -> [n, 8] bf16 operand of the chain kernel's bias MMA (nfs_bias_terms_bf16)."""
+    out = torch.empty((b.numel(), 8), device=b.device, dtype=torch.bfloat16)
+    with torch.cuda.device(b.device):
+        _lib.call("nfs_bias_terms_bf16", ptr(b), b.numel(), ptr(out), _stream())
+    return out
+
+
 _freq_cache = {}
 _pow2_cache = {}
 
@@ -224,7 +232,7 @@ class G1Plan:
             b[r:r + p.n_pad].copy_(p.bias)
             row0.append(r)
             r += p.n_pad
-        self.w_stack, self.b_stack, self.w_rows = w, b, rows
+        self.w_stack, self.b_stack, self.w_rows = w, bias_terms(b), rows
         n = len(layers)
         arr = ctypes.c_int32 * n
         self.c_k = arr(*[p.k_pad for p in layers])

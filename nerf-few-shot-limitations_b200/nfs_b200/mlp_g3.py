@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from ._lib import ptr
-from .mlp import PackedLinear, act_grad, encode_operand, pad_hidden, pad_in, _ceil_to
+from .mlp import PackedLinear, act_grad, bias_terms, encode_operand, pad_hidden, pad_in, _ceil_to
 from .ops import _stream
 
 
@@ -55,7 +55,7 @@ class _Stack:
                 b[r:r + m.shape[0]].copy_(p.bias)
             row0.append(r)
             r += m.shape[0]
-        self.w, self.b, self.rows = w, b, rows
+        self.w, self.b, self.rows = w, (None if b is None else bias_terms(b)), rows
         self.c_row0 = _i32arr(row0)
         self.c_k = _i32arr([m.shape[1] for m in mats])
         self.c_n = _i32arr([m.shape[0] for m in mats])

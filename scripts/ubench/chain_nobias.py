@@ -1,5 +1,6 @@
+"""Chain kernel with and without the bias operand (how much the bias costs)."""
 import os, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "nerf-few-shot-limitations_b200")]
 import torch
 from models.nerf_model import NeRFMLP
