@@ -75,6 +75,26 @@ int nfs_composite_fwd(const float *rgb, const float *density, const float *z_val
                       float *out_rgb, float *out_depth, float *out_weights,
                       void *stream);
 
+/* The forward with the loss fused into its epilogue: the same compositing, then, while the
+ * pixel is still in registers,
+ *   sum (rgb - target_rgb)^2            -> F.mse_loss(pred['rgb'], target['rgb'])   nerf_mlp.py:235, train.py:40
+ *   sum |depth - target_depth|          -> F.l1_loss(pred['depth'], target['depth']) nerf_mlp.py:240 (target_depth|NULL)
+ * are accumulated (fp64 atomics) into loss_sums[32][2] (32 slots the caller zeroes and sums: slot = block % 32;
+ * [.][0] squared error, [.][1] absolute depth error), and the upstream gradients of
+ *   loss = rgb_weight * mse + depth_weight * l1
+ * are written for nfs_composite_bwd:  g_rgb (N,3) = rgb_weight * 2 (rgb - target) / (3 N),
+ *   g_depth (N)|NULL = depth_weight * sign(depth - target_depth) / N.
+ * Everything else as nfs_composite_fwd (out_weights may be NULL when no resampling pass follows). */
+int nfs_composite_loss_fwd(const float *rgb, const float *density, const float *z_vals,
+                           const float *rays_d, const float *noise, float noise_std,
+                           const float *target_rgb, const float *target_depth,
+                           float rgb_weight, float depth_weight,
+                           int64_t n_rays, int32_t n_samples,
+                           int32_t white_bkgd, int32_t packed,
+                           float *out_rgb, float *out_depth, float *out_weights,
+                           float *g_rgb, float *g_depth, double *loss_sums,
+                           void *stream);
+
 /* Backward of the above by recomputation from the inputs (nothing is saved by
  * the forward).  Closed form of the autograd graph of nerf_mlp.py:181-215:
  *   G_i       = g_rgb.rgb_i + g_depth z_i + g_w_i - white_bkgd * sum_c g_rgb_c
@@ -300,6 +320,23 @@ int nfs_adam_step_dev(float *param, const float *grad, float *exp_avg, float *ex
                       int64_t n, float beta1, float beta2, float eps, float weight_decay,
                       int32_t *step_counter, float *state, float grad_scale, int32_t decoupled,
                       void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * K6  Ray generation + batch assembly
+ *   models.ray_sampler.get_rays (src/models/ray_sampler.py:4-30), utils.ray_utils.get_rays
+ *   (src/utils/ray_utils.py:4-37) and the per-batch gather of train.py:272-278
+ *   (rays_o_full.view(-1,3)[idx], rays_d_full.view(-1,3)[idx], target_rgb_full.view(-1,3)[idx]) in one launch:
+ *     pixel p = pix_idx[r] (row-major, p = j * width + i; pix_idx NULL: p = r and n_rays = height * width)
+ *     dirs   = [(i - width*0.5) / focal, -(j - height*0.5) / focal, -1]
+ *     rays_d[r] = sum(dirs * c2w[:3,:3], -1)   rays_o[r] = c2w[:3,3]   target[r] = image[p]
+ *   Bit-exact with the reference's CPU arithmetic (true division, products rounded one by one, left-to-right sum).
+ *   c2w: device pointer to a row-major (3|4, 4) pose with c2w_row_stride floats per row; image (height*width,3)|NULL;
+ *   rays_o / rays_d / target (n_rays,3), each may be NULL (target and image go together).  An index outside
+ *   [0, height*width) yields NaN rays (torch would raise).
+ * ------------------------------------------------------------------------- */
+int nfs_rays_generate(int32_t height, int32_t width, float focal, const float *c2w, int32_t c2w_row_stride,
+                      const int64_t *pix_idx, int64_t n_rays, const float *image,
+                      float *rays_o, float *rays_d, float *target, void *stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,14 @@ struct CompositeArgs {
   // backward inputs / outputs
   const float *g_rgb, *g_depth, *g_w;
   float *d_rgb, *d_density;
+  // fused loss epilogue of the forward (nfs_composite_loss_fwd); target == nullptr: plain forward
+  const float *target, *target_depth;
+  float rgb_coef, depth_coef;          // rgb_weight * 2 / (3 N), depth_weight / N
+  float *g_rgb_out, *g_depth_out;
+  double *loss_sums;                   // [kLossSlots][2]: sum (rgb - target)^2, sum |depth - target_depth|
 };
+
+constexpr int kLossSlots = 32;
 
 constexpr int kBlock = 256;
 
@@ -254,6 +261,39 @@ __global__ void __launch_bounds__(kBlock) composite_fwd_kernel(const CompositeAr
     }
     a.out_rgb[ray * 3] = acc_r; a.out_rgb[ray * 3 + 1] = acc_g; a.out_rgb[ray * 3 + 2] = acc_b;
     if (a.out_depth != nullptr) a.out_depth[ray] = acc_d;
+  }
+  if (a.target != nullptr) {
+    // Loss epilogue (block-uniform branch): F.mse_loss(rgb, target) (nerf_mlp.py:235, train.py:40) and
+    // F.l1_loss(depth, target_depth) (nerf_mlp.py:240) evaluated where the pixel is still in registers; the
+    // upstream gradients of the compositing backward leave this kernel instead of a chain of torch kernels.
+    float se = 0.f, ae = 0.f;
+    if (ray_ok && gl == 0) {
+      const float d0 = acc_r - __ldg(a.target + ray * 3), d1 = acc_g - __ldg(a.target + ray * 3 + 1),
+                  d2 = acc_b - __ldg(a.target + ray * 3 + 2);
+      se = d0 * d0 + d1 * d1 + d2 * d2;
+      a.g_rgb_out[ray * 3] = a.rgb_coef * d0; a.g_rgb_out[ray * 3 + 1] = a.rgb_coef * d1;
+      a.g_rgb_out[ray * 3 + 2] = a.rgb_coef * d2;
+      if (a.target_depth != nullptr) {
+        const float dd = acc_d - __ldg(a.target_depth + ray);
+        ae = fabsf(dd);
+        a.g_depth_out[ray] = dd > 0.f ? a.depth_coef : (dd < 0.f ? -a.depth_coef : 0.f);   // sign(dd), l1_loss backward
+      }
+    }
+    __shared__ float red[2][kBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      se += __shfl_xor_sync(0xffffffffu, se, o);
+      ae += __shfl_xor_sync(0xffffffffu, ae, o);
+    }
+    if (lane == 0) { red[0][threadIdx.x >> 5] = se; red[1][threadIdx.x >> 5] = ae; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) t += (double)red[threadIdx.x][w];
+      if (threadIdx.x == 0 || a.target_depth != nullptr)
+        atomicAdd(a.loss_sums + 2 * (blockIdx.x % kLossSlots) + threadIdx.x, t);
+    }
   }
 }
 
@@ -607,6 +647,34 @@ extern "C" int nfs_composite_fwd(const float *rgb, const float *density, const f
   a.rgb = rgb; a.density = density; a.z = z_vals; a.rays_d = rays_d; a.noise = noise; a.noise_std = noise_std;
   a.n_rays = n_rays; a.S = n_samples; a.white = white_bkgd;
   a.out_rgb = out_rgb; a.out_depth = out_depth; a.out_w = out_weights;
+  const bool aligned = (n_samples % 4 == 0) && aligned16(rgb) && aligned16(z_vals) &&
+                       (packed || aligned16(density)) && (!noise || aligned16(noise)) &&
+                       (!out_weights || aligned16(out_weights));
+  return dispatch<true>(a, aligned, packed != 0, (cudaStream_t)stream);
+}
+
+extern "C" int nfs_composite_loss_fwd(const float *rgb, const float *density, const float *z_vals,
+                                      const float *rays_d, const float *noise, float noise_std,
+                                      const float *target_rgb, const float *target_depth,
+                                      float rgb_weight, float depth_weight,
+                                      int64_t n_rays, int32_t n_samples, int32_t white_bkgd, int32_t packed,
+                                      float *out_rgb, float *out_depth, float *out_weights,
+                                      float *g_rgb, float *g_depth, double *loss_sums, void *stream) {
+  const char *fn = "nfs_composite_loss_fwd";
+  if (n_rays < 0 || n_samples <= 0) return fail_arg(fn, NFS_E_BADARG, "n_rays < 0 or n_samples <= 0");
+  if (n_rays == 0) return 0;
+  if (!rgb || !z_vals || !rays_d || !out_rgb || (!packed && !density) || !target_rgb || !g_rgb || !loss_sums)
+    return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  if (target_depth != nullptr && (!g_depth || !out_depth))
+    return fail_arg(fn, NFS_E_BADARG, "a depth target needs the g_depth and out_depth outputs");
+  CompositeArgs a{};
+  a.rgb = rgb; a.density = density; a.z = z_vals; a.rays_d = rays_d; a.noise = noise; a.noise_std = noise_std;
+  a.n_rays = n_rays; a.S = n_samples; a.white = white_bkgd;
+  a.out_rgb = out_rgb; a.out_depth = out_depth; a.out_w = out_weights;
+  a.target = target_rgb; a.target_depth = target_depth;
+  a.rgb_coef = (float)(2.0 * (double)rgb_weight / (3.0 * (double)n_rays));
+  a.depth_coef = (float)((double)depth_weight / (double)n_rays);
+  a.g_rgb_out = g_rgb; a.g_depth_out = g_depth; a.loss_sums = loss_sums;
   const bool aligned = (n_samples % 4 == 0) && aligned16(rgb) && aligned16(z_vals) &&
                        (packed || aligned16(density)) && (!noise || aligned16(noise)) &&
                        (!out_weights || aligned16(out_weights));

@@ -10,16 +10,11 @@ from nfs_b200 import ops as _ops
 
 
 def get_rays(H, W, focal, c2w):
-    """Pinhole rays for every pixel: rays_o, rays_d of shape (H, W, 3) on c2w's device.
-    Same arithmetic as ray_sampler.py:18-30 (meshgrid 'xy', dirs . R^T by multiply+sum).
-    Runs once per view, outside the per-ray hot path."""
-    device = c2w.device
-    i, j = torch.meshgrid(torch.arange(W, dtype=torch.float32, device=device),
-                          torch.arange(H, dtype=torch.float32, device=device), indexing="xy")
-    dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], -1)
-    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
-    rays_o = c2w[:3, 3].expand(rays_d.shape)
-    return rays_o, rays_d
+    """Pinhole rays for every pixel: rays_o, rays_d of shape (H, W, 3) on c2w's device - one kernel
+    (nfs_rays_generate), bit-exact with the CPU arithmetic of ray_sampler.py:18-30 (meshgrid 'xy',
+    dirs . R^T by multiply + sum).  c2w: (3,4) or (4,4) CUDA tensor."""
+    rays_o, rays_d = _ops.generate_rays(H, W, focal, c2w)
+    return rays_o.reshape(H, W, 3), rays_d.reshape(H, W, 3)
 
 
 def sample_points_along_rays(rays_o, rays_d, near, far, N_samples, perturb=True):

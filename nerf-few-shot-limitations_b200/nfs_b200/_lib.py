@@ -27,6 +27,9 @@ SIGNATURES = {
     "nfs_set_debug_trace": (None, [_p]),
     "nfs_composite_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "nfs_composite_bwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "nfs_composite_loss_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _f32, _f32, _i64, _i32, _i32, _i32,
+                                              _p, _p, _p, _p, _p, _p, _p]),
+    "nfs_rays_generate": (ctypes.c_int, [_i32, _i32, _f32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
     "nfs_posenc_fwd": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p]),
     "nfs_sample_stratified": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p]),
     "nfs_project_gather": (ctypes.c_int, [_p, _p, _f32, _i32, _i32, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p]),

@@ -120,6 +120,124 @@ def composite_packed(rgb_sigma, z_vals, rays_d, noise=None, noise_std=0.0, white
     return o_rgb.reshape(*lead, 3)
 
 
+class _CompositeLossFn(torch.autograd.Function):
+    """Compositing with the loss in its epilogue (nfs_composite_loss_fwd): the only differentiable
+    output is the loss; the kernel has already written d loss / d rgb_map (and d depth), so the backward
+    is nfs_composite_bwd on those, scaled by the incoming gradient of the loss."""
+
+    @staticmethod
+    def forward(ctx, rgb, density, z_vals, rays_d, target, target_depth, rgb_weight, depth_weight, white_bkgd,
+                packed, want_weights):
+        n_samples = z_vals.shape[-1]
+        n_rays = z_vals.numel() // n_samples
+        dev = z_vals.device
+        out_rgb = torch.empty((n_rays, 3), device=dev, dtype=torch.float32)
+        out_depth = torch.empty((n_rays,), device=dev, dtype=torch.float32)
+        out_w = torch.empty((n_rays, n_samples), device=dev, dtype=torch.float32) if want_weights else None
+        g_rgb = torch.empty((n_rays, 3), device=dev, dtype=torch.float32)
+        g_depth = torch.empty((n_rays,), device=dev, dtype=torch.float32) if target_depth is not None else None
+        sums = torch.zeros((32, 2), device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _lib.call("nfs_composite_loss_fwd", ptr(rgb), ptr(density), ptr(z_vals), ptr(rays_d), None, 0.0,
+                      ptr(target), ptr(target_depth), float(rgb_weight), float(depth_weight), n_rays, n_samples,
+                      int(bool(white_bkgd)), int(bool(packed)), ptr(out_rgb), ptr(out_depth), ptr(out_w),
+                      ptr(g_rgb), ptr(g_depth), ptr(sums), _stream())
+        terms = sums.sum(0)                                   # [sum sq err, sum abs depth err] (fp64)
+        mse = (terms[0] / (3.0 * n_rays)).float()
+        l1 = (terms[1] / float(n_rays)).float() if target_depth is not None else None
+        loss = rgb_weight * mse if l1 is None else rgb_weight * mse + depth_weight * l1
+        ctx.save_for_backward(rgb, density, z_vals, rays_d, g_rgb, g_depth)
+        ctx.cfg = (int(bool(white_bkgd)), int(bool(packed)), n_rays, n_samples)
+        outs = (loss, mse, l1, out_rgb, out_depth, out_w)
+        ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
+        ctx.set_materialize_grads(False)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_loss, *_unused):
+        rgb, density, z_vals, rays_d, g_rgb, g_depth = ctx.saved_tensors
+        white, packed, n_rays, n_samples = ctx.cfg
+        none = (None,) * 9
+        if g_loss is None:
+            return (None, None) + none
+        g_rgb = g_rgb * g_loss
+        if g_depth is not None:
+            g_depth = g_depth * g_loss
+        d_rgb = torch.empty_like(rgb)
+        d_density = None if packed else torch.empty_like(density)
+        with torch.cuda.device(z_vals.device):
+            _lib.call("nfs_composite_bwd", ptr(rgb), ptr(density), ptr(z_vals), ptr(rays_d), None, 0.0, ptr(g_rgb),
+                      ptr(g_depth), None, n_rays, n_samples, white, packed, ptr(d_rgb), ptr(d_density), _stream())
+        return (d_rgb, d_density) + none
+
+
+def composite_loss(rgb, density, z_vals, rays_d, target_rgb, target_depth=None, rgb_weight=1.0, depth_weight=0.1,
+                   white_bkgd=False, want_weights=False):
+    """VolumeRenderer.forward (nerf_mlp.py:165-215) followed by the rgb / depth terms of NeRFLoss
+    (nerf_mlp.py:225-258; train.py:36-44 is the rgb term alone) in ONE kernel.
+
+    rgb (N,S,3) + density (N,S,1)|(N,S), or rgb = packed (N,S,4) [r,g,b,sigma] with density None;
+    z_vals (N,S); rays_d (N,3); target_rgb (N,3); target_depth (N)|None.
+    Returns a dict: 'total' = rgb_weight * mse [+ depth_weight * l1] (the only differentiable entry),
+    'rgb' = mse, ['depth' = l1,] and the detached renderings 'rgb_map', 'depth_map' [, 'weights'].
+    The regularisation term of NeRFLoss (mean(weights^2)) is not fused: callers that use it composite with
+    ops.composite and apply models.nerf_mlp.NeRFLoss."""
+    packed = density is None
+    _need_cuda("composite_loss", rgb, density, z_vals, rays_d, target_rgb, target_depth)
+    if z_vals.dim() != 2 or z_vals.shape[1] < 2:
+        raise RuntimeError("composite_loss: z_vals must be (N,S) with S >= 2")
+    N, S = z_vals.shape
+    if not packed and density.dim() == 3:
+        density = density.reshape(N, S)
+    if rgb.shape != (N, S, 4 if packed else 3) or (not packed and density.shape != (N, S)) or rays_d.shape != (N, 3) \
+            or target_rgb.shape != (N, 3) or (target_depth is not None and target_depth.shape != (N,)):
+        raise RuntimeError("composite_loss: shape mismatch")
+    if N == 0:
+        raise RuntimeError("composite_loss: empty batch (the mean of no pixels is undefined)")
+    loss, mse, l1, o_rgb, o_depth, o_w = _CompositeLossFn.apply(
+        _f32c(rgb), _f32c(density), _f32c(z_vals), _f32c(rays_d), _f32c(target_rgb), _f32c(target_depth),
+        float(rgb_weight), float(depth_weight), white_bkgd, packed, want_weights)
+    out = {"total": loss, "rgb": mse, "rgb_map": o_rgb, "depth_map": o_depth}
+    if l1 is not None:
+        out["depth"] = l1
+    if o_w is not None:
+        out["weights"] = o_w
+    return out
+
+
+# --------------------------------------------------------------------------- K6
+def generate_rays(H, W, focal, c2w, pix_idx=None, image=None):
+    """get_rays (ray_sampler.py:4-30 / ray_utils.py:4-37) for the pixels pix_idx (int64, row-major p = j*W + i;
+    None = every pixel in order) plus the gather of their colours from image (H,W,3)|(H*W,3)|None - the batch
+    assembly of train.py:272-278 - in one kernel.  Returns rays_o, rays_d (n,3) [, target (n,3)].
+    Bit-exact with the reference's CPU arithmetic."""
+    _need_cuda("generate_rays", c2w, pix_idx, image)
+    if c2w.dim() != 2 or c2w.shape[0] < 3 or c2w.shape[1] != 4:
+        raise RuntimeError("generate_rays: c2w must be (3,4) or (4,4)")
+    c2w = _f32c(c2w)
+    dev = c2w.device
+    if pix_idx is None:
+        n = H * W
+    else:
+        if pix_idx.dtype != torch.int64:
+            pix_idx = pix_idx.long()
+        pix_idx = pix_idx.contiguous().reshape(-1)
+        n = pix_idx.numel()
+    if image is not None:
+        if image.numel() != H * W * 3:
+            raise RuntimeError("generate_rays: image must hold H*W*3 values")
+        image = _f32c(image)
+    rays_o = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    rays_d = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    target = torch.empty((n, 3), device=dev, dtype=torch.float32) if image is not None else None
+    if n == 0:
+        return (rays_o, rays_d) if image is None else (rays_o, rays_d, target)
+    with torch.cuda.device(dev):
+        _lib.call("nfs_rays_generate", int(H), int(W), float(focal), ptr(c2w), 4, ptr(pix_idx), n, ptr(image),
+                  ptr(rays_o), ptr(rays_d), ptr(target), _stream())
+    return (rays_o, rays_d) if image is None else (rays_o, rays_d, target)
+
+
 # --------------------------------------------------------------------------- K2
 def posenc(x, freqs, include_input=True):
     """x (...,D) -> (..., D*(2L+include_input)); freqs: L fp32 values (any device)."""

@@ -14,19 +14,27 @@ from . import ops
 
 
 def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_importance=0, perturb=True,
-                white_bkgd=False, t_rand=None, u=None):
+                white_bkgd=False, t_rand=None, u=None, target=None):
     """model: models.nerf_model.NeRFMLP (or any module with forward_points(points, freq_bands)
     -> (...,4) [rgb|sigma]).  rays (N,3).  Returns a dict with rgb/depth/weights/z of the last
     pass ('rgb', ...) and of the coarse pass ('rgb_coarse', ...) when n_importance > 0.
     t_rand (N,n_coarse) / u (N,n_importance) override the draws (parity tests); otherwise they come
-    from the global CUDA generator in the order the reference draws them."""
+    from the global CUDA generator in the order the reference draws them.
+    target (N,3): the rgb MSE of every pass (train.py:36-44) is evaluated in the compositing kernel's epilogue
+    (ops.composite_loss); out['loss'] = sum over the passes is then the only differentiable entry and the
+    renderings are detached."""
     N = rays_o.shape[0]
     dev = rays_o.device
     if perturb and t_rand is None:
         t_rand = torch.rand(N, n_coarse, device=dev)
     pts, z = ops.sample_stratified(rays_o, rays_d, near, far, n_coarse, t_rand=t_rand if perturb else None)
     raw = model.forward_points(pts.reshape(-1, 3), freq_bands).reshape(N, n_coarse, 4)
-    rgb, depth, weights = ops.composite_packed(raw, z, rays_d, white_bkgd=white_bkgd, want_aux=True)
+    loss = None
+    if target is not None:
+        c = ops.composite_loss(raw, None, z, rays_d, target, None, 1.0, 0.0, white_bkgd, want_weights=n_importance > 0)
+        rgb, depth, weights, loss = c["rgb_map"], c["depth_map"], c.get("weights"), c["total"]
+    else:
+        rgb, depth, weights = ops.composite_packed(raw, z, rays_d, white_bkgd=white_bkgd, want_aux=True)
     out = {"rgb": rgb, "depth": depth, "weights": weights, "z_vals": z}
     if n_importance > 0:
         out.update(rgb_coarse=rgb, depth_coarse=depth, weights_coarse=weights, z_coarse=z)
@@ -37,21 +45,32 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
             pts_f, z_f = ops.sample_hierarchical(rays_o, rays_d, z, w_in, n_importance, u=u)
         S = n_coarse + n_importance
         raw_f = model.forward_points(pts_f.reshape(-1, 3), freq_bands).reshape(N, S, 4)
-        rgb_f, depth_f, w_f = ops.composite_packed(raw_f, z_f, rays_d, white_bkgd=white_bkgd, want_aux=True)
+        if target is not None:
+            c = ops.composite_loss(raw_f, None, z_f, rays_d, target, None, 1.0, 0.0, white_bkgd)
+            rgb_f, depth_f, w_f, loss = c["rgb_map"], c["depth_map"], None, loss + c["total"]
+        else:
+            rgb_f, depth_f, w_f = ops.composite_packed(raw_f, z_f, rays_d, white_bkgd=white_bkgd, want_aux=True)
         out.update(rgb=rgb_f, depth=depth_f, weights=w_f, z_vals=z_f)
+    if loss is not None:
+        out["loss"] = loss
     return out
 
 
 def train_step(model, optimizer, freq_bands, rays_o, rays_d, target, near, far, n_coarse=64, n_importance=128,
-               perturb=True, loss_scale=1.0, allreduce=None):
+               perturb=True, loss_scale=1.0, allreduce=None, fused_loss=True):
     """One optimisation step of BASELINE config 3: render (coarse + fine), MSE on both passes
-    (train.py:36-44 uses rgb MSE only), backward through the compositing and MLP kernels,
-    optional gradient all-reduce, fused Adam.  Returns the (detached) loss tensor - no host sync."""
+    (train.py:36-44 uses rgb MSE only; evaluated in the compositing epilogue unless fused_loss=False),
+    backward through the compositing and MLP kernels, optional gradient all-reduce, fused Adam.
+    Returns the (detached) loss tensor - no host sync."""
     optimizer.zero_grad()
-    out = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb)
-    loss = torch.mean((out["rgb"] - target) ** 2)
-    if n_importance > 0:
-        loss = loss + torch.mean((out["rgb_coarse"] - target) ** 2)
+    if fused_loss:
+        loss = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb,
+                           target=target)["loss"]
+    else:
+        out = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb)
+        loss = torch.mean((out["rgb"] - target) ** 2)
+        if n_importance > 0:
+            loss = loss + torch.mean((out["rgb_coarse"] - target) ** 2)
     (loss * loss_scale if loss_scale != 1.0 else loss).backward()
     if hasattr(optimizer, "gather_grads"):
         g = optimizer.gather_grads()
@@ -184,11 +203,8 @@ class GraphedTrainStep(GraphedStep):
 
     def _loss(self):
         near, far, n_coarse, n_importance, perturb = self.cfg
-        out = render_rays(self.model, self.bands, self.rays_o, self.rays_d, near, far, n_coarse, n_importance, perturb)
-        loss = torch.mean((out["rgb"] - self.target) ** 2)
-        if n_importance > 0:
-            loss = loss + torch.mean((out["rgb_coarse"] - self.target) ** 2)
-        return loss
+        return render_rays(self.model, self.bands, self.rays_o, self.rays_d, near, far, n_coarse, n_importance, perturb,
+                           target=self.target)["loss"]
 
     def __call__(self, rays_o, rays_d, target):
         self.rays_o.copy_(rays_o, non_blocking=True)

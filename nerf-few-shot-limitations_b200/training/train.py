@@ -214,17 +214,24 @@ class NeRFDINOTrainer:
         total = torch.zeros((), device=self.device)
         n_batches = 0
         for view_idx in range(len(self.images)):
-            rays_o, rays_d, target = self.get_rays_for_view(view_idx, "train")
+            # train.py:262-278 builds the full (H,W,3) ray images of the view and gathers a randperm slice of them
+            # per batch; nfs_rays_generate evaluates the same rays for the batch's pixels only and gathers the
+            # target colours in the same launch (bit-identical values, no (H*W,3) round trips).
+            target = self.images[view_idx]
+            if target.shape[-1] == 4:
+                target = target[..., :3] * target[..., 3:4] + (1.0 - target[..., 3:4])
+            focal_t = self.focal
             if h_t != self.H or w_t != self.W:
-                rays_o, rays_d = get_rays(h_t, w_t, self.focal * (h_t / self.H), self.poses[view_idx])
+                focal_t = self.focal * (h_t / self.H)
                 target = F.interpolate(target.permute(2, 0, 1).unsqueeze(0), size=(h_t, w_t), mode="bilinear",
                                        align_corners=False).squeeze(0).permute(1, 2, 0)
-            perm = torch.randperm(rays_o.shape[0] * rays_o.shape[1], device=self.device)
-            ro, rd, tg = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), target.reshape(-1, 3)
+            target = target.contiguous()
+            perm = torch.randperm(h_t * w_t, device=self.device)
             for i in range(0, perm.shape[0], batch):
                 b = perm[i:i + batch]
-                pred = self.render_rays(ro[b], rd[b], view_idx, n_samples)
-                loss = sum(self.criterion(pred, {"rgb": tg[b]}).values())
+                ro_b, rd_b, tg_b = _ops.generate_rays(h_t, w_t, focal_t, self.poses[view_idx], pix_idx=b, image=target)
+                pred = self.render_rays(ro_b, rd_b, view_idx, n_samples)
+                loss = sum(self.criterion(pred, {"rgb": tg_b}).values())
                 self.optimizer.zero_grad()
                 loss.backward()
                 self.optimizer.step()

@@ -10,16 +10,12 @@ from nfs_b200 import ops as _ops
 
 
 def get_rays(H, W, focal, pose):
-    """(H, W, 3) ray origins / directions for a (4,4) camera-to-world pose.  The reference
-    builds the pixel grid on the CPU (ray_utils.py:18-22), which breaks on any other
-    device; here the grid lives on pose.device.  Same arithmetic."""
-    device = pose.device
-    i, j = torch.meshgrid(torch.arange(W, dtype=torch.float32, device=device),
-                          torch.arange(H, dtype=torch.float32, device=device), indexing='xy')
-    dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], dim=-1)
-    rays_d = torch.sum(dirs[..., None, :] * pose[:3, :3], dim=-1)
-    rays_o = pose[:3, 3].expand(rays_d.shape)
-    return rays_o, rays_d
+    """(H, W, 3) ray origins / directions for a (4,4) camera-to-world pose (ray_utils.py:4-37) - one kernel
+    (nfs_rays_generate), bit-exact with the reference's CPU arithmetic.  The reference builds the pixel grid
+    on the CPU (ray_utils.py:18-22), which breaks for a pose on any other device; here
+    the rays are produced on pose.device, which must be a CUDA device."""
+    rays_o, rays_d = _ops.generate_rays(H, W, focal, pose)
+    return rays_o.reshape(H, W, 3), rays_d.reshape(H, W, 3)
 
 
 def sample_points_along_rays(rays_o, rays_d, near, far, N_samples, perturb=True, lindisp=False):

@@ -316,6 +316,29 @@ def pixel_rays(H, W, focal, c2w):
     return c2w[:3, 3].expand(rays_d.shape), rays_d
 
 
+def ray_batch(H, W, focal, c2w, idx, image=None):
+    """The batch assembly of NeRFDINOTrainer.train_step, src/training/train.py:272-278: rays (and target colours)
+    of the pixels idx of one view, by gathering from the view's full ray images."""
+    ro, rd = pixel_rays(H, W, focal, c2w)
+    out = (ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx])                                # :275-276
+    return out if image is None else out + (image.reshape(-1, 3)[idx],)                  # :277
+
+
+def pixel_rays_scalar(H, W, focal, c2w):
+    """pixel_rays with the ATen arithmetic spelled out in numpy fp32 (what the CUDA kernel implements): true
+    division by the focal length, each product rounded, the three terms added left to right.  Equal to pixel_rays
+    bit for bit (tests/test_oracle_golden.py::test_rays)."""
+    import numpy as np
+    f32 = np.float32
+    R = c2w[:3, :3].numpy().astype(f32)
+    i, j = np.meshgrid(np.arange(W, dtype=f32), np.arange(H, dtype=f32), indexing="xy")
+    dx = (i - f32(W * 0.5)) / f32(focal)
+    dy = -((j - f32(H * 0.5)) / f32(focal))
+    dz = -np.ones_like(i)
+    rd = np.stack([(dx * R[k, 0] + dy * R[k, 1]) + dz * R[k, 2] for k in range(3)], -1)
+    return c2w[:3, 3].expand(H, W, 3), torch.from_numpy(rd)
+
+
 def lego_rays(n_rays, H=800, W=800, seed=0):
     """n_rays rays drawn from one synthetic Blender-lego-shaped view (camera_angle_x =
     0.6911112, r = 4.0311, phi = -30 deg) - the generator of SURVEY.md section 8d."""

@@ -239,7 +239,61 @@ def loss_cases():
                       rgb_only={k: v.clone() for k, v in rgb_only.items()}))
 
 
+def ray_cases():
+    """get_rays of both modules (ray_sampler.py:4-30, ray_utils.py:4-37) and the batch gather of
+    train.py:272-278 (rays / target colours of a randperm slice of the view's pixels)."""
+    gen = torch.Generator().manual_seed(808)
+    cases = []
+    for (H, W, focal, n_batch) in [(100, 100, 138.88887889922103, 1024), (37, 53, 77.7, 200), (1, 1, 3.0, 1),
+                                   (64, 48, 55.5 * (64 / 100), 512), (800, 800, 1111.1110311937682, 4096), (200, 200, 277.77775779844205, 4096)]:
+        c2w = torch.eye(4)
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen))
+        c2w[:3, :3] = q
+        c2w[:3, 3] = torch.randn(3, generator=gen) * 3
+        ro, rd = get_rays(H, W, focal, c2w)
+        ro2, rd2 = ray_utils.get_rays(H, W, focal, c2w)
+        assert torch.equal(ro, ro2) and torch.equal(rd, rd2)
+        image = torch.rand(H, W, 3, generator=gen)
+        idx = torch.randperm(H * W, generator=gen)[:n_batch].clone()
+        full = H * W <= 4096                              # whole ray images only for the small views (fixture size)
+        cases.append(dict(H=H, W=W, focal=focal, c2w=c2w, rays_o=ro.contiguous() if full else None,
+                          rays_d=rd.contiguous() if full else None, rays_d_sum=rd.double().sum(), image=image if full else None,
+                          idx=idx, batch_o=ro.reshape(-1, 3)[idx].clone(), batch_d=rd.reshape(-1, 3)[idx].clone(),
+                          batch_target=image.view(-1, 3)[idx].clone()))
+    c34 = cases[1]["c2w"][:3].clone()                     # (3,4) pose form (ray_sampler.py docstring)
+    ro, rd = get_rays(37, 53, 77.7, c34)
+    assert torch.equal(rd, cases[1]["rays_d"])
+    save("rays", cases)
+
+
+def render_loss_cases():
+    """VolumeRenderer.forward followed by NeRFLoss (nerf_mlp.py:165-258) on rgb [+ depth] targets, with the
+    autograd gradients back to the per-sample inputs: what nfs_composite_loss_fwd + nfs_composite_bwd fuse."""
+    gen = torch.Generator().manual_seed(909)
+    cases = []
+    for (n, s, scale, white, with_depth, wr, wd) in [(40, 64, 10.0, False, True, 1.0, 0.1), (33, 192, 3.0, True, False, 1.0, 0.1),
+                                                     (100, 64, 1.0, False, True, 2.0, 0.5), (5, 37, 30.0, False, False, 0.7, 0.0)]:
+        _, rd = rays(n, gen)
+        rgb = torch.rand(n, s, 3, generator=gen).requires_grad_()
+        den = (torch.randn(n, s, 1, generator=gen) * scale).requires_grad_()
+        z = torch.sort(2.0 + 4.0 * torch.rand(n, s, generator=gen), dim=-1).values
+        tgt = dict(rgb=torch.rand(n, 3, generator=gen))
+        if with_depth:
+            tgt["depth"] = 2.0 + 4.0 * torch.rand(n, generator=gen)
+        o_rgb, o_depth, o_w = VolumeRenderer().eval()(rgb, den, z, rd, white_bkgd=white)
+        losses = NeRFLoss(wr, wd, 0.01)({"rgb": o_rgb, "depth": o_depth}, tgt)        # no 'weights' key: no reg term
+        d_rgb, d_den = torch.autograd.grad(losses["total"], [rgb, den])
+        cases.append(dict(rgb=rgb.detach(), density=den.detach(), z=z, rays_d=rd, white_bkgd=white, target=tgt,
+                          rgb_weight=wr, depth_weight=wd, losses={k: v.detach().clone() for k, v in losses.items()},
+                          out_rgb=o_rgb.detach(), out_depth=o_depth.detach(), out_w=o_w.detach(), d_rgb=d_rgb, d_density=d_den))
+    save("render_loss", cases)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                                 # regenerate selected fixtures only
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     render_cases()
     packed_cases()
     posenc_cases()
@@ -248,3 +302,5 @@ if __name__ == "__main__":
     mlp_cases()
     loss_cases()
     gather_cases()
+    ray_cases()
+    render_loss_cases()
