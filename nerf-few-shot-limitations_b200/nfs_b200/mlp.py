@@ -258,15 +258,20 @@ class G1Plan:
         self.cb_row0 = arr_b(*row0_t)
         self.cb_mask = arr_b(*[nh - 1 - j for j in range(nh)])      # h_{nh-j} = forward save[nh-1-j]
 
-    def run_forward_fused(self, x16, keep):
+    def run_forward_fused(self, x16, keep, slot=None):
         """nfs_mlp_chain: all layers in one launch; hidden activations (for wgrad) and their ReLU sign bits
-        (for the dgrad chain) are written to HBM only when the backward pass will need them."""
+        (for the dgrad chain) are written to HBM only when the backward pass will need them.
+        slot = (StepSession, first row): they go into the session's arenas at that row instead of fresh tensors."""
         P = x16.shape[0]
         dev = x16.device
         n_hidden = len(self.packed)
         out = torch.empty((P, 4), device=dev, dtype=torch.float32)
         save, bits, rows = None, None, 0
-        if keep:
+        if slot is not None:
+            sess, r0 = slot
+            rows = sess.rows_cap                          # per-layer stride of the arenas
+            save, bits = sess.save[:, r0:], sess.bits[:, r0:]       # views: data_ptr = row r0 of layer 0
+        elif keep:
             rows = _ceil_to(P, 128)
             save = torch.empty((n_hidden, rows, self.h_pad), device=dev, dtype=torch.bfloat16)
             bits = torch.empty((n_hidden, rows, 8), device=dev, dtype=torch.int32)
@@ -275,6 +280,8 @@ class G1Plan:
                 _lib.call("nfs_mlp_chain", ptr(x16), P, n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0,
                           ptr(self.w_stack), self.w_rows, ptr(self.b_stack), None, 0, None, ptr(save), ptr(bits), rows,
                           ptr(out), 4, _stream())
+        if slot is not None:
+            return out, [x16], None
         acts = [x16] + ([save[i, :P] for i in range(n_hidden)] if keep else [])
         return out, acts, (save, bits) if keep else None
 
@@ -376,9 +383,137 @@ class G1Plan:
         return views
 
 
+class StepSession:
+    """One optimisation step's worth of MLP calls sharing arenas, so that the weight gradients of ALL calls of the
+    step (the coarse and the fine pass of BASELINE config 3) are computed by ONE nfs_wgrad_bf16 launch per layer
+    over the concatenated points, accumulated straight into the optimizer's flat gradient buffer:
+
+      begin(rows)  - zero the flat gradient, rewind the arenas (allocated once: static addresses, graph-safe)
+      forward      - each NeRFMLP call takes the next 128-row-aligned range: encoded operand, saved activations,
+                     ReLU sign bits land in the arenas (run_forward_fused(slot=...))
+      backward     - each call runs its head gradient + dgrad chain into the arenas and returns NO parameter
+                     gradients (autograd then has nothing to accumulate or copy)
+      flush()      - 1 + n_layers wgrad launches over all rows, alternating between two streams.
+
+    Against per-call wgrads this halves the launches (each pays ~15 us of ramp-up and 148 x 256 KB of fp32
+    red.add drain), removes the per-parameter autograd accumulation (19 adds) and the gradient flattening
+    (~40 copies).  Rows between a call's P and its 128-row boundary hold zero dY in every layer (the chain reads
+    rows >= P as zeros through its tensor map; the head's dY rows are zeroed here), so they add nothing."""
+
+    def __init__(self, plan, optimizer):
+        self.plan, self.opt = plan, optimizer
+        where = {id(p): i for i, p in enumerate(optimizer.params)}
+        offs = [0]
+        for n in optimizer.sizes:
+            offs.append(offs[-1] + n)
+        self.views = []
+        for p in plan.params():
+            if id(p) not in where:
+                raise RuntimeError("StepSession: every parameter of the model must belong to the optimizer")
+            i = where[id(p)]
+            self.views.append(optimizer.grad[offs[i]:offs[i + 1]].view(p.shape))
+        self.rows_cap = 0
+        self.cursor = 0
+
+    @staticmethod
+    def supported(plan, optimizer):
+        return (getattr(plan, "fusable", False) and len(plan.packed) >= 2 and hasattr(optimizer, "grad")
+                and os.environ.get("NFS_MLP_FUSED", "1") != "0" and os.environ.get("NFS_MLP_FUSED_BWD", "1") != "0"
+                and os.environ.get("NFS_MLP_SESSION", "1") != "0"
+                and all(any(p is q for q in optimizer.params) for p in plan.params()))
+
+    def begin(self, rows):
+        plan = self.plan
+        rows = _ceil_to(rows, 128) + 128 * 8              # room for the 128-row alignment of up to 8 calls
+        dev = self.opt.grad.device
+        if rows > self.rows_cap:
+            n_hidden = len(plan.packed)
+            self.rows_cap = rows
+            self.x16 = torch.zeros((rows, plan.k0), device=dev, dtype=torch.bfloat16)
+            self.save = torch.zeros((n_hidden, rows, plan.h_pad), device=dev, dtype=torch.bfloat16)
+            self.bits = torch.zeros((n_hidden, rows, 8), device=dev, dtype=torch.int32)
+            self.dy = torch.zeros((rows, 64), device=dev, dtype=torch.bfloat16)
+            self.dys = torch.zeros((n_hidden, rows, plan.h_pad), device=dev, dtype=torch.bfloat16)
+            self.head_w = torch.zeros((64, plan.h_pad), device=dev, dtype=torch.float32)
+            self.head_b = torch.zeros(64, device=dev, dtype=torch.float32)
+        self.cursor = 0
+        self.pending = 0
+        self.opt.grad.zero_()
+        self.head_w.zero_()
+        self.head_b.zero_()
+        plan._session = self
+        return self
+
+    def abort(self):
+        """Leave the session without computing gradients (the step raised)."""
+        self.plan._session = None
+        self.plan._slot = None
+
+    def take(self, P):
+        r0 = self.cursor
+        pad = _ceil_to(P, 128)
+        if r0 + pad > self.rows_cap:
+            raise RuntimeError("StepSession: the step evaluates more points than begin() was told")
+        self.cursor += pad
+        self.pending += 1
+        return r0
+
+    def backward_call(self, out, g_out, r0):
+        """Head gradient + dgrad chain of one call, into the arenas."""
+        plan = self.plan
+        P = out.shape[0]
+        pad = _ceil_to(P, 128)
+        if pad != P:
+            self.dy[r0 + P:r0 + pad].zero_()
+        dy = act_grad(out, g_out, 2, 64, dst=self.dy[r0:r0 + P])
+        n_hidden = len(plan.packed)
+        with torch.cuda.device(dy.device):
+            _lib.call("nfs_mlp_chain", ptr(dy), P, n_hidden, plan.cb_k, plan.cb_n, plan.cb_act, plan.cb_row0,
+                      ptr(plan.wt_stack), plan.wt_rows, None, ptr(self.bits[:, r0:]), self.rows_cap, plan.cb_mask,
+                      ptr(self.dys[:, r0:]), None, self.rows_cap, None, 0, _stream())
+        self.pending -= 1
+
+    def flush(self):
+        """The weight / bias gradients of every call since begin(), into the optimizer's flat gradient."""
+        plan, v = self.plan, self.views
+        plan._session = None
+        if self.pending != 0:
+            raise RuntimeError("StepSession: %d MLP call(s) of this step never received a backward pass" % self.pending)
+        T = self.cursor
+        if T == 0:
+            return
+        n_layers, hd = len(plan.packed), plan.hidden
+        dev = self.opt.grad.device
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.wgrad_bf16(self.save[n_layers - 1, :T], self.dy[:T], self.head_w, 1, plan.h_pad, colsum=self.head_b,
+                           colsum_of_v=True)
+            v[2 * n_layers + 0].add_(self.head_w[3:4, :hd])      # sigma_out.weight (head rows 0..2 rgb_out, 3 sigma_out)
+            v[2 * n_layers + 1].add_(self.head_b[3:4])
+            v[2 * n_layers + 2].add_(self.head_w[0:3, :hd])
+            v[2 * n_layers + 3].add_(self.head_b[0:3])
+        for n, i in enumerate(range(n_layers - 1, 0, -1)):
+            with torch.cuda.stream(side if n & 1 else main):
+                ops.wgrad_bf16(self.save[i - 1, :T], self.dys[n_layers - 1 - i, :T], v[2 * i], 1, hd, colsum=v[2 * i + 1],
+                               colsum_of_v=True, m_valid=hd, n_valid=hd)
+        with torch.cuda.stream(side):
+            ops.wgrad_bf16(self.dys[n_layers - 1, :T], self.x16[:T], v[0], plan.in_dim, 1, colsum=v[1],
+                           colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim)
+        main.wait_stream(side)
+
+
 class _G1Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, keep, x16, *params):
+        slot = getattr(plan, "_slot", None)
+        plan._slot = None
+        if slot is not None:
+            out, _, _ = plan.run_forward_fused(x16, True, slot=slot)
+            ctx.plan, ctx.slot, ctx.fused = plan, slot, True
+            ctx.save_for_backward(out)
+            return out
+        ctx.slot = None
         out, acts, save = plan.run_forward(x16, keep)
         ctx.plan = plan
         ctx.fused = save is not None
@@ -391,6 +526,11 @@ class _G1Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
+        if ctx.slot is not None:
+            (out,) = ctx.saved_tensors
+            sess, r0 = ctx.slot
+            sess.backward_call(out, g_out.contiguous(), r0)
+            return (None, None, None) + (None,) * len(ctx.plan.params())
         if ctx.fused:
             out, x16, sv, bits = ctx.saved_tensors
             P = out.shape[0]
@@ -429,7 +569,13 @@ def g1_forward(plan, x=None, points=None, freqs=None):
                 and os.environ.get("NFS_MLP_FUSED", "1") != "0" and os.environ.get("NFS_MLP_FUSED_ENC", "1") != "0"):
             # inference: the encoding is produced inside the chain kernel (no operand tensor in HBM)
             return plan.run_forward_points(ops._f32c(flat), freqs).reshape(*lead, 4)
-        x16 = encode_operand(flat, freqs, plan.k0)
+        sess = getattr(plan, "_session", None)
+        if sess is not None and keep and flat.shape[0] > 0:
+            r0 = sess.take(flat.shape[0])
+            x16 = encode_operand(flat, freqs, plan.k0, out=sess.x16[r0:r0 + flat.shape[0]])
+            plan._slot = (sess, r0)
+        else:
+            x16 = encode_operand(flat, freqs, plan.k0)
     params = plan.params()
     keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     out = _G1Fn.apply(plan, keep, x16, *params)

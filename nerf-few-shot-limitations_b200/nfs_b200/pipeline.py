@@ -63,17 +63,29 @@ def train_step(model, optimizer, freq_bands, rays_o, rays_d, target, near, far, 
     backward through the compositing and MLP kernels, optional gradient all-reduce, fused Adam.
     Returns the (detached) loss tensor - no host sync."""
     optimizer.zero_grad()
-    if fused_loss:
-        loss = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb,
-                           target=target)["loss"]
-    else:
-        out = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb)
-        loss = torch.mean((out["rgb"] - target) ** 2)
-        if n_importance > 0:
-            loss = loss + torch.mean((out["rgb_coarse"] - target) ** 2)
-    (loss * loss_scale if loss_scale != 1.0 else loss).backward()
+    sess = _session_for(model, optimizer)
+    if sess is not None:
+        sess.begin(rays_o.shape[0] * (n_coarse + (n_coarse + n_importance if n_importance > 0 else 0)))
+    try:
+        if fused_loss:
+            loss = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb,
+                               target=target)["loss"]
+        else:
+            out = render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance, perturb)
+            loss = torch.mean((out["rgb"] - target) ** 2)
+            if n_importance > 0:
+                loss = loss + torch.mean((out["rgb_coarse"] - target) ** 2)
+        (loss * loss_scale if loss_scale != 1.0 else loss).backward()
+    except BaseException:
+        if sess is not None:
+            sess.abort()
+        raise
     if hasattr(optimizer, "gather_grads"):
-        g = optimizer.gather_grads()
+        if sess is not None:
+            sess.flush()                     # all weight gradients of the step, straight into optimizer.grad
+            g = optimizer.grad
+        else:
+            g = optimizer.gather_grads()
         scale = 1.0
         if allreduce is not None:
             allreduce(g)
@@ -81,6 +93,26 @@ def train_step(model, optimizer, freq_bands, rays_o, rays_d, target, near, far, 
     else:
         optimizer.step()
     return loss.detach()
+
+
+def _session_for(model, optimizer):
+    """The model's mlp.StepSession (merged weight-gradient launches writing into the optimizer's flat gradient)
+    when model is the plain NeRFMLP on the fused chain and optimizer is the FusedAdam that owns all of its
+    parameters; else None (autograd accumulates per-call gradients as usual)."""
+    from . import mlp
+    get = getattr(model, "_get_plan", None)
+    if get is None or not hasattr(optimizer, "gather_grads"):
+        return None
+    plan = get()
+    if not isinstance(plan, mlp.G1Plan):
+        return None
+    plan.refresh()
+    if not mlp.StepSession.supported(plan, optimizer):
+        return None
+    sess = getattr(plan, "_step_session", None)
+    if sess is None or sess.opt is not optimizer:
+        sess = plan._step_session = mlp.StepSession(plan, optimizer)
+    return sess
 
 
 @torch.no_grad()
@@ -200,6 +232,22 @@ class GraphedTrainStep(GraphedStep):
         self.rays_d[:, 2] = -1.0
         self.target = torch.zeros(n_rays, 3, device=dev)
         super().__init__(optimizer, self._loss, loss_scale=loss_scale, allreduce=allreduce, warmup=warmup)
+
+    def _forward_backward(self):
+        sess = _session_for(self.model, self.opt)
+        if sess is None:
+            return super()._forward_backward()
+        near, far, n_coarse, n_importance, perturb = self.cfg
+        self.opt.zero_grad()
+        sess.begin(self.rays_o.shape[0] * (n_coarse + (n_coarse + n_importance if n_importance > 0 else 0)))
+        try:
+            loss = self.closure()
+            (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        except BaseException:
+            sess.abort()
+            raise
+        sess.flush()
+        return loss.detach()
 
     def _loss(self):
         near, far, n_coarse, n_importance, perturb = self.cfg
