@@ -257,6 +257,17 @@ int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_octaves, in
                          const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
                          const void *bias_terms_bf16, float *out_f32, int32_t out_cols, void *stream);
 
+/* nfs_mlp_chain_points_train: nfs_mlp_chain_points for the forward of a TRAINING step: the chain kernel encodes the
+ *   points itself, stores the encoded bf16 operand into x_bf16_out [n_points rounded up to 128, 64] (the first
+ *   layer's weight gradient reads it), and saves activations / ReLU sign bits exactly like nfs_mlp_chain
+ *   (save_bf16, relu_bits_out, save_rows_per_layer).  Rows between n_points and the 128-row boundary receive the
+ *   encoding of the origin. */
+int nfs_mlp_chain_points_train(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
+                               int32_t n_layers, const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts,
+                               const int32_t *row0, const void *w_stack_bf16, int32_t w_rows,
+                               const void *bias_terms_bf16, void *x_bf16_out, void *save_bf16, void *relu_bits_out,
+                               int64_t save_rows_per_layer, float *out_f32, int32_t out_cols, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * K2 fused with the operand cast of the first dense layer
  *   (positional_encoding.py:27-33 / nerf_mlp.py:24-33, the torch.cat with DINO features of

@@ -53,6 +53,7 @@ struct FusedArgs {
   int n_layers;
   int K[kFmMaxLayers], N[kFmMaxLayers], act[kFmMaxLayers], row0[kFmMaxLayers];
   int has_bias;                        // the biases arrive as a tensor-core operand (tmap_b), see below
+  int x_save;                          // in-kernel encoding of a training forward: tmap_x stores the encoded operand
   float *out;                          // [P, out_cols] fp32
   int out_cols;
   int save;
@@ -416,7 +417,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t in_bar[2] = {map_to_cta(in_ready, 0), map_to_cta(in_ready + 1, 0)};
     uint32_t iter = 0;
     for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
-      if (!kMasked && !kTrain && a.points != nullptr && cq < 2) {
+      if (!kMasked && a.points != nullptr && cq < 2) {
         // K2 fused in: the warps with cq == t write the positional encoding of tile t (thread = point) straight
         // into slab 0 of act[t] - [x | sin(x f_0) | cos(x f_0) | sin(x f_1) | ...], one accurate sincosf per
         // coordinate and the double-angle recurrence for the higher octaves (identical arithmetic to
@@ -459,6 +460,16 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
+        if (kTrain && a.x_save) {
+          // training: the first layer's weight gradient needs this operand - store the warp's 32 rows (4 KB) and
+          // wait until the TMA has read them (another warp overwrites them in layer 0's epilogue)
+          if (lane == 0) {
+            tma_store_2d(&tmap_x, smem + t * kActBytes + q * 32 * 128, 0, (int)((4 * quad + 2 * rank + t) * 128 + q * 32));
+            bulk_commit();
+            bulk_wait_read0();
+          }
+          __syncwarp();
+        }
         if (lane == 0) mbar_arrive_cluster(in_bar[t]);
       }
       for (int l = 0; l < L; ++l, ++gl) {
@@ -608,6 +619,8 @@ extern "C" void nfs_set_debug_trace(void *buf) { g_fm_trace = (unsigned long lon
 
 // Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
 // default only in their row count (64 resp. 32).
+// points != NULL: in-kernel encoding; x_bf16 is then NULL (inference) or the [rows128, 64] bf16 buffer that RECEIVES the
+// encoded operand (training forward).
 static int launch_chain(const char *fn, const void *x_bf16, const float *points, float freq0, int n_octaves,
                         int64_t n_points, int32_t n_layers, const int32_t *k_dims,
                         const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
@@ -659,6 +672,12 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   if (points != nullptr) {
     if (a.K[0] != 64 || n_octaves < 1 || n_octaves > 10)
       return fail_arg(fn, NFS_E_UNSUPPORTED, "in-kernel encoding needs a 64-wide first layer and 1..10 octaves");
+    if (x_bf16 != nullptr) {
+      if (!a.save) return fail_arg(fn, NFS_E_BADARG, "the encoded operand is only stored by a training forward (save_bf16)");
+      a.x_save = 1;
+      rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)rows128, 64, 64, 32, fn);
+      if (rc) return rc;
+    }
   } else {
     rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)n_points, (uint64_t)a.K[0], (uint64_t)a.K[0], 128, fn);
     if (rc) return rc;
@@ -718,4 +737,17 @@ extern "C" int nfs_mlp_chain_points(const float *points, float freq0, int32_t n_
   if (!points || !out_f32) return fail_arg("nfs_mlp_chain_points", NFS_E_BADARG, "null pointer");
   return launch_chain("nfs_mlp_chain_points", nullptr, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0,
                       w_stack_bf16, w_rows, bias_terms_bf16, nullptr, 0, nullptr, nullptr, nullptr, 0, out_f32, out_cols, stream);
+}
+
+extern "C" int nfs_mlp_chain_points_train(const float *points, float freq0, int32_t n_octaves, int64_t n_points,
+                                          int32_t n_layers, const int32_t *k_dims, const int32_t *n_dims,
+                                          const int32_t *acts, const int32_t *row0, const void *w_stack_bf16,
+                                          int32_t w_rows, const void *bias_terms_bf16, void *x_bf16_out, void *save_bf16,
+                                          void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                                          int32_t out_cols, void *stream) {
+  const char *fn = "nfs_mlp_chain_points_train";
+  if (!points || !x_bf16_out || !save_bf16) return fail_arg(fn, NFS_E_BADARG, "null pointer");
+  return launch_chain(fn, x_bf16_out, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
+                      w_rows, bias_terms_bf16, nullptr, 0, nullptr, save_bf16, relu_bits_out, save_rows_per_layer, out_f32,
+                      out_cols, stream);
 }

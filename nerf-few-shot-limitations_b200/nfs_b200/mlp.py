@@ -258,10 +258,12 @@ class G1Plan:
         self.cb_row0 = arr_b(*row0_t)
         self.cb_mask = arr_b(*[nh - 1 - j for j in range(nh)])      # h_{nh-j} = forward save[nh-1-j]
 
-    def run_forward_fused(self, x16, keep, slot=None):
+    def run_forward_fused(self, x16, keep, slot=None, points=None, freqs=None):
         """nfs_mlp_chain: all layers in one launch; hidden activations (for wgrad) and their ReLU sign bits
         (for the dgrad chain) are written to HBM only when the backward pass will need them.
-        slot = (StepSession, first row): they go into the session's arenas at that row instead of fresh tensors."""
+        slot = (StepSession, first row): they go into the session's arenas at that row instead of fresh tensors.
+        points (+ freqs): training forward with the encoding done in the kernel (nfs_mlp_chain_points_train); x16 is
+        then the [P of ceil128(P) rows, k0] buffer that RECEIVES the encoded operand (layer 0's wgrad reads it)."""
         P = x16.shape[0]
         dev = x16.device
         n_hidden = len(self.packed)
@@ -275,7 +277,12 @@ class G1Plan:
             rows = _ceil_to(P, 128)
             save = torch.empty((n_hidden, rows, self.h_pad), device=dev, dtype=torch.bfloat16)
             bits = torch.empty((n_hidden, rows, 8), device=dev, dtype=torch.int32)
-        if P:
+        if P and points is not None:
+            with torch.cuda.device(dev):
+                _lib.call("nfs_mlp_chain_points_train", ptr(points), float(first_band(freqs)), int(freqs.numel()), P,
+                          n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0, ptr(self.w_stack), self.w_rows,
+                          ptr(self.b_stack), ptr(x16), ptr(save), ptr(bits), rows, ptr(out), 4, _stream())
+        elif P:
             with torch.cuda.device(dev):
                 _lib.call("nfs_mlp_chain", ptr(x16), P, n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0,
                           ptr(self.w_stack), self.w_rows, ptr(self.b_stack), None, 0, None, ptr(save), ptr(bits), rows,
@@ -505,16 +512,21 @@ class StepSession:
 
 class _G1Fn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, keep, x16, *params):
-        slot = getattr(plan, "_slot", None)
-        plan._slot = None
+    def forward(ctx, plan, keep, x16, extra, *params):
+        """extra: None, or dict(slot=(StepSession, row)|None, points=fp32 [P,3]|None, freqs=...) - where the saved
+        tensors go and whether the chain kernel encodes the points itself."""
+        extra = extra or {}
+        slot, points, freqs = extra.get("slot"), extra.get("points"), extra.get("freqs")
         if slot is not None:
-            out, _, _ = plan.run_forward_fused(x16, True, slot=slot)
+            out, _, _ = plan.run_forward_fused(x16, True, slot=slot, points=points, freqs=freqs)
             ctx.plan, ctx.slot, ctx.fused = plan, slot, True
             ctx.save_for_backward(out)
             return out
         ctx.slot = None
-        out, acts, save = plan.run_forward(x16, keep)
+        if points is not None:
+            out, acts, save = plan.run_forward_fused(x16, True, points=points, freqs=freqs)
+        else:
+            out, acts, save = plan.run_forward(x16, keep)
         ctx.plan = plan
         ctx.fused = save is not None
         if keep:
@@ -530,7 +542,7 @@ class _G1Fn(torch.autograd.Function):
             (out,) = ctx.saved_tensors
             sess, r0 = ctx.slot
             sess.backward_call(out, g_out.contiguous(), r0)
-            return (None, None, None) + (None,) * len(ctx.plan.params())
+            return (None, None, None, None) + (None,) * len(ctx.plan.params())
         if ctx.fused:
             out, x16, sv, bits = ctx.saved_tensors
             P = out.shape[0]
@@ -540,7 +552,7 @@ class _G1Fn(torch.autograd.Function):
             out, *acts = ctx.saved_tensors
             save = None
         grads = ctx.plan.run_backward(acts, out, g_out.contiguous(), save_fwd=save)
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 def g1_forward(plan, x=None, points=None, freqs=None):
@@ -554,6 +566,7 @@ def g1_forward(plan, x=None, points=None, freqs=None):
         raise RuntimeError("NeRFMLP: gradients w.r.t. the input coordinates are not supported")
     lead = src.shape[:-1]
     flat = src.reshape(-1, src.shape[-1])
+    extra = None
     if x is not None:
         if flat.shape[-1] != plan.in_dim:
             raise RuntimeError("NeRFMLP: expected %d input features, got %d" % (plan.in_dim, flat.shape[-1]))
@@ -569,14 +582,27 @@ def g1_forward(plan, x=None, points=None, freqs=None):
                 and os.environ.get("NFS_MLP_FUSED", "1") != "0" and os.environ.get("NFS_MLP_FUSED_ENC", "1") != "0"):
             # inference: the encoding is produced inside the chain kernel (no operand tensor in HBM)
             return plan.run_forward_points(ops._f32c(flat), freqs).reshape(*lead, 4)
-        sess = getattr(plan, "_session", None)
-        if sess is not None and keep and flat.shape[0] > 0:
-            r0 = sess.take(flat.shape[0])
-            x16 = encode_operand(flat, freqs, plan.k0, out=sess.x16[r0:r0 + flat.shape[0]])
-            plan._slot = (sess, r0)
+        P = flat.shape[0]
+        fused_ok = (getattr(plan, "fusable", False) and keep and P > 0 and os.environ.get("NFS_MLP_FUSED", "1") != "0")
+        sess = getattr(plan, "_session", None) if fused_ok else None
+        enc_in_kernel = (fused_ok and len(plan.packed) >= 2 and plan.k0 == 64 and flat.shape[-1] == 3
+                         and 1 <= int(freqs.numel()) <= 10 and bands_are_octaves(freqs)
+                         and os.environ.get("NFS_MLP_FUSED_ENC", "1") != "0")
+        if sess is not None:
+            r0 = sess.take(P)
+            extra = {"slot": (sess, r0)}
+            dst = sess.x16[r0:r0 + P]
+        elif enc_in_kernel:
+            dst = torch.empty((_ceil_to(P, 128), plan.k0), device=flat.device, dtype=torch.bfloat16)[:P]
         else:
-            x16 = encode_operand(flat, freqs, plan.k0)
+            dst = None
+        if enc_in_kernel:
+            # training: the chain kernel encodes the points itself and stores the operand for layer 0's wgrad
+            extra = dict(extra or {}, points=ops._f32c(flat), freqs=freqs)
+            x16 = dst
+        else:
+            x16 = encode_operand(flat, freqs, plan.k0, out=dst)
     params = plan.params()
     keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    out = _G1Fn.apply(plan, keep, x16, *params)
+    out = _G1Fn.apply(plan, keep, x16, extra, *params)
     return out.reshape(*lead, 4)

@@ -208,6 +208,39 @@ def test_in_kernel_encoding_matches_two_kernel_route(cuda, P, monkeypatch):
     assert float(((fused.cpu()[:, 3] - out_ref[:, 3]).abs() / (3e-2 * out_ref[:, 3].abs() + 1e-2)).max()) <= 1.0
 
 
+@pytest.mark.parametrize("P", [1, 129, 5000, 70001])
+def test_in_kernel_encoding_training_forward(cuda, P, monkeypatch):
+    """nfs_mlp_chain_points_train (training forward with K2 fused in: the kernel stores the encoded operand for
+    layer 0's weight gradient) against posenc_bf16 -> nfs_mlp_chain: bit-identical outputs, the stored operand
+    equals the encoding kernel's, parameter gradients equal up to the order of wgrad's fp32 atomics."""
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import mlp
+    from oracle import nerf_oracle as O
+    torch.manual_seed(3)
+    mod = NeRFMLP().to(cuda)
+    g = torch.Generator().manual_seed(P)
+    pts = ((torch.rand(P, 3, generator=g) - 0.5) * 8).to(cuda)
+    g_out = torch.randn(P, 4, generator=g).to(cuda)
+    bands = O.frequency_bands(10)
+    res = []
+    for enc in ("1", "0"):
+        monkeypatch.setenv("NFS_MLP_FUSED_ENC", enc)
+        mod.zero_grad()
+        out = mod.forward_points(pts, bands)
+        out.backward(g_out)
+        res.append((out.detach().clone(), [p.grad.clone() for p in mod.parameters()]))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max() + 1e-12) + 1e-7
+    # the operand the kernel stored == the encoding kernel's operand
+    plan = mod._get_plan()
+    monkeypatch.setenv("NFS_MLP_FUSED_ENC", "1")
+    x_two = mlp.encode_operand(pts, bands, plan.k0)
+    x_in = torch.zeros(((P + 127) // 128 * 128, plan.k0), device=cuda, dtype=torch.bfloat16)
+    plan.run_forward_fused(x_in[:P], True, points=pts, freqs=bands)
+    assert torch.equal(x_in[:P], x_two)
+
+
 def test_chain_stress_repeatable(cuda):
     """The CTA-pair chain hands tiles between two SMs through mbarriers and remote arrives: a protocol race would
     show up as run-to-run differences.  Repeat inference, training forward (activations + sign bits) and the dgrad
