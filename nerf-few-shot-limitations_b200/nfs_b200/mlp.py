@@ -371,8 +371,10 @@ class G1Plan:
                     ops.wgrad_bf16(acts[i], dyi, views[2 * i], 1, hd, colsum=views[2 * i + 1], colsum_of_v=True,
                                    m_valid=hd, n_valid=hd)
             with torch.cuda.stream(side):
-                ops.wgrad_bf16(dys[n_layers - 1, :P], acts[0], views[0], self.in_dim, 1, colsum=views[1],
+                w0_t = torch.zeros((self.k0, self.h_pad), device=dev, dtype=torch.float32)     # see StepSession.flush
+                ops.wgrad_bf16(dys[n_layers - 1, :P], acts[0], w0_t, 1, self.h_pad, colsum=views[1],
                                colsum_of_v=False, m_valid=hd, n_valid=self.in_dim)
+                views[0].copy_(w0_t[:self.in_dim, :hd].t())
             main.wait_stream(side)
             return views
         dh, _ = ops.linear_bf16(dy, self.head.w16t, None, act=0, relu_mask_src=h_last)
@@ -443,11 +445,13 @@ class StepSession:
             self.dys = torch.zeros((n_hidden, rows, plan.h_pad), device=dev, dtype=torch.bfloat16)
             self.head_w = torch.zeros((64, plan.h_pad), device=dev, dtype=torch.float32)
             self.head_b = torch.zeros(64, device=dev, dtype=torch.float32)
+            self.w0_t = torch.zeros((plan.k0, plan.h_pad), device=dev, dtype=torch.float32)
         self.cursor = 0
         self.pending = 0
         self.opt.grad.zero_()
         self.head_w.zero_()
         self.head_b.zero_()
+        self.w0_t.zero_()
         plan._session = self
         return self
 
@@ -505,8 +509,16 @@ class StepSession:
                 ops.wgrad_bf16(self.save[i - 1, :T], self.dys[n_layers - 1 - i, :T], v[2 * i], 1, hd, colsum=v[2 * i + 1],
                                colsum_of_v=True, m_valid=hd, n_valid=hd)
         with torch.cuda.stream(side):
-            ops.wgrad_bf16(self.dys[n_layers - 1, :T], self.x16[:T], v[0], plan.in_dim, 1, colsum=v[1],
-                           colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim)
+            # first layer: M must be the 256-wide side (dY), so the kernel's lanes run along the OUTPUT index; into
+            # W's own [out,in] layout that is a stride-in_dim scatter of fp32 atomics - accumulate the transpose
+            # (lanes contiguous) and add it back transposed
+            if os.environ.get("NFS_WGRAD0_DIRECT", "0") != "0":      # developer A/B switch
+                ops.wgrad_bf16(self.dys[n_layers - 1, :T], self.x16[:T], v[0], plan.in_dim, 1, colsum=v[1],
+                               colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim)
+            else:
+                ops.wgrad_bf16(self.dys[n_layers - 1, :T], self.x16[:T], self.w0_t, 1, plan.h_pad, colsum=v[1],
+                               colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim)
+                v[0].add_(self.w0_t[:plan.in_dim, :hd].t())
         main.wait_stream(side)
 
 
