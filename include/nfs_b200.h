@@ -301,6 +301,15 @@ int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float *extra, co
 int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n_pad, int32_t k_pad,
                          int32_t row0, int32_t col0, void *w_bf16, void *wt_bf16, void *stream);
 
+/* nfs_pack_stack: one launch refreshes every bf16 operand of a fused chain (nfs_mlp_chain) from the fp32 master
+ * parameters after an optimizer step.  table: device int64 [n_entries, 8], row =
+ *   [pointer to the fp32 parameter, n_dim, k_dim, w_row0, w_col0, wt_row0 (-1: none), wt_col0, bias_row0]
+ *   k_dim > 0: weight [n_dim,k_dim] -> w_stack[(w_row0+n), w_col0+k] and wt_stack[(wt_row0+k), wt_col0+n]
+ *   k_dim = 0: bias [n_dim] -> bias_terms[bias_row0+n] (see nfs_bias_terms_bf16)
+ * w_stack / wt_stack are [rows, 256] bf16, zero where no parameter lands; max_elems = the largest n_dim*k_dim. */
+int nfs_pack_stack(const void *table, int32_t n_entries, int32_t max_elems, void *w_stack_bf16, void *wt_stack_bf16,
+                   void *bias_terms_bf16, void *stream);
+
 /* fp32 bias[n] -> terms_bf16 [n, 8] bf16, row i = [hi, mid, lo, 0, 0, 0, 0, 0] with hi + mid + lo = bias[i] to
  * ~2^-24 relative: the bias operand of nfs_mlp_chain (nn.Linear's "+ b", nerf_model.py:16-24, added on the
  * tensor core as ones[128x16] . terms^T).  Refreshed with the packed weights after an optimizer step. */

@@ -247,6 +247,49 @@ __global__ void bias_terms_kernel(const float *__restrict__ bias, int n, uint4 *
                       (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
 }
 
+// ------------------------------------------------------------------ whole-chain operand refresh
+// One launch rebuilds every bf16 operand of a fused chain from the fp32 master parameters after an optimizer step:
+// table row e = [src pointer, n_dim, k_dim, w_row0, w_col0, wt_row0 (-1: none), wt_col0, bias_row0] (int64 each);
+//   k_dim > 0: weight W [n_dim,k_dim] -> w_stack[(w_row0+n)*256 + w_col0+k] and, transposed, wt_stack[(wt_row0+k)*256 + wt_col0+n]
+//   k_dim = 0: bias [n_dim]            -> the three-term bf16 rows bias_terms[bias_row0+n] (see bias_terms_kernel)
+__global__ void __launch_bounds__(256)
+pack_stack_kernel(const long long *__restrict__ table, __nv_bfloat16 *__restrict__ w_stack,
+                  __nv_bfloat16 *__restrict__ wt_stack, uint4 *__restrict__ terms) {
+  const long long *e = table + 8 * blockIdx.y;
+  const float *src = reinterpret_cast<const float *>(e[0]);
+  const int N = (int)e[1], K = (int)e[2];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (K == 0) {
+    if (idx >= N || terms == nullptr) return;
+    const float b = __ldg(src + idx);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const float r1 = b - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    terms[e[7] + idx] = make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                                   (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+    return;
+  }
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(src + idx));
+  w_stack[(e[3] + n) * 256 + e[4] + k] = v;
+  if (e[5] >= 0 && wt_stack != nullptr) wt_stack[(e[5] + k) * 256 + e[6] + n] = v;
+}
+
+extern "C" int nfs_pack_stack(const void *table, int32_t n_entries, int32_t max_elems, void *w_stack_bf16,
+                              void *wt_stack_bf16, void *bias_terms_bf16, void *stream) {
+  const char *fn = "nfs_pack_stack";
+  if (n_entries < 0 || max_elems < 0) return fail_arg(fn, NFS_E_BADARG, "negative size");
+  if (n_entries == 0 || max_elems == 0) return 0;
+  if (!table || !w_stack_bf16) return fail_arg(fn, NFS_E_BADARG, "null pointer");
+  if (n_entries > 65535) return fail_arg(fn, NFS_E_TOOLARGE, "too many entries");
+  dim3 grid((unsigned)((max_elems + 255) / 256), (unsigned)n_entries);
+  pack_stack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)table, (__nv_bfloat16 *)w_stack_bf16,
+                                                            (__nv_bfloat16 *)wt_stack_bf16, (uint4 *)bias_terms_bf16);
+  return check_launch(fn);
+}
+
 extern "C" int nfs_bias_terms_bf16(const float *bias, int32_t n, void *terms_bf16, void *stream) {
   const char *fn = "nfs_bias_terms_bf16";
   if (n < 0) return fail_arg(fn, NFS_E_BADARG, "negative size");

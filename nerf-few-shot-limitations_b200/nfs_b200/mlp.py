@@ -207,32 +207,57 @@ class G1Plan:
         return ps
 
     def refresh(self):
-        stale = any(p._key is None for p in self.packed + [self.head])
-        keys = [p._key for p in self.packed + [self.head]]
-        for p in self.packed:
-            p.refresh()
-        self.head.refresh()
-        if keys != [p._key for p in self.packed + [self.head]] or stale or getattr(self, "w_stack", None) is None:
-            self._build_stack()
+        """Bring the bf16 operands up to date with the fp32 parameters.  On the fused path that is ONE launch
+        (nfs_pack_stack writes every layer's W, W^T and bias terms into the stacked operands); the per-layer copies
+        of the layer-by-layer route are refreshed lazily (refresh_layers)."""
+        params = self.params()
+        dev = params[0].device
+        if not params[0].is_cuda:
+            raise RuntimeError("nfs_b200: model parameters must live on a CUDA device (no CPU fallback)")
+        key = (str(dev), _WEIGHT_EPOCH) + tuple((p.data_ptr(), p._version) for p in params)
+        if key == getattr(self, "_key", None):
+            return
+        place = (str(dev),) + tuple((p.data_ptr(), p.dtype, p.is_contiguous()) for p in params)
+        if place != getattr(self, "_place", None):
+            self._build_stack(dev)
+            self._place = place
+        self._layers_stale = True
+        if self.fusable:
+            if self._table is None or os.environ.get("NFS_PACK_STACK", "1") == "0":   # non-contiguous / non-fp32 parameters (or the developer switch): through the layer copies
+                self.refresh_layers()
+                self._copy_layers_into_stack()
+            else:
+                with torch.cuda.device(dev), torch.no_grad():
+                    _lib.call("nfs_pack_stack", ptr(self._table), self._table.shape[0], self._max_elems,
+                              ptr(self.w_stack), ptr(self.wt_stack), ptr(self.b_stack), _stream())
+        else:
+            self.refresh_layers()
+        self._key = key
 
-    def _build_stack(self):
-        """One [rows,256] bf16 tensor holding every layer's padded W (and the biases likewise) for
-        the fused chain kernel."""
+    def refresh_layers(self):
+        """Per-layer operand copies (PackedLinear) used by the layer-by-layer route."""
+        if getattr(self, "_layers_stale", True):
+            for p in self.packed:
+                p.refresh()
+            self.head.refresh()
+            self._layers_stale = False
+
+    def _build_stack(self, dev):
+        """Allocate the stacked operands of the fused chain - one [rows,256] bf16 tensor holding every layer's padded
+        W, one holding the W^T of the dgrad chain, the [rows,8] bias terms - and the table nfs_pack_stack fills
+        them from."""
         layers = self.packed + [self.head]
         self.fusable = self.k0 <= 256 and len(layers) <= 12
         if not self.fusable:
             return
-        dev = self.head.w16.device
         rows = sum(p.n_pad for p in layers)
-        w = torch.zeros(rows, 256, device=dev, dtype=torch.bfloat16)
-        b = torch.zeros(rows, device=dev, dtype=torch.float32)
         r, row0 = 0, []
         for p in layers:
-            w[r:r + p.n_pad, :p.k_pad].copy_(p.w16)
-            b[r:r + p.n_pad].copy_(p.bias)
             row0.append(r)
             r += p.n_pad
-        self.w_stack, self.b_stack, self.w_rows = w, bias_terms(b), rows
+        self.w_stack = torch.zeros(rows, 256, device=dev, dtype=torch.bfloat16)
+        self.b_stack = torch.zeros(rows, 8, device=dev, dtype=torch.bfloat16)
+        self.w_rows = rows
         n = len(layers)
         arr = ctypes.c_int32 * n
         self.c_k = arr(*[p.k_pad for p in layers])
@@ -244,19 +269,42 @@ class G1Plan:
         nh = n - 1
         back = [self.head] + [self.packed[i] for i in range(nh - 1, 0, -1)]
         rows_t = sum(p.k_pad for p in back)
-        wt = torch.zeros(rows_t, 256, device=dev, dtype=torch.bfloat16)
-        r, row0_t = 0, []
+        r, row0_t = 0, {}
         for p in back:
-            wt[r:r + p.k_pad, :p.n_pad].copy_(p.w16t)
-            row0_t.append(r)
+            row0_t[id(p)] = r
             r += p.k_pad
-        self.wt_stack, self.wt_rows = wt, rows_t
+        self.wt_stack, self.wt_rows = torch.zeros(rows_t, 256, device=dev, dtype=torch.bfloat16), rows_t
         arr_b = ctypes.c_int32 * nh
         self.cb_k = arr_b(*[p.n_pad for p in back])
         self.cb_n = arr_b(*[p.k_pad for p in back])
         self.cb_act = arr_b(*([4] * nh))
-        self.cb_row0 = arr_b(*row0_t)
+        self.cb_row0 = arr_b(*[row0_t[id(p)] for p in back])
         self.cb_mask = arr_b(*[nh - 1 - j for j in range(nh)])      # h_{nh-j} = forward save[nh-1-j]
+        # nfs_pack_stack table: one row per parameter tensor
+        self._row0, self._row0_t = row0, row0_t
+        table, ok = [], True
+        for p, r0 in zip(layers, row0):
+            sub = 0
+            for lin in p.linears:
+                for t in (lin.weight, lin.bias):
+                    ok = ok and t.dtype == torch.float32 and t.is_contiguous()
+                table.append([lin.weight.data_ptr(), lin.out_features, lin.in_features, r0 + sub, 0,
+                              row0_t.get(id(p), -1), sub, 0])
+                table.append([lin.bias.data_ptr(), lin.out_features, 0, 0, 0, -1, 0, r0 + sub])
+                sub += lin.out_features
+        self._table = torch.tensor(table, dtype=torch.int64, device=dev) if ok else None
+        self._max_elems = max(row[1] * max(row[2], 1) for row in table)
+
+    def _copy_layers_into_stack(self):
+        layers = self.packed + [self.head]
+        b = torch.zeros(self.w_rows, device=self.w_stack.device, dtype=torch.float32)
+        for p, r in zip(layers, self._row0):
+            self.w_stack[r:r + p.n_pad, :p.k_pad].copy_(p.w16)
+            b[r:r + p.n_pad].copy_(p.bias)
+            if id(p) in self._row0_t:
+                rt = self._row0_t[id(p)]
+                self.wt_stack[rt:rt + p.k_pad, :p.n_pad].copy_(p.w16t)
+        self.b_stack.copy_(bias_terms(b))
 
     def run_forward_fused(self, x16, keep, slot=None, points=None, freqs=None):
         """nfs_mlp_chain: all layers in one launch; hidden activations (for wgrad) and their ReLU sign bits
@@ -323,6 +371,7 @@ class G1Plan:
         (fused path) or None (layer-by-layer path)."""
         if getattr(self, "fusable", False) and os.environ.get("NFS_MLP_FUSED", "1") != "0":
             return self.run_forward_fused(x16, keep)
+        self.refresh_layers()
         acts = [x16]
         h = x16
         for p in self.packed:
@@ -377,6 +426,7 @@ class G1Plan:
                 views[0].copy_(w0_t[:self.in_dim, :hd].t())
             main.wait_stream(side)
             return views
+        self.refresh_layers()
         dh, _ = ops.linear_bf16(dy, self.head.w16t, None, act=0, relu_mask_src=h_last)
         for i in range(n_layers - 1, 0, -1):
             x_in = acts[i]                                   # input of layer i (= output of layer i-1)
