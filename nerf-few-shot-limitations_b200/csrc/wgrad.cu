@@ -142,19 +142,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
     const int q = warp & 3;
     if (a.bulk_drain) {
       // The destination is one contiguous fp32 block dw[n * M + m]: transpose the accumulator through shared
-      // memory (lanes own consecutive m: conflict-free 128-byte rows) in rounds of 128 n-rows and let the TMA
-      // reduce each round into global memory (cp.reduce.async.bulk ... add.f32).  Per-thread fp32 atomics issue at
-      // ~1 warp instruction per 20 cycles per SM: 2048 of them made every launch cost ~22 us whatever its size
-      // (scripts/dev/wgrad_sizes.py); the bulk reduction takes ~3.
-      float *stage = reinterpret_cast<float *>(smem);        // the operand ring is idle: every MMA has completed
+      // memory (lanes own consecutive m: conflict-free 128-byte rows) and let the TMA reduce it into global memory
+      // (cp.reduce.async.bulk ... add.f32).  The per-thread fp32 atomics of the fallback below are 2048 warp
+      // instructions per CTA, ~16k cycles on top of this path for every launch whatever its size
+      // (scripts/dev/wgrad_sizes.py, wgrad_trace.py).
+      // Rounds of 64 n-rows through two buffers: staging round r + 1 overlaps the TMA's read of round r (the
+      // bulk reduction drains shared memory at ~24 B/cycle: 2 650 cycles per 64 KB round, staging takes 1 400).
       const int M = a.M;
+      float *stage0 = reinterpret_cast<float *>(smem);       // the operand ring is idle: every MMA has completed
       asm volatile("bar.sync 1, 128;" ::: "memory");         // every drain warp has finished its column sums (they read the ring)
-      for (int n0 = 0; n0 < a.n_valid; n0 += 128) {
-        const int rows = min(128, a.n_valid - n0), cols = min(128, a.N - n0);
+      int round = 0;
+      for (int n0 = 0; n0 < a.n_valid; n0 += 64, ++round) {
+        float *stage = stage0 + (round & 1) * 64 * M;
+        if (round >= 2) {                                    // the reduction issued two rounds ago has read this buffer
+          if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const int rows = min(64, a.n_valid - n0);
         for (int h = 0; h < (M >> 7); ++h) {
           const int m = h * 128 + q * 32 + lane;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * a.N + n0);
-          for (int c0 = 0; c0 < cols; c0 += 32) {
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
             float v[32];
             tmem_ld32(taddr + c0, v);
 #pragma unroll
@@ -168,9 +177,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                        ::"l"(a.dw + (long long)n0 * M), "r"(smem_u32(stage)), "r"(bytes) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // the stage buffer may be overwritten
       }
       if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (n_slabs > (long long)blockIdx.x) {
@@ -232,7 +239,7 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   if (stages < 2) return fail_arg(fn, NFS_E_TOOLARGE, "operands too wide for the staging ring");
   a.n_stages = stages;
   const size_t ring = (size_t)stages * stage_bytes;
-  const size_t round_bytes = (size_t)(n_dim < 128 ? n_dim : 128) * m_dim * 4;
+  const size_t round_bytes = (size_t)2 * 64 * m_dim * 4;          // two 64-row staging buffers
   a.bulk_drain = ld_m == 1 && ld_n == m_dim && a.m_valid == m_dim && round_bytes <= ring &&
                  (reinterpret_cast<uintptr_t>(dw) & 15u) == 0 && getenv("NFS_WGRAD_ATOMIC_DRAIN") == nullptr;
   int cols = 32;
@@ -249,16 +256,10 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_slabs = (n_points + kSlabP - 1) / kSlabP;
-  // Every CTA ends by reducing its whole [M x N] fp32 partial into global memory (M*N*4 bytes of red.add, ~2 TB/s
-  // over the GPU), whatever number of points it has seen; a CTA streams its operands at ~80 GB/s.  For small
-  // launches the drains of 148 CTAs cost more than the loads: minimise  G * drain + load / G  over the grid size G,
-  //   G* = sqrt(P (M+N) 2 / 80e9 / (M N 4 / 2e12))   (cfg 4, 32 768 points: 57 CTAs, 28 -> 15 us per launch;
-  // cfg 3, >= 262 144 points: all SMs).  scripts/profile_step_g3.py.
-  long long g_opt = (long long)ceil(sqrt((double)n_points * (double)(m_dim + n_dim) * 12.5 / ((double)m_dim * (double)n_dim)));
-  if (g_opt < 8) g_opt = 8;
-  if (const char *force = getenv("NFS_WGRAD_GRID")) g_opt = atoll(force) > 0 ? atoll(force) : g_opt;   // developer A/B switch
+  // Every CTA pays a fixed ~12 us (setup, first slab, ~19k cycles of accumulator drain) whatever its share of the
+  // points, so small launches want ALL SMs to keep the streaming part short (scripts/dev/wgrad_trace.py).
   long long g = n_slabs < sms ? n_slabs : sms;
-  if (g_opt < g) g = g_opt;
+  if (const char *force = getenv("NFS_WGRAD_GRID")) g = atoll(force) > 0 && atoll(force) < g ? atoll(force) : g;   // developer switch
   const unsigned grid = (unsigned)g;
   wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tu, tv, a);
   return check_launch(fn);
