@@ -19,6 +19,7 @@
 // The kernel is HBM-bound: 24*S+28 B/ray forward, 36*S+28 (+4*S with g_weights)
 // backward (DESIGN.md "K1").
 #include "nfs_common.cuh"
+#include <cstdlib>
 
 namespace nfs {
 namespace {
@@ -193,6 +194,42 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// Loss epilogue (block-uniform call): F.mse_loss(rgb, target) (nerf_mlp.py:235, train.py:40) and
+// F.l1_loss(depth, target_depth) (nerf_mlp.py:240) evaluated where the pixel is still in registers; the upstream
+// gradients of the compositing backward leave this kernel instead of a chain of torch kernels.  `leader`: this
+// thread holds a finished ray.  Contains a __syncthreads().
+__device__ __forceinline__ void loss_epilogue(const CompositeArgs &a, long long ray, bool leader, float acc_r, float acc_g,
+                                              float acc_b, float acc_d, long long slot) {
+  float se = 0.f, ae = 0.f;
+  if (leader) {
+    const float d0 = acc_r - __ldg(a.target + ray * 3), d1 = acc_g - __ldg(a.target + ray * 3 + 1),
+                d2 = acc_b - __ldg(a.target + ray * 3 + 2);
+    se = d0 * d0 + d1 * d1 + d2 * d2;
+    a.g_rgb_out[ray * 3] = a.rgb_coef * d0; a.g_rgb_out[ray * 3 + 1] = a.rgb_coef * d1;
+    a.g_rgb_out[ray * 3 + 2] = a.rgb_coef * d2;
+    if (a.target_depth != nullptr) {
+      const float dd = acc_d - __ldg(a.target_depth + ray);
+      ae = fabsf(dd);
+      a.g_depth_out[ray] = dd > 0.f ? a.depth_coef : (dd < 0.f ? -a.depth_coef : 0.f);   // sign(dd), l1_loss backward
+    }
+  }
+  __shared__ float red[2][kBlock / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+    ae += __shfl_xor_sync(0xffffffffu, ae, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = se; red[1][threadIdx.x >> 5] = ae; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) t += (double)red[threadIdx.x][w];
+    if (threadIdx.x == 0 || a.target_depth != nullptr)
+      atomicAdd(a.loss_sums + 2 * (slot % kLossSlots) + threadIdx.x, t);
+  }
+}
+
 // ------------------------------- forward -----------------------------------
 template <int G, bool ALIGNED, bool PACKED>
 __global__ void __launch_bounds__(kBlock) composite_fwd_kernel(const CompositeArgs a) {
@@ -262,39 +299,7 @@ __global__ void __launch_bounds__(kBlock) composite_fwd_kernel(const CompositeAr
     a.out_rgb[ray * 3] = acc_r; a.out_rgb[ray * 3 + 1] = acc_g; a.out_rgb[ray * 3 + 2] = acc_b;
     if (a.out_depth != nullptr) a.out_depth[ray] = acc_d;
   }
-  if (a.target != nullptr) {
-    // Loss epilogue (block-uniform branch): F.mse_loss(rgb, target) (nerf_mlp.py:235, train.py:40) and
-    // F.l1_loss(depth, target_depth) (nerf_mlp.py:240) evaluated where the pixel is still in registers; the
-    // upstream gradients of the compositing backward leave this kernel instead of a chain of torch kernels.
-    float se = 0.f, ae = 0.f;
-    if (ray_ok && gl == 0) {
-      const float d0 = acc_r - __ldg(a.target + ray * 3), d1 = acc_g - __ldg(a.target + ray * 3 + 1),
-                  d2 = acc_b - __ldg(a.target + ray * 3 + 2);
-      se = d0 * d0 + d1 * d1 + d2 * d2;
-      a.g_rgb_out[ray * 3] = a.rgb_coef * d0; a.g_rgb_out[ray * 3 + 1] = a.rgb_coef * d1;
-      a.g_rgb_out[ray * 3 + 2] = a.rgb_coef * d2;
-      if (a.target_depth != nullptr) {
-        const float dd = acc_d - __ldg(a.target_depth + ray);
-        ae = fabsf(dd);
-        a.g_depth_out[ray] = dd > 0.f ? a.depth_coef : (dd < 0.f ? -a.depth_coef : 0.f);   // sign(dd), l1_loss backward
-      }
-    }
-    __shared__ float red[2][kBlock / 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      se += __shfl_xor_sync(0xffffffffu, se, o);
-      ae += __shfl_xor_sync(0xffffffffu, ae, o);
-    }
-    if (lane == 0) { red[0][threadIdx.x >> 5] = se; red[1][threadIdx.x >> 5] = ae; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-      double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < kBlock / 32; ++w) t += (double)red[threadIdx.x][w];
-      if (threadIdx.x == 0 || a.target_depth != nullptr)
-        atomicAdd(a.loss_sums + 2 * (blockIdx.x % kLossSlots) + threadIdx.x, t);
-    }
-  }
+  if (a.target != nullptr) loss_epilogue(a, ray, ray_ok && gl == 0, acc_r, acc_g, acc_b, acc_d, blockIdx.x);
 }
 
 // ------------------------------- backward ----------------------------------
@@ -586,6 +591,145 @@ int launch_bwd_staged(const CompositeArgs &a, cudaStream_t st) {
   return check_launch("nfs_composite_bwd");
 }
 
+// ------------------------------- forward, staged ----------------------------
+// The forward with the same load pipeline as composite_bwd_staged_kernel (persistent blocks, bulk async copies of
+// each tile's three contiguous input blocks into a 2-stage shared-memory ring): identical arithmetic to
+// composite_fwd_kernel (bit-identical results), but ~40 KB of loads per block always in flight instead of one
+// round trip per block.
+template <int G>
+__global__ void __launch_bounds__(kBlock, 4) composite_fwd_staged_kernel(const CompositeArgs a, const long long n_tiles) {
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int kRays = (kBlock / 32) * kGroupsPerWarp;          // rays per tile
+  extern __shared__ __align__(128) unsigned char s_stage[];
+  const int S = a.S;
+  const int stage_floats = kRays * S * 5;                         // rgb 3S | density S | z S per ray
+  float *ring = reinterpret_cast<float *>(s_stage);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBwdStages * stage_floats);
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const int group_in_block = (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBwdStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int stage) {                    // thread 0 only
+    const long long r0 = tile * kRays;
+    const long long nr = (a.n_rays - r0) < kRays ? (a.n_rays - r0) : kRays;
+    const uint32_t row = (uint32_t)(nr * S * 4);
+    float *st = ring + stage * stage_floats;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(full + stage)), "r"(row * 5u) : "memory");
+    bulk_g2s(st, a.rgb + r0 * S * 3, row * 3, full + stage);
+    bulk_g2s(st + kRays * S * 3, a.density + r0 * S, row, full + stage);
+    bulk_g2s(st + kRays * S * 4, a.z + r0 * S, row, full + stage);
+  };
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBwdStages; ++i)
+      if (first + i * step < n_tiles) issue(first + i * step, i);
+
+  uint32_t it = 0;
+  for (long long tile = first; tile < n_tiles; tile += step, ++it) {
+    const int stage = it % kBwdStages;
+    const uint32_t parity = (it / kBwdStages) & 1;
+    const long long ray = tile * kRays + group_in_block;
+    const bool ray_ok = ray < a.n_rays;
+    float dnorm = 0.f;
+    if (ray_ok) {
+      const float dx = __ldg(a.rays_d + ray * 3), dy = __ldg(a.rays_d + ray * 3 + 1), dz = __ldg(a.rays_d + ray * 3 + 2);
+      dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    {                                                               // wait for the tile
+      uint32_t ok = 0, spin = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(full + stage)), "r"(parity) : "memory");
+        if (++spin > (1u << 26)) { printf("nfs_b200: composite_fwd tile wait timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+      }
+    }
+    const float *st = ring + stage * stage_floats;
+    const int s0 = 4 * gl;
+    Lane4 v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v.z[j] = 0.f; v.sg[j] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v.col[j] = 0.f;
+    if (ray_ok && s0 < S) {
+      const int o = group_in_block * S + s0;
+      const float4 c0 = *reinterpret_cast<const float4 *>(st + o * 3);
+      const float4 c1 = *reinterpret_cast<const float4 *>(st + o * 3 + 4);
+      const float4 c2 = *reinterpret_cast<const float4 *>(st + o * 3 + 8);
+      const float4 dd = *reinterpret_cast<const float4 *>(st + kRays * S * 3 + o);
+      const float4 zz = *reinterpret_cast<const float4 *>(st + kRays * S * 4 + o);
+      v.col[0] = c0.x; v.col[1] = c0.y; v.col[2] = c0.z; v.col[3] = c0.w;
+      v.col[4] = c1.x; v.col[5] = c1.y; v.col[6] = c1.z; v.col[7] = c1.w;
+      v.col[8] = c2.x; v.col[9] = c2.y; v.col[10] = c2.z; v.col[11] = c2.w;
+      v.sg[0] = dd.x; v.sg[1] = dd.y; v.sg[2] = dd.z; v.sg[3] = dd.w;
+      v.z[0] = zz.x; v.z[1] = zz.y; v.z[2] = zz.z; v.z[3] = zz.w;
+    }
+    float zn = __shfl_down_sync(kFullMask, v.z[0], 1, G);          // single chunk (S <= 4G)
+    if (gl == G - 1) zn = 0.f;
+    Alpha4 al;
+    alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+    const float p1 = al.q[0], p2 = p1 * al.q[1], p3 = p2 * al.q[2], p4 = p3 * al.q[3];
+    float chunk_all;
+    const float tb = 1.f * group_excl_prod<G>(p4, gl, chunk_all);
+    const float T[4] = {tb, tb * p1, tb * p2, tb * p3};
+    float w[4];
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_w = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = al.alpha[j] * T[j];
+      acc_r += w[j] * v.col[3 * j];
+      acc_g += w[j] * v.col[3 * j + 1];
+      acc_b += w[j] * v.col[3 * j + 2];
+      acc_d += w[j] * v.z[j];
+      acc_w += w[j];
+    }
+    if (a.out_w != nullptr && ray_ok && s0 < S)
+      stg_stream4(a.out_w + ray * (long long)S + s0, make_float4(w[0], w[1], w[2], w[3]));
+    acc_r = group_sum<G>(acc_r);
+    acc_g = group_sum<G>(acc_g);
+    acc_b = group_sum<G>(acc_b);
+    acc_d = group_sum<G>(acc_d);
+    acc_w = group_sum<G>(acc_w);
+    if (ray_ok && gl == 0) {
+      if (a.white) {
+        const float bg = 1.0f - acc_w;
+        acc_r += bg; acc_g += bg; acc_b += bg;
+      }
+      a.out_rgb[ray * 3] = acc_r; a.out_rgb[ray * 3 + 1] = acc_g; a.out_rgb[ray * 3 + 2] = acc_b;
+      if (a.out_depth != nullptr) a.out_depth[ray] = acc_d;
+    }
+    if (a.target != nullptr) loss_epilogue(a, ray, ray_ok && gl == 0, acc_r, acc_g, acc_b, acc_d, tile);
+    __syncthreads();                                                // everyone has read this stage
+    if (threadIdx.x == 0 && tile + kBwdStages * step < n_tiles) issue(tile + kBwdStages * step, stage);
+  }
+}
+
+template <int G>
+int launch_fwd_staged(const CompositeArgs &a, cudaStream_t st) {
+  constexpr int kRays = (kBlock / 32) * (32 / G);
+  const long long n_tiles = (a.n_rays + kRays - 1) / kRays;
+  const size_t smem = sizeof(float) * (size_t)kBwdStages * kRays * a.S * 5 + 64;
+  static PerDeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.need(&attr_dev)) {
+    cudaError_t e = cudaFuncSetAttribute(composite_fwd_staged_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return fail_cuda("nfs_composite_fwd", e);
+    attr_once.mark(attr_dev);
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long max_blocks = (long long)sms * 4;
+  const unsigned grid = (unsigned)(n_tiles < max_blocks ? n_tiles : max_blocks);
+  composite_fwd_staged_kernel<G><<<grid, kBlock, smem, st>>>(a, n_tiles);
+  return check_launch("nfs_composite_fwd");
+}
+
 // ------------------------------- dispatch -----------------------------------
 int pick_group(int S) { return S <= 32 ? 8 : (S <= 64 ? 16 : 32); }
 
@@ -618,6 +762,18 @@ int dispatch(const CompositeArgs &a, bool aligned, bool packed, cudaStream_t st)
     if (G == 8) return launch_bwd_staged<8>(a, st);
     if (G == 16) return launch_bwd_staged<16>(a, st);
     return launch_bwd_staged<32>(a, st);
+  }
+  // forward: the staged pipeline pays once every block has at least two tiles to overlap
+  if (FWD && aligned && !packed && a.noise == nullptr && a.S <= 4 * G && getenv("NFS_FWD_UNSTAGED") == nullptr &&
+      sizeof(float) * (size_t)kBwdStages * (kBlock / 32) * (32 / G) * a.S * 5 + 64 <= 96 * 1024) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long n_tiles = (a.n_rays + (kBlock / 32) * (32 / G) - 1) / ((kBlock / 32) * (32 / G));
+    if (n_tiles >= 2LL * sms * 4) {
+      if (G == 8) return launch_fwd_staged<8>(a, st);
+      if (G == 16) return launch_fwd_staged<16>(a, st);
+      return launch_fwd_staged<32>(a, st);
+    }
   }
 #define NFS_CASE(GV, AL, PK)                                                         \
   if (G == GV && aligned == AL && packed == PK)                                      \
