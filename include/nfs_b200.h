@@ -219,6 +219,20 @@ int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int6
                    float *dw, int64_t ld_m, int64_t ld_n,
                    float *colsum, int32_t colsum_of_v, void *stream);
 
+/* nfs_wgrad_multi_bf16: several independent nfs_wgrad_bf16 jobs in ONE launch (the SMs are divided among the jobs
+ *   in proportion to their operand bytes).  For models with many small layers (NeRFWithDINO: 21 weight gradients
+ *   of a few ten thousand points each) a launch per layer is mostly fixed cost.  jobs: HOST array, read during the
+ *   call; every field as the nfs_wgrad_bf16 argument of the same name. */
+typedef struct nfs_wgrad_job {
+  const void *u_bf16; int64_t u_pitch;
+  const void *v_bf16; int64_t v_pitch;
+  int64_t n_points;
+  int32_t m_dim, n_dim, m_valid, n_valid;
+  float *dw; int64_t ld_m, ld_n;
+  float *colsum; int32_t colsum_of_v;
+} nfs_wgrad_job;
+int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, void *stream);
+
 /* nfs_mlp_chain: a whole chain of dense layers in ONE launch (fused multi-layer MLP):
  *   h_0 = X;  h_{l+1} = act_l( h_l . W_l^T + b_l ),  l = 0 .. n_layers-1
  *   Forward use: replaces nerf_model.NeRFMLP.forward (src/models/nerf_model.py:16-24) and the equal-width

@@ -41,8 +41,10 @@ struct WgradArgs {
   int bulk_drain;     // destination is a contiguous n-major [n_valid x M] block: drain through smem + TMA bulk reduce
 };
 
-__global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v, const WgradArgs a) {
+// One CTA's share of one weight-gradient job: CTA `cta` of `n_cta` takes the slabs cta, cta + n_cta, ...
+__device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CUtensorMap *tmap_v_p, const WgradArgs &a,
+                                           const unsigned cta, const unsigned n_cta) {
+  const CUtensorMap &tmap_u = *tmap_u_p, &tmap_v = *tmap_v_p;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int mb = a.M >> 6, nb = a.N >> 6, S = a.n_stages;
@@ -75,7 +77,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++it) {
+      for (long long slab = cta; slab < n_slabs; slab += n_cta, ++it) {
         const uint32_t stage = it % S, ph = (it / S) & 1;
         mbar_wait(empty + stage, ph ^ 1);
         mbar_expect_tx(full + stage, (uint32_t)stage_bytes);
@@ -89,7 +91,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, a.N, 1, 1);   // both operands MN-major
       uint32_t it = 0;
-      for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++it) {
+      for (long long slab = cta; slab < n_slabs; slab += n_cta, ++it) {
         const uint32_t stage = it % S, ph = (it / S) & 1;
         mbar_wait(full + stage, ph);
         tc_fence_after();
@@ -117,7 +119,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
       const int blk = col >> 6, cc = col & 63;
       float s0 = 0.f, s1 = 0.f;
       uint32_t it = 0;
-      for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++it) {
+      for (long long slab = cta; slab < n_slabs; slab += n_cta, ++it) {
         const uint32_t stage = it % S, ph = (it / S) & 1;
         mbar_wait(full + stage, ph);
         if (active) {
@@ -172,7 +174,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
         }
         fence_proxy_async();                                 // generic-proxy writes -> visible to the bulk copy
         asm volatile("bar.sync 1, 128;" ::: "memory");       // the four drain warps
-        if (threadIdx.x == 64 && n_slabs > (long long)blockIdx.x) {
+        if (threadIdx.x == 64 && n_slabs > (long long)cta) {
           const uint32_t bytes = (uint32_t)rows * (uint32_t)M * 4u;
           asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                        ::"l"(a.dw + (long long)n0 * M), "r"(smem_u32(stage)), "r"(bytes) : "memory");
@@ -180,7 +182,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
         }
       }
       if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    } else if (n_slabs > (long long)blockIdx.x) {
+    } else if (n_slabs > (long long)cta) {
       for (int h = 0; h < (a.M >> 7); ++h) {
         const long long m = h * 128 + q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * a.N);
@@ -206,28 +208,48 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__
   }
 }
 
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v, const WgradArgs a) {
+  wgrad_body(&tmap_u, &tmap_v, a, blockIdx.x, gridDim.x);
+}
+
+// Several independent weight-gradient jobs in ONE launch (the ~21 layers of NeRFWithDINO at a few ten thousand
+// points each: a launch per layer is ~25 us of mostly fixed cost).  The CTAs are divided among the jobs in
+// proportion to their operand bytes; each CTA then runs exactly the single-job body on its job.
+constexpr int kWgMaxJobs = 24;
+struct alignas(64) WgradMulti {
+  CUtensorMap tu[kWgMaxJobs], tv[kWgMaxJobs];
+  WgradArgs a[kWgMaxJobs];
+  unsigned cta0[kWgMaxJobs + 1];        // job j owns CTAs cta0[j] .. cta0[j+1]
+  int n_jobs;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_multi_kernel(const __grid_constant__ WgradMulti m) {
+  int j = 0;
+  while (j + 1 < m.n_jobs && blockIdx.x >= m.cta0[j + 1]) ++j;
+  wgrad_body(&m.tu[j], &m.tv[j], m.a[j], blockIdx.x - m.cta0[j], m.cta0[j + 1] - m.cta0[j]);
+}
+
 }  // namespace
 }  // namespace nfs
 
 using namespace nfs;
 
-extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int64_t v_pitch,
-                              int64_t n_points, int32_t m_dim, int32_t n_dim, int32_t m_valid, int32_t n_valid,
-                              float *dw, int64_t ld_m, int64_t ld_n, float *colsum, int32_t colsum_of_v, void *stream) {
-  const char *fn = "nfs_wgrad_bf16";
+// Validates one job and fills its tensor maps / arguments; returns 0, or 1 for an empty job, or an error (< 0 / cudaError).
+static int prepare_job(const char *fn, const void *u_bf16, int64_t u_pitch, const void *v_bf16, int64_t v_pitch,
+                       int64_t n_points, int32_t m_dim, int32_t n_dim, int32_t m_valid, int32_t n_valid, float *dw,
+                       int64_t ld_m, int64_t ld_n, float *colsum, int32_t colsum_of_v, CUtensorMap *tu, CUtensorMap *tv,
+                       WgradArgs *out, size_t *smem) {
   if (n_points < 0 || m_dim <= 0 || n_dim <= 0) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
-  if (n_points == 0) return 0;
+  if (n_points == 0) return 1;
   if (!u_bf16 || !v_bf16 || !dw) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
   if (m_dim % 128 != 0 || m_dim > 256 || n_dim % 64 != 0 || n_dim > 256 || (m_dim / 128) * n_dim > 512)
     return fail_arg(fn, NFS_E_UNSUPPORTED, "need M in {128,256}, N % 64 == 0, N <= 256");
   if (u_pitch < m_dim || v_pitch < n_dim) return fail_arg(fn, NFS_E_BADARG, "row pitch smaller than the row");
-
-  CUtensorMap tu, tv;
-  int rc = tc::make_tmap_bf16(&tu, u_bf16, (uint64_t)n_points, (uint64_t)m_dim, (uint64_t)u_pitch, kSlabP, fn);
+  int rc = tc::make_tmap_bf16(tu, u_bf16, (uint64_t)n_points, (uint64_t)m_dim, (uint64_t)u_pitch, kSlabP, fn);
   if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tv, v_bf16, (uint64_t)n_points, (uint64_t)n_dim, (uint64_t)v_pitch, kSlabP, fn);
+  rc = tc::make_tmap_bf16(tv, v_bf16, (uint64_t)n_points, (uint64_t)n_dim, (uint64_t)v_pitch, kSlabP, fn);
   if (rc) return rc;
-
   WgradArgs a{};
   a.P = n_points; a.M = m_dim; a.N = n_dim; a.dw = dw; a.ld_m = ld_m; a.ld_n = ld_n;
   a.colsum = colsum; a.colsum_of_v = colsum_of_v;
@@ -245,14 +267,36 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   int cols = 32;
   while (cols < (m_dim / 128) * n_dim) cols <<= 1;
   a.tmem_cols = cols;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;
+  *smem = 1024 + (size_t)stages * stage_bytes + 256;
+  *out = a;
+  return 0;
+}
+
+static int wgrad_attrs(const char *fn) {
   static PerDeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.need(&attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(fn, e);
     attr_once.mark(attr_dev);
   }
+  return 0;
+}
+
+extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v_bf16, int64_t v_pitch,
+                              int64_t n_points, int32_t m_dim, int32_t n_dim, int32_t m_valid, int32_t n_valid,
+                              float *dw, int64_t ld_m, int64_t ld_n, float *colsum, int32_t colsum_of_v, void *stream) {
+  const char *fn = "nfs_wgrad_bf16";
+  CUtensorMap tu, tv;
+  WgradArgs a{};
+  size_t smem = 0;
+  int rc = prepare_job(fn, u_bf16, u_pitch, v_bf16, v_pitch, n_points, m_dim, n_dim, m_valid, n_valid, dw, ld_m, ld_n,
+                       colsum, colsum_of_v, &tu, &tv, &a, &smem);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  if ((rc = wgrad_attrs(fn))) return rc;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long n_slabs = (n_points + kSlabP - 1) / kSlabP;
@@ -260,7 +304,52 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   // points, so small launches want ALL SMs to keep the streaming part short (scripts/dev/wgrad_trace.py).
   long long g = n_slabs < sms ? n_slabs : sms;
   if (const char *force = getenv("NFS_WGRAD_GRID")) g = atoll(force) > 0 && atoll(force) < g ? atoll(force) : g;   // developer switch
-  const unsigned grid = (unsigned)g;
-  wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tu, tv, a);
+  wgrad_kernel<<<(unsigned)g, kWgThreads, smem, (cudaStream_t)stream>>>(tu, tv, a);
   return check_launch(fn);
+}
+
+extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, void *stream) {
+  const char *fn = "nfs_wgrad_multi_bf16";
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail_arg(fn, NFS_E_BADARG, "bad job list");
+  int rc = wgrad_attrs(fn);
+  if (rc) return rc;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (int first = 0; first < n_jobs;) {
+    WgradMulti m{};
+    double bytes[kWgMaxJobs];
+    long long slabs[kWgMaxJobs];
+    double total = 0.0;
+    size_t smem = 0;
+    int k = 0;
+    for (; first < n_jobs && k < kWgMaxJobs && k < sms; ++first) {
+      const nfs_wgrad_job &j = jobs[first];
+      size_t sm = 0;
+      rc = prepare_job(fn, j.u_bf16, j.u_pitch, j.v_bf16, j.v_pitch, j.n_points, j.m_dim, j.n_dim, j.m_valid, j.n_valid,
+                       j.dw, j.ld_m, j.ld_n, j.colsum, j.colsum_of_v, &m.tu[k], &m.tv[k], &m.a[k], &sm);
+      if (rc == 1) continue;
+      if (rc) return rc;
+      if (sm > smem) smem = sm;
+      slabs[k] = (j.n_points + kSlabP - 1) / kSlabP;
+      bytes[k] = (double)j.n_points * (j.m_dim + j.n_dim) * 2.0 + 8e5;    // + the fixed cost of a CTA, in byte-equivalents
+      total += bytes[k];
+      ++k;
+    }
+    if (k == 0) continue;
+    // CTAs per job: proportional to its share of the work, at least 1, at most its slab count
+    unsigned used = 0;
+    for (int i = 0; i < k; ++i) {
+      long long c = (long long)(sms * bytes[i] / total);
+      if (c < 1) c = 1;
+      if (c > slabs[i]) c = slabs[i];
+      m.cta0[i] = used;
+      used += (unsigned)c;
+    }
+    m.cta0[k] = used;
+    m.n_jobs = k;
+    wgrad_multi_kernel<<<used, kWgThreads, smem, (cudaStream_t)stream>>>(m);
+    rc = check_launch(fn);
+    if (rc) return rc;
+  }
+  return 0;
 }

@@ -35,6 +35,7 @@ SIGNATURES = {
     "nfs_project_gather": (ctypes.c_int, [_p, _p, _f32, _i32, _i32, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _p]),
     "nfs_linear_bf16": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p, _p]),
     "nfs_wgrad_bf16": (ctypes.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _i64, _i64, _p, _i32, _p]),
+    "nfs_wgrad_multi_bf16": (ctypes.c_int, [_p, _i32, _p]),
     "nfs_mlp_chain": (ctypes.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _i64, _p, _p, _p, _i64, _p, _i32, _p]),
     "nfs_pack_stack": (ctypes.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "nfs_bias_terms_bf16": (ctypes.c_int, [_p, _i32, _p, _p]),
@@ -49,6 +50,15 @@ SIGNATURES = {
     "nfs_adam_step_dev": (ctypes.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p, _f32, _i32, _p]),
     "nfs_sample_hierarchical": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
 }
+
+
+
+class WgradJob(ctypes.Structure):
+    """struct nfs_wgrad_job of include/nfs_b200.h."""
+    _fields_ = [("u_bf16", _p), ("u_pitch", _i64), ("v_bf16", _p), ("v_pitch", _i64), ("n_points", _i64),
+                ("m_dim", _i32), ("n_dim", _i32), ("m_valid", _i32), ("n_valid", _i32),
+                ("dw", _p), ("ld_m", _i64), ("ld_n", _i64), ("colsum", _p), ("colsum_of_v", _i32)]
+
 
 _lib = None
 

@@ -17,6 +17,7 @@ and bias (the fusion layers W1, W2 receive both of their uses), nfs_gate_bwd_bf1
 gate.  Nothing here computes on the CPU or in eager PyTorch.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -123,26 +124,35 @@ def _epoch():
     return mlp._WEIGHT_EPOCH
 
 
-def wgrad_layer(x16, blocks, dy16, lin, dw, db):
+def _wg(jobs, u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True, m_valid=0, n_valid=0):
+    if jobs is None:
+        ops.wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=colsum, colsum_of_v=colsum_of_v, m_valid=m_valid, n_valid=n_valid)
+    else:
+        jobs.append(dict(u=u, v=v, dw=dw, ld_m=ld_m, ld_n=ld_n, colsum=colsum, colsum_of_v=colsum_of_v,
+                         m_valid=m_valid, n_valid=n_valid))
+
+
+def wgrad_layer(x16, blocks, dy16, lin, dw, db, jobs=None):
     """dW[out,in] += dY^T X, db[out] += column sums of dY for one Linear (nfs_wgrad_bf16).
     x16 bf16 [P, *] operand; blocks = [(first input column, width, first operand column, padded width)];
     dy16 bf16 [P, n_pad].  The reduction runs over points, so either operand can take the M side:
-    a 128/256-wide input block does (its index is the contiguous one of dW), else dY must be 128/256 wide."""
+    a 128/256-wide input block does (its index is the contiguous one of dW), else dY must be 128/256 wide.
+    jobs: a list - the launches are appended to it (ops.wgrad_multi runs them together) instead of issued."""
     out_f, in_f = lin.out_features, lin.in_features
     n_pad = dy16.shape[1]
     first = True
     for c_in, width, c_op, w_pad in blocks:
         if w_pad in (128, 256) and n_pad % 64 == 0:
-            ops.wgrad_bf16(x16[:, c_op:c_op + w_pad], dy16, dw[:, c_in:], 1, in_f, colsum=db if first else None,
-                           colsum_of_v=True, m_valid=width, n_valid=out_f)
+            _wg(jobs, x16[:, c_op:c_op + w_pad], dy16, dw[:, c_in:], 1, in_f, colsum=db if first else None,
+                colsum_of_v=True, m_valid=width, n_valid=out_f)
         elif n_pad in (128, 256):
             for c in range(0, w_pad, 256):
                 w = min(256, w_pad - c)
                 valid = min(width - c, w)
                 if valid <= 0:
                     break
-                ops.wgrad_bf16(dy16, x16[:, c_op + c:c_op + c + w], dw[:, c_in + c:], in_f, 1,
-                               colsum=db if first else None, colsum_of_v=False, m_valid=out_f, n_valid=valid)
+                _wg(jobs, dy16, x16[:, c_op + c:c_op + c + w], dw[:, c_in + c:], in_f, 1,
+                    colsum=db if first else None, colsum_of_v=False, m_valid=out_f, n_valid=valid)
                 first = False
         else:
             raise RuntimeError("nfs_b200: unsupported layer shape for wgrad (%d -> %d)" % (in_f, out_f))
@@ -267,11 +277,15 @@ class G3Plan:
             off += n
         gw = {id(l): (views[2 * i], views[2 * i + 1]) for i, l in enumerate(lins)}
 
+        # every weight gradient of the step is collected and issued as ONE multi-job launch at the end (a launch
+        # per layer costs ~25 us of mostly fixed time at cfg 4's 32 768 points); operands stay alive in `jobs`
+        jobs = [] if os.environ.get("NFS_WGRAD_MULTI", "1") != "0" else None
+
         def wg(lin, x16, dy16, blocks=None):
             dw, db = gw[id(lin)]
             if blocks is None:
                 blocks = [(0, lin.in_features, 0, x16.shape[1])]
-            wgrad_layer(x16, blocks, dy16, lin, dw, db)
+            wgrad_layer(x16, blocks, dy16, lin, dw, db, jobs=jobs)
 
         hn = sb[nb - 1, :P]
         # ---- colour MLP (nerf_mlp.py:82-84)
@@ -322,6 +336,8 @@ class G3Plan:
         wg(self.W2, h1, dh2)
         dh1, _ = ops.linear_bf16(dh2, self.p2.w16t, None, act=0, relu_mask_src=h1)
         wg(self.W1, c16, dh1, blocks=k0_blocks)
+        if jobs:
+            ops.wgrad_multi(jobs)
         return views
 
 

@@ -487,3 +487,34 @@ def wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True, m_valid=0, n
             _lib.call("nfs_wgrad_bf16", ptr(u), u.stride(0), ptr(v), v.stride(0), P, M, N, int(m_valid), int(n_valid),
                       ptr(dw), int(ld_m), int(ld_n), ptr(colsum), int(bool(colsum_of_v)), _stream())
     return dw
+
+
+def wgrad_multi(jobs):
+    """Several wgrad_bf16 calls in one launch (nfs_wgrad_multi_bf16).  jobs: list of dicts with the keyword
+    arguments of wgrad_bf16 (u, v, dw, ld_m, ld_n, colsum, colsum_of_v, m_valid, n_valid)."""
+    arr = (_lib.WgradJob * max(len(jobs), 1))()
+    keep, n, dev = [], 0, None
+    for jb in jobs:
+        u, v, dw, colsum = jb["u"], jb["v"], jb["dw"], jb.get("colsum")
+        _need_cuda("wgrad_multi", u, v, dw, colsum)
+        if u.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or u.stride(1) != 1 or v.stride(1) != 1:
+            raise RuntimeError("wgrad_multi: operands must be bf16 with contiguous columns")
+        if dw.dtype != torch.float32 or (colsum is not None and colsum.dtype != torch.float32):
+            raise RuntimeError("wgrad_multi: destinations must be fp32")
+        if v.shape[0] != u.shape[0]:
+            raise RuntimeError("wgrad_multi: operands disagree on the number of points")
+        if u.shape[0] == 0:
+            continue
+        dev = u.device
+        a = arr[n]
+        a.u_bf16, a.u_pitch, a.v_bf16, a.v_pitch = u.data_ptr(), u.stride(0), v.data_ptr(), v.stride(0)
+        a.n_points, a.m_dim, a.n_dim = u.shape[0], u.shape[1], v.shape[1]
+        a.m_valid, a.n_valid = int(jb.get("m_valid", 0)), int(jb.get("n_valid", 0))
+        a.dw, a.ld_m, a.ld_n = dw.data_ptr(), int(jb["ld_m"]), int(jb["ld_n"])
+        a.colsum = colsum.data_ptr() if colsum is not None else None
+        a.colsum_of_v = int(bool(jb.get("colsum_of_v", True)))
+        keep.append((u, v, dw, colsum))
+        n += 1
+    if n:
+        with torch.cuda.device(dev):
+            _lib.call("nfs_wgrad_multi_bf16", ctypes.byref(arr), n, _stream())
