@@ -324,6 +324,14 @@ int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n
 int nfs_pack_stack(const void *table, int32_t n_entries, int32_t max_elems, void *w_stack_bf16, void *wt_stack_bf16,
                    void *bias_terms_bf16, void *stream);
 
+/* nfs_pack_table: the general form of nfs_pack_stack for models whose bf16 operands live in many tensors
+ * (NeRFWithDINO).  table: device int64 [n_entries, 10], row =
+ *   [src (fp32 pointer), n_dim, k_dim (0: vector), src_pitch, dst (pointer), dst_pitch, row0, col0, mode, 0]
+ *   mode 0: bf16 dst[(row0+n)*dst_pitch + col0+k] = src[n*src_pitch + k]     mode 1: the transpose,
+ *           dst[(row0+k)*dst_pitch + col0+n];   mode 2: fp32 dst[row0+n] = src[n];   mode 3: bias terms
+ *           (nfs_bias_terms_bf16) dst[row0+n].  max_elems = the largest n_dim*max(k_dim,1). */
+int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_elems, void *stream);
+
 /* fp32 bias[n] -> terms_bf16 [n, 8] bf16, row i = [hi, mid, lo, 0, 0, 0, 0, 0] with hi + mid + lo = bias[i] to
  * ~2^-24 relative: the bias operand of nfs_mlp_chain (nn.Linear's "+ b", nerf_model.py:16-24, added on the
  * tensor core as ones[128x16] . terms^T).  Refreshed with the packed weights after an optimizer step. */

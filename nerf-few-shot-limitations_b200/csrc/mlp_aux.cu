@@ -290,6 +290,50 @@ extern "C" int nfs_pack_stack(const void *table, int32_t n_entries, int32_t max_
   return check_launch(fn);
 }
 
+// General form of the above for models whose operands live in many tensors (NeRFWithDINO: per-layer W / W^T / bias
+// copies for the single-layer kernels plus three stacked chain operands).  Table row (int64 x 10):
+//   [src (fp32), n_dim, k_dim (0: vector), src_pitch, dst, dst_pitch, row0, col0, mode, unused]
+//   mode 0: bf16 dst[(row0+n)*dst_pitch + col0+k] = src[n*src_pitch + k]
+//   mode 1: bf16 dst[(row0+k)*dst_pitch + col0+n] = src[n*src_pitch + k]          (transposed)
+//   mode 2: fp32 dst[row0+n] = src[n]                                            (bias copy)
+//   mode 3: bias terms (uint4 rows) dst[row0+n] = split(src[n])
+__global__ void __launch_bounds__(256) pack_table_kernel(const long long *__restrict__ table) {
+  const long long *e = table + 10 * blockIdx.y;
+  const float *src = reinterpret_cast<const float *>(e[0]);
+  const int N = (int)e[1], K = (int)e[2], mode = (int)e[8];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode >= 2) {
+    if (idx >= N) return;
+    const float b = __ldg(src + idx);
+    if (mode == 2) { reinterpret_cast<float *>(e[4])[e[6] + idx] = b; return; }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const float r1 = b - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    reinterpret_cast<uint4 *>(e[4])[e[6] + idx] =
+        make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                   (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+    return;
+  }
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(src + (long long)n * e[3] + k));
+  __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(e[4]);
+  if (mode == 0) dst[(e[6] + n) * e[5] + e[7] + k] = v;
+  else dst[(e[6] + k) * e[5] + e[7] + n] = v;
+}
+
+extern "C" int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_elems, void *stream) {
+  const char *fn = "nfs_pack_table";
+  if (n_entries < 0 || max_elems < 0) return fail_arg(fn, NFS_E_BADARG, "negative size");
+  if (n_entries == 0 || max_elems == 0) return 0;
+  if (!table) return fail_arg(fn, NFS_E_BADARG, "null pointer");
+  if (n_entries > 65535) return fail_arg(fn, NFS_E_TOOLARGE, "too many entries");
+  dim3 grid((unsigned)((max_elems + 255) / 256), (unsigned)n_entries);
+  pack_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)table);
+  return check_launch(fn);
+}
+
 extern "C" int nfs_bias_terms_bf16(const float *bias, int32_t n, void *terms_bf16, void *stream) {
   const char *fn = "nfs_bias_terms_bf16";
   if (n < 0) return fail_arg(fn, NFS_E_BADARG, "negative size");

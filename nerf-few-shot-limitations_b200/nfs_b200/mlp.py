@@ -67,6 +67,27 @@ class PackedLinear:
         self._key = None
         self.w16 = self.w16t = self.bias = None
 
+    def current_key(self):
+        params = [p for l in self.linears for p in (l.weight, l.bias)]
+        return (str(params[0].device), _WEIGHT_EPOCH) + tuple((p.data_ptr(), p._version) for p in params)
+
+    def alloc(self, dev):
+        if self.w16 is None or self.w16.device != dev:
+            self.w16 = torch.zeros(self.n_pad, self.k_pad, device=dev, dtype=torch.bfloat16)
+            self.w16t = torch.zeros(self.k_pad, self.n_pad, device=dev, dtype=torch.bfloat16)
+            self.bias = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+
+    def table_rows(self):
+        """Rows of an nfs_pack_table table that refresh this layer's operand copies (after alloc())."""
+        rows, row = [], 0
+        for l in self.linears:
+            w, b, n, k = l.weight, l.bias, l.out_features, l.in_features
+            rows.append([w.data_ptr(), n, k, k, self.w16.data_ptr(), self.k_pad, row, 0, 0, 0])
+            rows.append([w.data_ptr(), n, k, k, self.w16t.data_ptr(), self.n_pad, 0, row, 1, 0])
+            rows.append([b.data_ptr(), n, 0, 0, self.bias.data_ptr(), 0, row, 0, 2, 0])
+            row += n
+        return rows
+
     def refresh(self):
         params = [p for l in self.linears for p in (l.weight, l.bias)]
         dev = params[0].device
@@ -75,10 +96,7 @@ class PackedLinear:
             return self
         if not params[0].is_cuda:
             raise RuntimeError("nfs_b200: model parameters must live on a CUDA device (no CPU fallback)")
-        if self.w16 is None or self.w16.device != dev:
-            self.w16 = torch.zeros(self.n_pad, self.k_pad, device=dev, dtype=torch.bfloat16)
-            self.w16t = torch.zeros(self.k_pad, self.n_pad, device=dev, dtype=torch.bfloat16)
-            self.bias = torch.zeros(self.n_pad, device=dev, dtype=torch.float32)
+        self.alloc(dev)
         row = 0
         with torch.cuda.device(dev), torch.no_grad():
             for l in self.linears:

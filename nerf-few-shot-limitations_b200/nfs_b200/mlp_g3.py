@@ -40,6 +40,37 @@ class _Stack:
         self.layers, self.transposed = layers, transposed
         self.key = None
 
+    def alloc(self, dev):
+        """Allocate (zeroed) the stacked operands; shapes depend only on the layer widths."""
+        shapes = [((p.k_pad, p.n_pad) if self.transposed else (p.n_pad, p.k_pad)) for p in self.layers]
+        rows = sum(sh[0] for sh in shapes)
+        if getattr(self, "w", None) is None or self.w.device != dev or self.w.shape[0] != rows:
+            self.w = torch.zeros(rows, 256, device=dev, dtype=torch.bfloat16)
+            self.b = None if self.transposed else torch.zeros(rows, 8, device=dev, dtype=torch.bfloat16)
+            self.rows = rows
+            row0, r = [], 0
+            for sh in shapes:
+                row0.append(r)
+                r += sh[0]
+            self._row0 = row0
+            self.c_row0 = _i32arr(row0)
+            self.c_k = _i32arr([sh[1] for sh in shapes])
+            self.c_n = _i32arr([sh[0] for sh in shapes])
+
+    def table_rows(self):
+        rows = []
+        for p, r in zip(self.layers, self._row0):
+            sub = 0
+            for l in p.linears:
+                w, b, n, k = l.weight, l.bias, l.out_features, l.in_features
+                if self.transposed:
+                    rows.append([w.data_ptr(), n, k, k, self.w.data_ptr(), 256, r, sub, 1, 0])
+                else:
+                    rows.append([w.data_ptr(), n, k, k, self.w.data_ptr(), 256, r + sub, 0, 0, 0])
+                    rows.append([b.data_ptr(), n, 0, 0, self.b.data_ptr(), 0, r + sub, 0, 3, 0])
+                sub += n
+        return rows
+
     def refresh(self):
         key = tuple(p._key for p in self.layers)
         if key == self.key:
@@ -72,6 +103,17 @@ class _SplitColumns(PackedLinear):
         super().__init__([linear], k_pad, n_pad)
         self.blocks = blocks                      # (first input column, width, first operand column)
 
+    def table_rows(self):
+        l = self.linears[0]
+        n, k_in = l.out_features, l.in_features
+        rows = []
+        for c_in, width, c_op in self.blocks:
+            src = l.weight.data_ptr() + 4 * c_in
+            rows.append([src, n, width, k_in, self.w16.data_ptr(), self.k_pad, 0, c_op, 0, 0])
+            rows.append([src, n, width, k_in, self.w16t.data_ptr(), self.n_pad, c_op, 0, 1, 0])
+        rows.append([l.bias.data_ptr(), n, 0, 0, self.bias.data_ptr(), 0, 0, 0, 2, 0])
+        return rows
+
     def refresh(self):
         l = self.linears[0]
         key = (str(l.weight.device), l.weight.data_ptr(), l.weight._version, l.bias._version, _epoch())
@@ -102,14 +144,21 @@ class _StackedHeads(PackedLinear):
         super().__init__(heads, k_pad, n_pad)
         self.row_offsets = row_offsets
 
+    def alloc(self, dev):
+        if self.w16t is None or self.w16t.device != dev:
+            self.w16t = torch.zeros(self.k_pad, self.n_pad, device=dev, dtype=torch.bfloat16)
+
+    def table_rows(self):
+        return [[l.weight.data_ptr(), l.out_features, l.in_features, l.in_features, self.w16t.data_ptr(), self.n_pad,
+                 0, r0, 1, 0] for l, r0 in zip(self.linears, self.row_offsets)]
+
     def refresh(self):
         params = [p for l in self.linears for p in (l.weight, l.bias)]
         dev = params[0].device
         key = (str(dev), _epoch()) + tuple((p.data_ptr(), p._version) for p in params)
         if key == self._key:
             return self
-        if self.w16t is None or self.w16t.device != dev:
-            self.w16t = torch.zeros(self.k_pad, self.n_pad, device=dev, dtype=torch.bfloat16)
+        self.alloc(dev)
         with torch.cuda.device(dev), torch.no_grad():
             for l, r0 in zip(self.linears, self.row_offsets):
                 w = l.weight.detach().float().contiguous()
@@ -223,11 +272,41 @@ class G3Plan:
         return ps
 
     def refresh(self):
+        """Bring every bf16 operand up to date with the fp32 parameters: ONE nfs_pack_table launch (the table lists
+        where each parameter lands in the per-layer copies and in the three stacked chain operands)."""
+        params = self.params()
+        dev = params[0].device
+        if not params[0].is_cuda:
+            raise RuntimeError("nfs_b200: model parameters must live on a CUDA device (no CPU fallback)")
+        key = (str(dev), _epoch()) + tuple((p.data_ptr(), p._version) for p in params)
+        if key == getattr(self, "_key", None):
+            return
+        simple = all(p.dtype == torch.float32 and p.is_contiguous() for p in params)
+        if not simple or os.environ.get("NFS_PACK_STACK", "1") == "0":       # layer by layer (any dtype / layout)
+            for p in self.all_packed:
+                p.refresh()
+            for st in (self.chain_a, self.chain_b, self.chain_b_bwd):
+                st.key = None
+                st.refresh()
+            self._key, self._place = key, None
+            return
+        place = (str(dev),) + tuple(p.data_ptr() for p in params)
+        if place != getattr(self, "_place", None):
+            rows = []
+            for p in self.all_packed:
+                p.alloc(dev)
+                rows += p.table_rows()
+            for st in (self.chain_a, self.chain_b, self.chain_b_bwd):
+                st.alloc(dev)
+                rows += st.table_rows()
+            self._table = torch.tensor(rows, dtype=torch.int64, device=dev)
+            self._max_elems = max(r[1] * max(r[2], 1) for r in rows)
+            self._place = place
+        with torch.cuda.device(dev), torch.no_grad():
+            _lib.call("nfs_pack_table", ptr(self._table), self._table.shape[0], self._max_elems, _stream())
         for p in self.all_packed:
-            p.refresh()
-        self.chain_a.refresh()
-        self.chain_b.refresh()
-        self.chain_b_bwd.refresh()
+            p._key = p.current_key() if hasattr(p, "current_key") and type(p).refresh is PackedLinear.refresh else None
+        self._key = key
 
     def _chain(self, x16, stack, n_layers, acts, P, bits_in=None, mask_idx=None, want_bits=False):
         """nfs_mlp_chain without an output head: every layer's output is saved -> [n_layers, rows, hp]
