@@ -276,7 +276,7 @@ def measure_extras(dev, rank, world, dist, quick):
         out["dino_nerf_cfg4"] = {
             "rays_per_s": world * nb / (ms4 * 1e-3), "ms_per_step": ms4, "rays_per_gpu": nb, "points_per_step": nb * 64,
             "tflops_per_gpu": nb * flop4 / (ms4 * 1e-3) / 1e12, "launch": "CUDA graph replay",
-            "note": "batch 512 x 64 samples = 32768 points per step: latency-bound, ~230 kernels per step"}
+            "note": "batch 512 x 64 samples = 32768 points per step: latency-bound, ~46 kernels per step"}
     except Exception as e:
         out["dino_nerf_cfg4"] = {"error": repr(e)[:300]}
     # render: this rank's contiguous share of the 640 000 rays of one 800 x 800 frame
