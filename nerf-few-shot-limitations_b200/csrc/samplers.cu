@@ -69,7 +69,13 @@ __global__ void __launch_bounds__(256) stratified_kernel(const float *__restrict
 }
 
 // -------------------------------------------------------------- hierarchical
-// one warp = one ray.  Shared memory per warp: cdf[M+1] | zc[M+1] | buf[P2]
+// one warp = one ray.  Shared memory per warp: cdf[M+1] | zc[M+1] | smp[P2] | buf[M+1+Ni]  (P2 = pow2 >= Ni)
+// The reference sorts cat([z_vals, samples]) (ray_utils.py:138).  z_vals is already sorted and the inverse-CDF
+// samples are non-decreasing in u, so with sorted draws (perturb=False: u = linspace) both lists are sorted and the
+// output is a MERGE: every element's position is its own index plus its rank in the other list (one binary search,
+// ~8 steps), instead of a 256-key bitonic network (288 compare-exchange sweeps - the kernel was instruction-bound
+// on it: 462 us per 65 536 rays, 4.2 % of a full-frame render).  Random draws (training) first sort the Ni samples
+// (bitonic over P2 keys).  Either way the result is the sorted multiset, bit-identical to torch.sort's values.
 __global__ void __launch_bounds__(128) hierarchical_kernel(
     const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ z_vals,
     const float *__restrict__ weights, const float *__restrict__ u, long long u_stride,
@@ -81,11 +87,12 @@ __global__ void __launch_bounds__(128) hierarchical_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ray = (long long)blockIdx.x * warps + warp;
   if (ray >= n_rays) return;   // whole warp leaves together
-  const int per_warp = 2 * (M + 1) + P2;
+  const int total = M + 1 + Ni;
+  const int per_warp = 2 * (M + 1) + P2 + total;
   float *cdf = smem + (size_t)warp * per_warp;
   float *zc = cdf + (M + 1);
-  float *buf = zc + (M + 1);
-  const int total = M + 1 + Ni;
+  float *smp = zc + (M + 1);
+  float *buf = smp + P2;
 
   for (int i = lane; i <= M; i += 32) zc[i] = __ldg(z_vals + ray * (long long)(M + 1) + i);
 
@@ -125,46 +132,78 @@ __global__ void __launch_bounds__(128) hierarchical_kernel(
   if (cdf_out != nullptr)
     for (int i = lane; i <= M; i += 32) cdf_out[ray * (long long)(M + 1) + i] = cdf[i];
 
-  // merge buffer: coarse z, fine samples, +inf padding
-  for (int i = lane; i <= M; i += 32) buf[i] = zc[i];
-  for (int i = total + lane; i < P2; i += 32) buf[i] = __int_as_float(0x7f800000);
-
   const float *urow = u + ray * u_stride;
-  for (int k = lane; k < Ni; k += 32) {
-    const float uu = __ldg(urow + k);
-    // searchsorted(cdf, u, right=True): number of entries <= u     ray_utils.py:121
-    int lo = 0, hi = M + 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+  bool sorted = true;
+  float prev_last = -__int_as_float(0x7f800000);
+  for (int k0 = 0; k0 < Ni; k0 += 32) {
+    const int k = k0 + lane;
+    float smp_k = __int_as_float(0x7f800000);
+    if (k < Ni) {
+      const float uu = __ldg(urow + k);
+      // searchsorted(cdf, u, right=True): number of entries <= u     ray_utils.py:121
+      int lo = 0, hi = M + 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+      }
+      const int below = max(0, lo - 1), above = min(M, lo);             // :122-123
+      const float c0 = cdf[below], c1 = cdf[above];
+      const float b0 = zc[below], b1 = zc[above];
+      float den = __fsub_rn(c1, c0);                                    // :132
+      if (den < 1e-5f) den = 1.0f;                                      // :133
+      const float t = __fdiv_rn(__fsub_rn(uu, c0), den);                // :134
+      smp_k = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));           // :135
+      if (idx_out != nullptr) idx_out[ray * (long long)Ni + k] = lo;
+      if (samples_out != nullptr) samples_out[ray * (long long)Ni + k] = smp_k;
     }
-    const int below = max(0, lo - 1), above = min(M, lo);             // :122-123
-    const float c0 = cdf[below], c1 = cdf[above];
-    const float b0 = zc[below], b1 = zc[above];
-    float den = __fsub_rn(c1, c0);                                    // :132
-    if (den < 1e-5f) den = 1.0f;                                      // :133
-    const float t = __fdiv_rn(__fsub_rn(uu, c0), den);                // :134
-    const float smp = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0))); // :135
-    buf[M + 1 + k] = smp;
-    if (idx_out != nullptr) idx_out[ray * (long long)Ni + k] = lo;
-    if (samples_out != nullptr) samples_out[ray * (long long)Ni + k] = smp;
+    smp[k] = smp_k;                                                     // k < P2: rounds of 32 never pass a power of two >= 32
+    // non-decreasing so far?  (compare with the previous element: the lane below, or the last lane of the previous round)
+    float before = __shfl_up_sync(kFullMask, smp_k, 1);
+    if (lane == 0) before = prev_last;
+    if (k < Ni && !(before <= smp_k)) sorted = false;
+    prev_last = __shfl_sync(kFullMask, smp_k, 31);
   }
+  for (int i = ((Ni + 31) & ~31) + lane; i < P2; i += 32) smp[i] = __int_as_float(0x7f800000);
+  sorted = __all_sync(kFullMask, sorted);
   __syncwarp();
 
-  // bitonic sort of P2 keys, ascending (torch.sort, ray_utils.py:138)
-  for (int k = 2; k <= P2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < P2; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const float x = buf[i], y = buf[ixj];
-          const bool asc = (i & k) == 0;
-          if ((x > y) == asc) { buf[i] = y; buf[ixj] = x; }
+  if (!sorted) {
+    // bitonic sort of the P2 sample keys, ascending
+    for (int k = 2; k <= P2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P2; i += 32) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float x = smp[i], y = smp[ixj];
+            const bool asc = (i & k) == 0;
+            if ((x > y) == asc) { smp[i] = y; smp[ixj] = x; }
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
+
+  // merge: position = own index + rank in the other list (coarse depths first among equals)
+  for (int i = lane; i <= M; i += 32) {
+    const float v = zc[i];
+    int lo = 0, hi = Ni;                                 // number of samples < v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (smp[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    buf[i + lo] = v;
+  }
+  for (int k = lane; k < Ni; k += 32) {
+    const float v = smp[k];
+    int lo = 0, hi = M + 1;                              // number of coarse depths <= v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (zc[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    buf[k + lo] = v;
+  }
+  __syncwarp();
 
   const float ox = __ldg(rays_o + ray * 3), oy = __ldg(rays_o + ray * 3 + 1), oz = __ldg(rays_o + ray * 3 + 2);
   const float dx = __ldg(rays_d + ray * 3), dy = __ldg(rays_d + ray * 3 + 1), dz = __ldg(rays_d + ray * 3 + 2);
@@ -220,10 +259,10 @@ extern "C" int nfs_sample_hierarchical(const float *rays_o, const float *rays_d,
   if (!rays_o || !rays_d) return fail_arg(fn, NFS_E_BADARG, "rays_o / rays_d are required");
   const int total = n_bins + 1 + n_importance;
   if (total > 4096) return fail_arg(fn, NFS_E_TOOLARGE, "n_bins + 1 + n_importance > 4096");
-  int p2 = 2;
-  while (p2 < total) p2 <<= 1;
-  // scratch for w+1e-5 lives in buf: needs M <= P2 (always true)
-  const size_t per_warp = sizeof(float) * (size_t)(2 * (n_bins + 1) + p2);
+  int p2 = 32;                                  // samples are processed in rounds of 32; bitonic needs a power of two
+  while (p2 < n_importance) p2 <<= 1;
+  // scratch for w+1e-5 lives in buf (M <= total entries)
+  const size_t per_warp = sizeof(float) * (size_t)(2 * (n_bins + 1) + p2 + total);
   int warps = 4;
   while (warps > 1 && per_warp * warps > 48 * 1024) warps >>= 1;
   if (per_warp * warps > 48 * 1024) return fail_arg(fn, NFS_E_TOOLARGE, "shared memory");
