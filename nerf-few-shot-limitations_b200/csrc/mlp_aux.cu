@@ -301,26 +301,44 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const long long *__rest
   const long long *e = table + 10 * blockIdx.y;
   const float *src = reinterpret_cast<const float *>(e[0]);
   const int N = (int)e[1], K = (int)e[2], mode = (int)e[8];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
   if (mode >= 2) {
-    if (idx >= N) return;
-    const float b = __ldg(src + idx);
-    if (mode == 2) { reinterpret_cast<float *>(e[4])[e[6] + idx] = b; return; }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
-    const float r1 = b - __bfloat162float(hi);
-    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-    reinterpret_cast<uint4 *>(e[4])[e[6] + idx] =
-        make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
-                   (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N; idx += stride) {
+      const float b = __ldg(src + idx);
+      if (mode == 2) { reinterpret_cast<float *>(e[4])[e[6] + idx] = b; continue; }
+      const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+      const float r1 = b - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      reinterpret_cast<uint4 *>(e[4])[e[6] + idx] =
+          make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16),
+                     (uint32_t)__bfloat16_as_ushort(lo), 0u, 0u);
+    }
     return;
   }
-  if (idx >= N * K) return;
-  const int n = idx / K, k = idx - n * K;
-  const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(src + (long long)n * e[3] + k));
   __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(e[4]);
-  if (mode == 0) dst[(e[6] + n) * e[5] + e[7] + k] = v;
-  else dst[(e[6] + k) * e[5] + e[7] + n] = v;
+  if (mode == 0) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * K; idx += stride) {
+      const int n = idx / K, k = idx - n * K;
+      dst[(e[6] + n) * e[5] + e[7] + k] = __float2bfloat16_rn(__ldg(src + (long long)n * e[3] + k));
+    }
+    return;
+  }
+  // transposed copy through a 32 x 32 shared-memory tile: reads coalesced along k, writes coalesced along n
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8 threads
+  const int tiles_k = (K + 31) >> 5, n_tiles = ((N + 31) >> 5) * tiles_k;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n0 = (t / tiles_k) << 5, k0 = (t % tiles_k) << 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+      tile[r][tx] = (n0 + r < N && k0 + tx < K) ? __ldg(src + (long long)(n0 + r) * e[3] + k0 + tx) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+      if (k0 + r < K && n0 + tx < N) dst[(e[6] + k0 + r) * e[5] + e[7] + n0 + tx] = __float2bfloat16_rn(tile[tx][r]);
+    __syncthreads();
+  }
 }
 
 extern "C" int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_elems, void *stream) {
@@ -329,7 +347,9 @@ extern "C" int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_
   if (n_entries == 0 || max_elems == 0) return 0;
   if (!table) return fail_arg(fn, NFS_E_BADARG, "null pointer");
   if (n_entries > 65535) return fail_arg(fn, NFS_E_TOOLARGE, "too many entries");
-  dim3 grid((unsigned)((max_elems + 255) / 256), (unsigned)n_entries);
+  // most entries are a few hundred elements (biases): a short grid per entry, threads stride over the large ones
+  const int bx = (max_elems + 255) / 256;
+  dim3 grid((unsigned)(bx < 16 ? bx : 16), (unsigned)n_entries);
   pack_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)table);
   return check_launch(fn);
 }
