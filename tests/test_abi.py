@@ -60,6 +60,29 @@ def test_product_path_has_no_cpu_fallback():
         sample_points_along_rays(torch.rand(5, 3), torch.rand(5, 3), 2.0, 6.0, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         hierarchical_sampling(torch.rand(5, 3), torch.rand(5, 3), torch.rand(5, 8), torch.rand(5, 7), 4)
+    # the 8f additions: ray generation, loss epilogue, feature gather, MLPs, fused optimizer
+    from models.nerf_mlp import NeRFWithDINO
+    from models.nerf_model import NeRFMLP
+    from models.ray_sampler import get_rays
+    from nfs_b200 import ops
+    from nfs_b200.optim import FusedAdam
+    from utils.ray_utils import get_rays as get_rays_u, project_points_to_image
+    for fn in (get_rays, get_rays_u):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(4, 5, 3.0, torch.eye(4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.composite_loss(torch.rand(2, 4, 3), torch.rand(2, 4), torch.rand(2, 4), torch.rand(2, 3), torch.rand(2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        project_points_to_image(torch.rand(6, 3), torch.eye(4), 10.0, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        NeRFMLP()(torch.rand(3, 63))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        NeRFWithDINO()(torch.rand(3, 3), torch.rand(3, 3), torch.rand(3, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdam(NeRFMLP().parameters())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.wgrad_multi([dict(u=torch.zeros(64, 128, dtype=torch.bfloat16), v=torch.zeros(64, 64, dtype=torch.bfloat16),
+                              dw=torch.zeros(64, 128), ld_m=1, ld_n=128)])
 
 
 def test_product_never_imports_the_oracle():
