@@ -232,6 +232,13 @@ class GraphedTrainStep(GraphedStep):
         self.rays_d[:, 2] = -1.0
         self.target = torch.zeros(n_rays, 3, device=dev)
         super().__init__(optimizer, self._loss, loss_scale=loss_scale, allreduce=allreduce, warmup=warmup)
+        # the graphs hold raw pointers into the session's arenas and the plan's stacked operands: keep those
+        # tensors alive even if another caller later makes the session / plan allocate bigger ones
+        sess = _session_for(model, optimizer)
+        plan = model._get_plan() if hasattr(model, "_get_plan") else None
+        self._captured = [getattr(o, k, None) for o, keys in (
+            (sess, ("x16", "save", "bits", "dy", "dys", "head_w", "head_b", "w0_t")),
+            (plan, ("w_stack", "wt_stack", "b_stack", "_table"))) if o is not None for k in keys]
 
     def _forward_backward(self):
         sess = _session_for(self.model, self.opt)
