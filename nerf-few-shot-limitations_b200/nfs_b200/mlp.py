@@ -497,6 +497,7 @@ class StepSession:
         return (getattr(plan, "fusable", False) and len(plan.packed) >= 2 and hasattr(optimizer, "grad")
                 and os.environ.get("NFS_MLP_FUSED", "1") != "0" and os.environ.get("NFS_MLP_FUSED_BWD", "1") != "0"
                 and os.environ.get("NFS_MLP_SESSION", "1") != "0"
+                and len(optimizer.params) == len(plan.params())          # the session fills the WHOLE flat gradient
                 and all(any(p is q for q in optimizer.params) for p in plan.params()))
 
     def begin(self, rows):
