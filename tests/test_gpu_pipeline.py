@@ -145,7 +145,10 @@ def test_conditioned_render_vs_oracle(cuda):
     torch.manual_seed(21)
     ref = O.ConditionedNeRF(pos_freq=12, dino_dim=64)
     mod = NeRFWithDINO(pos_freq=12, dino_dim=64)
-    mod.load_state_dict(ref.state_dict())
+    sd = ref.state_dict()
+    sd["density_mlp.density_head.bias"].fill_(0.3)      # the default init leaves relu(density) = 0 everywhere here:
+    ref.load_state_dict(sd)                              # nothing would be composited and the comparison be vacuous
+    mod.load_state_dict(sd)
     mod = mod.to(cuda).eval()
     # oracle chain
     pts, z = O.stratified(ro, rd, 2.0, 6.0, S, t_rand=t_rand)
@@ -160,6 +163,7 @@ def test_conditioned_render_vs_oracle(cuda):
     e_depth = float((out["depth"].cpu() - ref_out[1].detach()).abs().max())
     record("conditioned_pipeline_vs_oracle", rgb_abs=e_rgb, depth_abs=e_depth)
     assert torch.equal(out["z_vals"].cpu(), z)
+    assert float(ref_out[0].abs().max()) > 0.1 and float(ref_out[1].abs().max()) > 1.0       # a live rendering
     assert e_rgb <= 1e-2 and e_depth <= 5e-2, (e_rgb, e_depth)
 
 
