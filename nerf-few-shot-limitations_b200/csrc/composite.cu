@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kBlock, 5) composite_bwd_kernel(const Composit
 // Same arithmetic as composite_bwd_kernel for the common case (row-major rgb / density / z, S <= 4G, 16-byte
 // aligned, no noise), with the loads decoupled from the compute: persistent blocks walk tiles of
 // kStageRays rays; one thread streams each tile's three (four with g_weights) contiguous input blocks into a
-// 3-stage shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx), the warps read
+// 2-stage shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx), the warps read
 // their samples from shared memory.  The long dependent chains of the backward (two shuffle scans, exp,
 // quotient) then never wait on DRAM latency, and ~40 KB of loads per block are always in flight.
 constexpr int kStageRays = 16;       // 8 warps x (32 / G) rays at G = 16; G = 8 -> 32, G = 32 -> 8 (see launch)
