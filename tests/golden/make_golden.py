@@ -266,6 +266,19 @@ def ray_cases():
     save("rays", cases)
 
 
+def ray_batch_cases():
+    """utils.ray_utils.get_ray_batch (ray_utils.py:145-174): the generator of (rays_o, rays_d, pixel indices) slices."""
+    c2w = torch.eye(4)
+    c2w[:3, 3] = torch.tensor([0.3, -0.2, 4.0])
+    ro, rd = ray_utils.get_rays(7, 5, 9.5, c2w)
+    ro = ro.contiguous()
+    cases = []
+    for bs in (8, 35, 100):
+        batches = [(o.clone(), d.clone(), i.clone()) for o, d, i in ray_utils.get_ray_batch(ro, rd, batch_size=bs)]
+        cases.append(dict(rays_o=ro, rays_d=rd, batch_size=bs, batches=batches))
+    save("ray_batch", cases)
+
+
 def render_loss_cases():
     """VolumeRenderer.forward followed by NeRFLoss (nerf_mlp.py:165-258) on rgb [+ depth] targets, with the
     autograd gradients back to the per-sample inputs: what nfs_composite_loss_fwd + nfs_composite_bwd fuse."""
@@ -303,4 +316,5 @@ if __name__ == "__main__":
     loss_cases()
     gather_cases()
     ray_cases()
+    ray_batch_cases()
     render_loss_cases()

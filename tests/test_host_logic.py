@@ -85,3 +85,29 @@ def test_two_rank_gloo_sharding_and_allreduce(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_get_ray_batch_matches_reference_fixture(golden):
+    """utils.ray_utils.get_ray_batch (ray_utils.py:145-174) - pure slicing, runs on any device."""
+    from utils.ray_utils import get_ray_batch
+    for c in golden("ray_batch"):
+        got = list(get_ray_batch(c["rays_o"], c["rays_d"], batch_size=c["batch_size"]))
+        assert len(got) == len(c["batches"])
+        for (o, d, i), (ro, rd, ri) in zip(got, c["batches"]):
+            assert torch.equal(o, ro) and torch.equal(d, rd) and torch.equal(i, ri)
+    assert sum(b[0].shape[0] for b in get_ray_batch(torch.zeros(3, 4, 3), torch.zeros(3, 4, 3))) == 12      # default 1024
+
+
+def test_dropin_loss_matches_reference_fixture(golden):
+    """models.nerf_mlp.NeRFLoss (a handful of scalar torch reductions, device-agnostic) against the reference's
+    outputs (nerf_mlp.py:217-258); the fused kernel version is tests/test_gpu_rays.py."""
+    from models.nerf_mlp import NeRFLoss
+    c = golden("loss")
+    full = NeRFLoss()(c["pred"], c["target"])
+    assert set(full) == set(c["full"])
+    for k, v in c["full"].items():
+        assert torch.allclose(full[k], v, rtol=2e-6, atol=0), k
+    only = NeRFLoss(2.0, 0.5, 0.1)({"rgb": c["pred"]["rgb"]}, {"rgb": c["target"]["rgb"]})
+    assert set(only) == set(c["rgb_only"])
+    for k, v in c["rgb_only"].items():
+        assert torch.allclose(only[k], v, rtol=2e-6, atol=0), k
