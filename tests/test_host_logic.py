@@ -111,3 +111,26 @@ def test_dropin_loss_matches_reference_fixture(golden):
     assert set(only) == set(c["rgb_only"])
     for k, v in c["rgb_only"].items():
         assert torch.allclose(only[k], v, rtol=2e-6, atol=0), k
+
+
+def test_module_construction_matches_reference_fixture(golden):
+    """Same parameter names, creation order and seeded initial values as the reference's modules (CPU: construction
+    only - a checkpoint or a seed means the same thing on both sides)."""
+    from models.nerf_mlp import NeRFWithDINO
+    from models.nerf_model import NeRFMLP
+    n = 0
+    for c in golden("mlp"):
+        if c["kind"] != "g3":
+            continue
+        n += 1
+        torch.manual_seed(c["seed"])
+        mod = NeRFWithDINO(**c["kwargs"])
+        assert list(mod.state_dict().keys()) == c["keys"]
+        for k, v in mod.state_dict().items():
+            assert abs(float(v.double().sum()) - c["param_sums"][k]) < 1e-9, k
+    assert n >= 1
+    torch.manual_seed(3)
+    a = NeRFMLP()
+    torch.manual_seed(3)
+    b = O.PlainNeRF()
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
