@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """Benchmark of the NeRF render hot path on B200 (contract: see DESIGN.md "Measurement").
 
-Workload at every N: BASELINE.json configs[1], the volume-render composite micro-bench -
-2^20 rays x 64 samples per GPU, fp32, forward + backward of VolumeRenderer
-(reference: src/models/nerf_mlp.py:165-215).  One "step" = one forward (rgb, depth, weights
-out) + one backward (g_rgb, g_depth in; d_rgb, d_density out) over one batch of synthetic
-Blender-lego-shaped rays.  Rays are independent, so N GPUs each composite their own 2^20 rays
-(weak scaling, no data-path collective).
+Headline workload at every N: BASELINE.json configs[2], the baseline NeRF training step - 4096 rays per GPU from a
+synthetic 800x800 Blender-lego-shaped view, 64 stratified coarse samples + 128 importance samples (192 fine
+evaluations) per ray through nerf_model.NeRFMLP, compositing and rgb MSE on both passes, backward, fused Adam
+(reference: src/training/train.py:188-292).  One "step" = one optimisation step.  Rays shard across GPUs
+(weak scaling: 4096 rays per GPU); the only exchange is the sum of the flat fp32 weight gradient (1.9 MB).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          the CUDA path
-  python bench.py --impl reference ...                          the reference's CPU path (oracle
-                                                                port of it) on the host cores
+  python bench.py --impl reference ...                          the reference's CPU path (oracle port of it:
+                                                                the same ATen op sequence) on the host cores
+`extras` carries BASELINE configs[1] (compositing micro-bench, HBM roofline), configs[3] (DINO-NeRF step) and
+configs[4] (800x800 render), each with its own CPU baseline and clock record.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -29,20 +30,41 @@ for p in (ROOT, PKG):
 
 import torch  # noqa: E402
 
+# ---- headline workload (BASELINE.json configs[2])
+TRAIN_RAYS = 4096
+N_COARSE, N_IMPORTANCE = 64, 128
+EVALS_PER_RAY = N_COARSE + (N_COARSE + N_IMPORTANCE)        # 64 coarse + 192 fine network evaluations
+TRAIN_FLOP_PER_POINT = 2823168.0                            # fwd + dgrad (no layer-0 dgrad) + wgrad of G1
+FWD_FLOP_PER_POINT = 951808.0
+WORKLOAD = "nerf_train_step_4096rays_64c+192f_G1_bf16"
+# ---- cfg 2 (compositing micro-bench)
 N_RAYS = 1 << 20
 N_SAMPLES = 64
-# algorithmic bytes per ray (SURVEY.md section 8d / DESIGN.md K1)
 FWD_BYTES = 24 * N_SAMPLES + 28          # read rgb 12S, density 4S, z 4S, rays_d 12; write rgb 12, depth 4, weights 4S
 BWD_BYTES = 36 * N_SAMPLES + 28          # read 20S + rays_d 12 + g_rgb 12 + g_depth 4; write d_rgb 12S + d_density 4S
-WORKLOAD = "composite_fwd_bwd_1Mrays_x64_fp32"
+
+
+def _peaks_file():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def peaks():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    p = _peaks_file()
+    if "hbm_gbs" in p:
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bf16_peak():
+    """Sustained dense bf16 peak (the step is timed inside a long loop under the power cap)."""
+    p = _peaks_file()
+    if "bf16_tflops_sustained" in p:
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
 
 
 def lego_rays(n_rays, H=800, W=800, seed=0):
@@ -70,7 +92,7 @@ def lego_rays(n_rays, H=800, W=800, seed=0):
 
 
 def make_inputs(n_rays, n_samples, seed, device):
-    """Synthetic lego-shaped batch (SURVEY.md section 8d cfg 2): rgb~U[0,1), density~10*N(0,1),
+    """Synthetic lego-shaped compositing batch (SURVEY.md section 8d cfg 2): rgb~U[0,1), density~10*N(0,1),
     z = one stratified draw in [2,6], unnormalised rays_d from an 800x800 Blender camera."""
     g = torch.Generator().manual_seed(seed)
     _, rays_d = lego_rays(n_rays, seed=seed)
@@ -145,174 +167,416 @@ class ClockSampler:
             out["error"] = self.err
         sm = sorted(s for s, _ in self.samples)
         if sm:
-            out.update(sm_mhz=sm[len(sm) // 2], samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], samples=len(sm))
         out["reasons"] = sorted(self.reasons)
         return out
 
 
-def cpu_reference_rate(n_rays, reps, threads):
-    """The reference's CPU path for this workload (oracle port = the same ATen op sequence as
-    VolumeRenderer.forward + autograd backward) on `threads` host threads; returns rays/s and
-    seconds per pass on an n_rays sample of the bench workload."""
+class Timer:
+    """CUDA-event timing of `fn` under a clock record: keeps the GPU under the same load for `settle` seconds before
+    and `tail` seconds after the timed region so that the 50 ms NVML samples describe it; max over ranks."""
+
+    def __init__(self, dev, rank, dist, local_rank, quick):
+        self.dev, self.rank, self.dist, self.local_rank, self.quick = dev, rank, dist, local_rank, quick
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run(self, fn, steps, warmup, settle=0.3, tail=0.2, clocks=True):
+        """-> (ms per step [max over ranks], clocks dict | None)"""
+        sampler = ClockSampler(self.local_rank) if (clocks and self.rank == 0 and not self.quick) else None
+        t0 = time.perf_counter()
+        while not self.quick and time.perf_counter() - t0 < settle:
+            for _ in range(8):
+                fn()
+            torch.cuda.synchronize()
+        for _ in range(max(warmup, 3)):
+            fn()
+        self.sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        self.sync_all()
+        ms = self.max_over_ranks(a.elapsed_time(b) / steps)
+        if sampler is not None:
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < tail:
+                for _ in range(8):
+                    fn()
+                torch.cuda.synchronize()
+        return ms, (sampler.stop() if sampler is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_train_step_rate(n_rays, reps, threads, warm=1):
+    """The reference's training step on the host cores (oracle port = the same ATen op sequence as
+    NeRFDINOTrainer.render_rays + loss + backward + Adam, train.py:188-292, with the hierarchical pass of
+    ray_utils.py:86-143): stratified sampling -> encoding -> NeRFMLP -> compositing -> inverse-CDF resampling ->
+    encoding -> NeRFMLP -> compositing -> MSE on both passes -> autograd backward -> torch.optim.Adam.
+    A step works on `n_rays` rays x (64 + 192) evaluations; returns (rays/s, seconds per step)."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = O.PlainNeRF()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    bands = O.frequency_bands(10)
+    ro, rd = lego_rays(n_rays, seed=0)
+    target = torch.rand(n_rays, 3)
+
+    def step():
+        opt.zero_grad()
+        pts, z = O.stratified(ro, rd, 2.0, 6.0, N_COARSE, t_rand=torch.rand(n_rays, N_COARSE))
+        raw = model(O.encode(pts.reshape(-1, 3), bands)).reshape(n_rays, N_COARSE, 4)
+        rgb_c, _, w = O.render(raw[..., :3], raw[..., 3:], z, rd)
+        with torch.no_grad():
+            h = O.hierarchical(ro, rd, z, w.detach()[:, :-1], torch.rand(n_rays, N_IMPORTANCE))
+        S = N_COARSE + N_IMPORTANCE
+        raw_f = model(O.encode(h["pts"].reshape(-1, 3), bands)).reshape(n_rays, S, 4)
+        rgb_f, _, _ = O.render(raw_f[..., :3], raw_f[..., 3:], h["z"], rd)
+        loss = torch.mean((rgb_c - target) ** 2) + torch.mean((rgb_f - target) ** 2)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    sec = (time.perf_counter() - t0) / reps
+    return n_rays / sec, sec
+
+
+def cpu_composite_rate(n_rays, reps, threads):
+    """cfg 2 on the host cores: VolumeRenderer.forward + autograd backward (oracle port), rays/s."""
     from oracle import nerf_oracle as O
     torch.set_num_threads(threads)
     d = make_inputs(n_rays, N_SAMPLES, seed=0, device=None)
     rgb, den = d["rgb"].requires_grad_(), d["density"].requires_grad_()
     g_rgb = torch.randn(n_rays, 3) / n_rays
     g_depth = torch.randn(n_rays) / n_rays
-    best, total = float("inf"), 0.0
+    total = 0.0
     for i in range(reps + 1):
         t0 = time.perf_counter()
         o = O.render(rgb, den, d["z"], d["rays_d"])
         torch.autograd.grad([o[0], o[1]], [rgb, den], [g_rgb, g_depth])
-        dt = time.perf_counter() - t0
         if i:                      # first pass warms the allocator / thread pool
-            best = min(best, dt)
-            total += dt
-    return n_rays / (total / reps), total / reps, n_rays / best
+            total += time.perf_counter() - t0
+    return n_rays / (total / reps), total / reps
+
+
+def cpu_render_rate(n_rays, reps, threads):
+    """cfg 5 on the host cores: eval-mode coarse + fine render of n_rays rays (no_grad), rays/s."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = O.PlainNeRF().eval()
+    bands = O.frequency_bands(10)
+    ro, rd = lego_rays(n_rays, seed=7)
+    u = torch.linspace(0.0, 1.0, N_IMPORTANCE)
+    total = 0.0
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            pts, z = O.stratified(ro, rd, 2.0, 6.0, N_COARSE)
+            raw = model(O.encode(pts.reshape(-1, 3), bands)).reshape(n_rays, N_COARSE, 4)
+            _, _, w = O.render(raw[..., :3], raw[..., 3:], z.contiguous(), rd)
+            h = O.hierarchical(ro, rd, z.contiguous(), w[:, :-1], u)
+            raw_f = model(O.encode(h["pts"].reshape(-1, 3), bands)).reshape(n_rays, N_COARSE + N_IMPORTANCE, 4)
+            O.render(raw_f[..., :3], raw_f[..., 3:], h["z"], rd)
+            if i:
+                total += time.perf_counter() - t0
+    return n_rays / (total / reps), total / reps
+
+
+def cpu_dino_rate(n_rays, reps, threads):
+    """cfg 4 on the host cores: stratified samples -> projection + grid_sample feature lookup -> NeRFWithDINO ->
+    compositing -> MSE -> backward -> Adam (oracle port), rays/s."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(1)
+    model = O.ConditionedNeRF(pos_freq=12, dir_freq=4, dino_dim=64)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    ro, rd = lego_rays(n_rays, H=128, W=128, seed=200)
+    tgt = torch.rand(n_rays, 3)
+    fmap = torch.randn(1, 9, 9, 64)
+    pose = torch.eye(4)
+    pose[2, 3] = 4.0
+    focal = 0.5 * 128 / math.tan(0.5 * 0.6911112)
+    total = 0.0
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        pts, z = O.stratified(ro, rd, 2.0, 6.0, 64, t_rand=torch.rand(n_rays, 64))
+        flat = pts.reshape(-1, 3)
+        with torch.no_grad():
+            p2d, _, _ = O.project_points(flat, pose, focal, 128, 128)
+            feats = O.sample_features(fmap, p2d)
+        dirs = rd.unsqueeze(1).expand(-1, 64, -1).reshape(-1, 3)
+        rgb, den = model(flat, dirs, feats)
+        out, _, _ = O.render(rgb.reshape(n_rays, 64, 3), den.reshape(n_rays, 64, 1), z, rd)
+        torch.mean((out - tgt) ** 2).backward()
+        opt.step()
+        if i:
+            total += time.perf_counter() - t0
+    return n_rays / (total / reps), total / reps
 
 
 def run_reference(args):
-    """--impl reference: CPU arm.  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the headline step (oracle port - the reference is a
+    script tree that can neither be pip-installed nor travels to the GPU box).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 1 << 17                                    # 1/8 of the workload per step (~0.3 s on 8 cores)
-    torch.set_num_threads(threads)
-    rate_w, _, _ = cpu_reference_rate(sample, max(1, args.warmup), threads) if args.warmup else (0, 0, 0)
-    rate, sec, best = cpu_reference_rate(sample, max(1, args.steps), threads)
+    sample = 256                                        # 1/16 of the step's rays: 65 536 network evaluations
+    rate, sec = cpu_train_step_rate(sample, max(1, args.steps), threads, warm=max(1, min(args.warmup, 3)))
     line = {
-        "impl": "reference", "metric": "rays/sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "rays/sec (train fwd+bwd)", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays": N_RAYS, "samples": N_SAMPLES,
-                   "note": "each step = a 131072-ray sample of the workload, fwd+autograd bwd, ATen CPU"},
+        "config": {"workload": WORKLOAD, "rays_per_gpu": TRAIN_RAYS, "coarse": N_COARSE, "fine": N_COARSE + N_IMPORTANCE,
+                   "note": "each step = a %d-ray sample of the 4096-ray step (x256 evaluations): sampler, encoding, "
+                           "NeRFMLP, compositing, hierarchical resampling, MSE, autograd backward, Adam; ATen CPU fp32"
+                           % sample},
         "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": "131072 of 1048576 rays x 64 samples per step, fwd + autograd bwd"},
+                         "sample": "%d of 4096 rays x (64 + 192) evaluations per step, %.2f s per step" % (sample, sec)},
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def measure_extras(dev, rank, world, dist, quick):
-    """BASELINE configs 3 and 5 on the same box, same run (reported under "extras"; the headline
-    stays config 2).  cfg 3: one optimisation step of the G1 model, 4096 rays per GPU, 64 coarse +
-    192 fine evaluations per ray, CUDA-graph replay, one NCCL sum-allreduce of the 1.9 MB flat
-    gradient per step when N > 1.  cfg 5: 800x800 render (640 000 rays, 64 + 192 evaluations per ray)
-    split contiguously over the N GPUs.  Times are CUDA events, max over ranks."""
+# ------------------------------------------------------------------------------------------------ GPU arms
+def kernel_breakdown(step_eager, reps=3):
+    """Per-kernel device time of the eagerly launched step (kineto / CUPTI), us per step, largest first."""
+    from torch.profiler import profile, ProfilerActivity
+    for _ in range(2):
+        step_eager()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            step_eager()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", None)
+        if t is None:
+            t = getattr(e, "cuda_time_total", 0)
+        if t > 0:
+            rows.append({"kernel": e.key[:90], "us_per_step": t / reps, "launches_per_step": e.count / reps})
+    rows.sort(key=lambda r: -r["us_per_step"])
+    return rows
+
+
+def bench_train_step(T, world, args):
+    """Headline: the graph-replayed training step.  -> dict of measurements."""
     from models.nerf_model import NeRFMLP
+    from nfs_b200 import _lib, pipeline
     from nfs_b200 import dist as nd
-    from nfs_b200 import pipeline
     from nfs_b200.optim import FusedAdam
+    dev, rank = T.dev, T.rank
     torch.manual_seed(0)
     model = NeRFMLP().to(dev).train()
     opt = FusedAdam(model.parameters(), lr=5e-4)
     bands = 2.0 ** torch.linspace(0.0, 9.0, 10)
-    n = 4096
+    n = TRAIN_RAYS
     ro, rd = lego_rays(n, seed=100 + rank)
-    ro, rd = ro.to(dev), rd.to(dev)
-    target = torch.rand(n, 3, device=dev)
-    allreduce = (lambda g: nd.allreduce_sum_(g)) if world > 1 else None
-    step = pipeline.GraphedTrainStep(model, opt, bands, n, 2.0, 6.0, 64, 128, perturb=True,
-                                     loss_scale=1.0 / world, allreduce=allreduce)
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(100 + rank))
+    allreduce = nd.make_allreduce(opt.grad) if world > 1 else None
+    l0 = _lib.launch_count()
+    step = pipeline.GraphedTrainStep(model, opt, bands, n, 2.0, 6.0, N_COARSE, N_IMPORTANCE, perturb=True,
+                                     loss_scale=1.0 / world, allreduce=allreduce, warmup=3)
+    launches_per_step = (_lib.launch_count() - l0) // 4             # 3 eager warm-up steps + 1 capture
+    step(ro.to(dev), rd.to(dev), target.to(dev))                    # inputs resident in the step's static buffers
+    ms, clk = T.run(step.replay, args.steps, args.warmup, settle=0.5)
+    loss_end = float(step.loss.item())
 
-    def timed(fn, reps, warm):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # end to end through the public call with HOST buffers (pinned): H2D of the step's rays / targets and the D2H
+    # read of its loss are inside the timed region
+    h_ro, h_rd, h_tg = ro.pin_memory(), rd.pin_memory(), target.pin_memory()
+    h_loss = torch.empty(1, pin_memory=True)
 
-    reps = 5 if quick else 30
-    ms = timed(lambda: step(ro, rd, target), reps, 3)
-    flop_ray = 256 * 2823168.0                       # SURVEY.md 8d: 64 + 192 evaluations x train flop per point
-    out = {"train_step_cfg3": {
-        "rays_per_s": world * n / (ms * 1e-3), "ms_per_step": ms, "rays_per_gpu": n,
-        "tflops_per_gpu": n * flop_ray / (ms * 1e-3) / 1e12,
-        "frac_of_bf16_sustained_peak": n * flop_ray / (ms * 1e-3) / 1e12 / bf16_peak(),
-        "allreduce": ("nccl sum of %d fp32 gradients per step, %s" % (
-            opt.flat.numel(), "captured in the step's CUDA graph" if step.allreduce_in_graph else
-            "eager between two graphs")) if world > 1 else "none (1 GPU)",
-        "launch": "CUDA graph replay"}}
-    # cfg 4: DINO-NeRF (experiments/dino_nerf.yaml): NeRFWithDINO, pos_freq 12, 64-d feature map (random values
-    # stand in for the frozen Dinov2 + projection head, which is per-view preprocessing), batch 512 rays x 64
-    # samples, projection + bilinear feature lookup + MLP + compositing, forward + backward + Adam, graph replay
-    try:
-        from models.nerf_mlp import NeRFWithDINO
-        torch.manual_seed(1)
-        g3 = NeRFWithDINO(pos_freq=12, dir_freq=4, dino_dim=64).to(dev).train()
-        opt3 = FusedAdam(g3.parameters(), lr=5e-4)
-        nb = 512
-        ro4, rd4 = lego_rays(nb, H=128, W=128, seed=200 + rank)
-        ro4, rd4 = ro4.to(dev), rd4.to(dev)
-        tgt4 = torch.rand(nb, 3, device=dev)
-        fmap = torch.randn(1, 9, 9, 64, device=dev)
-        pose4 = torch.eye(4, device=dev)
-        pose4[2, 3] = 4.0
-        focal4 = 0.5 * 128 / math.tan(0.5 * 0.6911112)
-        pose4_inv = torch.inverse(pose4)             # per view, outside the captured step
+    def e2e_step():
+        loss = step(h_ro, h_rd, h_tg)
+        h_loss.copy_(loss.reshape(1), non_blocking=True)
 
-        def loss4():
-            o = pipeline.render_rays_conditioned(g3, ro4, rd4, 2.0, 6.0, 64, pose4, focal4, 128, 128, fmap, perturb=True,
-                                                 pose_inv=pose4_inv)
-            return torch.mean((o["rgb"] - tgt4) ** 2)
+    e2e_ms, _ = T.run(e2e_step, max(3, args.steps), 3, settle=0.0, tail=0.0, clocks=False)
+    out = {"ms": ms, "clocks": clk, "e2e_ms": e2e_ms, "h2d": 3 * n * 3 * 4, "d2h": 4, "launches_per_step": int(launches_per_step),
+           "loss": loss_end, "n_params": int(opt.flat.numel()),
+           "allreduce": getattr(allreduce, "describe", "none (1 GPU)") if world > 1 else "none (1 GPU)",
+           "graphs_per_step": 1 if step.g_update is None else 2}
+    if rank == 0 and not args.quick and not args.no_breakdown:
+        try:
+            d_ro, d_rd, d_tg = ro.to(dev), rd.to(dev), target.to(dev)
+            rows = kernel_breakdown(lambda: pipeline.train_step(model, opt, bands, d_ro, d_rd, d_tg, 2.0, 6.0, N_COARSE,
+                                                                N_IMPORTANCE))
+            out["kernels"] = rows[:10]
+            out["kernels_total_us"] = sum(r["us_per_step"] for r in rows)
+        except Exception as e:
+            out["kernels_error"] = repr(e)[:200]
+    out["_keep"] = (model, opt, bands)
+    return out
 
-        step4 = pipeline.GraphedStep(opt3, loss4, loss_scale=1.0 / world, allreduce=allreduce)
-        ms4 = timed(step4.replay, reps, 3)
-        flop4 = 64 * 5.51e6                          # SURVEY.md 8d: ~5.51 MFLOP per point for G3 training
-        out["dino_nerf_cfg4"] = {
-            "rays_per_s": world * nb / (ms4 * 1e-3), "ms_per_step": ms4, "rays_per_gpu": nb, "points_per_step": nb * 64,
-            "tflops_per_gpu": nb * flop4 / (ms4 * 1e-3) / 1e12, "launch": "CUDA graph replay",
-            "note": "batch 512 x 64 samples = 32768 points per step: latency-bound, ~46 kernels per step"}
-    except Exception as e:
-        out["dino_nerf_cfg4"] = {"error": repr(e)[:300]}
-    # render: this rank's contiguous share of the 640 000 rays of one 800 x 800 frame
+
+def bench_composite(T, world, args):
+    """cfg 2: compositing forward + backward of 2^20 rays x 64 samples per GPU through the C ABI (HBM roofline)."""
+    import ctypes
+    from nfs_b200 import _lib
+    from nfs_b200._lib import ptr
+    from models.nerf_mlp import VolumeRenderer
+    dev, rank = T.dev, T.rank
+    d = make_inputs(N_RAYS, N_SAMPLES, seed=rank, device=dev)
+    rgb, den, z, rays_d = d["rgb"], d["density"].reshape(N_RAYS, N_SAMPLES), d["z"], d["rays_d"]
+    out_rgb = torch.empty(N_RAYS, 3, device=dev)
+    out_depth = torch.empty(N_RAYS, device=dev)
+    out_w = torch.empty(N_RAYS, N_SAMPLES, device=dev)
+    d_rgb, d_den = torch.empty_like(rgb), torch.empty_like(den)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def fwd():
+        _lib.call("nfs_composite_fwd", ptr(rgb), ptr(den), ptr(z), ptr(rays_d), None, 0.0, N_RAYS, N_SAMPLES,
+                  0, 0, ptr(out_rgb), ptr(out_depth), ptr(out_w), stream)
+
+    fwd()       # upstream gradients of loss = mse(rgb, target) + 0.1 * mean|depth - d*| at the first forward
+    g_rgb = (2.0 / (3 * N_RAYS)) * (out_rgb - d["target"])
+    g_depth = (0.1 / N_RAYS) * torch.sign(out_depth - d["depth_t"])
+
+    def bwd():
+        _lib.call("nfs_composite_bwd", ptr(rgb), ptr(den), ptr(z), ptr(rays_d), None, 0.0, ptr(g_rgb),
+                  ptr(g_depth), None, N_RAYS, N_SAMPLES, 0, 0, ptr(d_rgb), ptr(d_den), stream)
+
+    steps = 5 if args.quick else 20
+    fwd_ms, _ = T.run(fwd, steps, 3, settle=0.0, tail=0.0, clocks=False)
+    bwd_ms, _ = T.run(bwd, steps, 3, settle=0.0, tail=0.0, clocks=False)
+    both_ms, clk = T.run(lambda: (fwd(), bwd()), steps, 3)
+    peak, peak_src = peaks()
+    res = {"workload": "composite_fwd_bwd_1Mrays_x64_fp32", "rays_per_s": world * N_RAYS / (both_ms * 1e-3),
+           "ms_per_step": both_ms, "clocks": clk,
+           "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                        "fwd": {"ms": fwd_ms, "gbs": FWD_BYTES * N_RAYS / (fwd_ms * 1e-3) / 1e9,
+                                "frac": FWD_BYTES * N_RAYS / (fwd_ms * 1e-3) / 1e9 / peak},
+                        "bwd": {"ms": bwd_ms, "gbs": BWD_BYTES * N_RAYS / (bwd_ms * 1e-3) / 1e9,
+                                "frac": BWD_BYTES * N_RAYS / (bwd_ms * 1e-3) / 1e9 / peak},
+                        "step_gbs": (FWD_BYTES + BWD_BYTES) * N_RAYS / (both_ms * 1e-3) / 1e9,
+                        "step_frac": (FWD_BYTES + BWD_BYTES) * N_RAYS / (both_ms * 1e-3) / 1e9 / peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            res["roofline"]["traffic"] = json.load(open(traffic_file))
+        except Exception:
+            pass
+    if not args.quick:
+        # end to end through VolumeRenderer + autograd with pinned host buffers.  The D2H leg returns the
+        # renderings and the loss (16.8 MB); the 1.07 GB of input gradients stay on the device, as they would
+        # for the MLP that consumes them.
+        vr = VolumeRenderer().eval()
+        host = {k: d[k].cpu().pin_memory() for k in ("rgb", "density", "z", "rays_d", "target", "depth_t")}
+        h_out = torch.empty(N_RAYS, 4, pin_memory=True)
+        h_loss = torch.empty(1, pin_memory=True)
+
+        def e2e_step():
+            r = host["rgb"].to(dev, non_blocking=True).requires_grad_()
+            s = host["density"].to(dev, non_blocking=True).requires_grad_()
+            zz = host["z"].to(dev, non_blocking=True)
+            dd = host["rays_d"].to(dev, non_blocking=True)
+            tg = host["target"].to(dev, non_blocking=True)
+            dt = host["depth_t"].to(dev, non_blocking=True)
+            o_rgb, o_depth, _ = vr(r, s, zz, dd)
+            loss = ((o_rgb - tg) ** 2).mean() + 0.1 * (o_depth - dt).abs().mean()
+            loss.backward()
+            h_out[:, :3].copy_(o_rgb.detach(), non_blocking=True)
+            h_out[:, 3].copy_(o_depth.detach(), non_blocking=True)
+            h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        e_ms, _ = T.run(e2e_step, 5, 3, settle=0.0, tail=0.0, clocks=False)
+        res["e2e"] = {"value": world * N_RAYS / (e_ms * 1e-3), "unit": "rays/s",
+                      "h2d_bytes_per_step": sum(host[k].numel() * 4 for k in host), "d2h_bytes_per_step": h_out.numel() * 4 + 4,
+                      "note": "gradients (1.07 GB) stay on the device"}
+    return res
+
+
+def bench_dino(T, world, args):
+    """cfg 4: DINO-NeRF (experiments/dino_nerf.yaml): NeRFWithDINO, pos_freq 12, 64-d feature map (random values
+    stand in for the frozen Dinov2 + projection head, which is per-view preprocessing), batch 512 rays x 64
+    samples: projection + bilinear feature lookup + MLP + compositing, forward + backward + Adam, graph replay."""
+    from models.nerf_mlp import NeRFWithDINO
+    from nfs_b200 import dist as nd
+    from nfs_b200 import pipeline
+    from nfs_b200.optim import FusedAdam
+    dev, rank = T.dev, T.rank
+    torch.manual_seed(1)
+    g3 = NeRFWithDINO(pos_freq=12, dir_freq=4, dino_dim=64).to(dev).train()
+    opt3 = FusedAdam(g3.parameters(), lr=5e-4)
+    nb = 512
+    ro4, rd4 = lego_rays(nb, H=128, W=128, seed=200 + rank)
+    ro4, rd4 = ro4.to(dev), rd4.to(dev)
+    tgt4 = torch.rand(nb, 3, device=dev)
+    fmap = torch.randn(1, 9, 9, 64, device=dev)
+    pose4 = torch.eye(4, device=dev)
+    pose4[2, 3] = 4.0
+    focal4 = 0.5 * 128 / math.tan(0.5 * 0.6911112)
+    pose4_inv = torch.inverse(pose4)             # per view, outside the captured step
+
+    def loss4():
+        o = pipeline.render_rays_conditioned(g3, ro4, rd4, 2.0, 6.0, 64, pose4, focal4, 128, 128, fmap, perturb=True,
+                                             pose_inv=pose4_inv)
+        return torch.mean((o["rgb"] - tgt4) ** 2)
+
+    allreduce = nd.make_allreduce(opt3.grad) if world > 1 else None
+    step4 = pipeline.GraphedStep(opt3, loss4, loss_scale=1.0 / world, allreduce=allreduce)
+    ms4, clk = T.run(step4.replay, 5 if args.quick else 30, 3)
+    flop4 = 64 * 5.51e6                          # SURVEY.md 8d: ~5.51 MFLOP per point for G3 training
+    peak, _ = bf16_peak()
+    return {"workload": "dino_nerf_step_512rays_x64_G3", "rays_per_s": world * nb / (ms4 * 1e-3), "ms_per_step": ms4,
+            "rays_per_gpu": nb, "points_per_step": nb * 64, "tflops_per_gpu": nb * flop4 / (ms4 * 1e-3) / 1e12,
+            "frac_of_bf16_sustained_peak": nb * flop4 / (ms4 * 1e-3) / 1e12 / peak, "launch": "CUDA graph replay",
+            "clocks": clk}
+
+
+def bench_render(T, world, args, model, bands):
+    """cfg 5: one 800x800 frame (640 000 rays, 64 + 192 evaluations per ray, eval mode) split contiguously over the GPUs
+    (strong scaling)."""
+    from nfs_b200 import dist as nd
+    from nfs_b200 import pipeline
+    dev, rank = T.dev, T.rank
     total = 640000
     lo, hi = nd.shard_range(total, rank, world)
     ro2, rd2 = lego_rays(hi - lo, seed=7)
     ro2, rd2 = ro2.to(dev), rd2.to(dev)
     model.eval()
-    ms = timed(lambda: pipeline.render_image(model, bands, ro2, rd2, 2.0, 6.0, 64, 128, chunk=65536),
-               1 if quick else 3, 1)
-    fwd_flop_ray = 256 * 951808.0
-    out["render_cfg5"] = {
-        "rays_per_s": total / (ms * 1e-3), "ms_per_frame": ms, "rays_per_gpu": hi - lo,
-        "tflops_per_gpu": (hi - lo) * fwd_flop_ray / (ms * 1e-3) / 1e12,
-        "frac_of_bf16_sustained_peak": (hi - lo) * fwd_flop_ray / (ms * 1e-3) / 1e12 / bf16_peak()}
-    return out
-
-
-def bf16_peak():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["bf16_tflops_sustained"])
-    except Exception:
-        return 1415.0
+    ms, clk = T.run(lambda: pipeline.render_image(model, bands, ro2, rd2, 2.0, 6.0, N_COARSE, N_IMPORTANCE, chunk=65536),
+                    1 if args.quick else 3, 1, settle=0.0 if args.quick else 0.3)
+    model.train()
+    peak, _ = bf16_peak()
+    tf = (hi - lo) * EVALS_PER_RAY * FWD_FLOP_PER_POINT / (ms * 1e-3) / 1e12
+    return {"workload": "render_800x800_64c+192f_G1", "rays_per_s": total / (ms * 1e-3), "ms_per_frame": ms,
+            "rays_per_gpu": hi - lo, "scaling": "strong", "tflops_per_gpu": tf, "frac_of_bf16_sustained_peak": tf / peak,
+            "clocks": clk}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the cfg 3 / cfg 5 measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg 2 / cfg 4 / cfg 5 measurements")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel (kineto) breakdown of the step")
     ap.add_argument("--quick", action="store_true",
-                    help="profiling aid (ncu): no clock-settle loop, no e2e leg, no CPU baseline")
+                    help="profiling aid (ncu): no clock-settle loops, no e2e leg, no CPU baselines, no breakdown")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -329,163 +593,85 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    T = Timer(dev, rank, dist, local_rank, args.quick)
 
-    from nfs_b200 import _lib, ops
-    from nfs_b200._lib import ptr
-    from models.nerf_mlp import VolumeRenderer
-    import ctypes
-
-    steps, warmup = args.steps, max(args.warmup, 3)
-    d = make_inputs(N_RAYS, N_SAMPLES, seed=rank, device=dev)
-    rgb, den, z, rays_d = d["rgb"], d["density"].reshape(N_RAYS, N_SAMPLES), d["z"], d["rays_d"]
-    out_rgb = torch.empty(N_RAYS, 3, device=dev)
-    out_depth = torch.empty(N_RAYS, device=dev)
-    out_w = torch.empty(N_RAYS, N_SAMPLES, device=dev)
-    d_rgb, d_den = torch.empty_like(rgb), torch.empty_like(den)
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-    def fwd():
-        _lib.call("nfs_composite_fwd", ptr(rgb), ptr(den), ptr(z), ptr(rays_d), None, 0.0, N_RAYS, N_SAMPLES,
-                  0, 0, ptr(out_rgb), ptr(out_depth), ptr(out_w), stream)
-
-    # upstream gradients of loss = mse(rgb, target) + 0.1 * mean|depth - d*| at the first forward
-    fwd()
-    g_rgb = (2.0 / (3 * N_RAYS)) * (out_rgb - d["target"])
-    g_depth = (0.1 / N_RAYS) * torch.sign(out_depth - d["depth_t"])
-
-    def bwd():
-        _lib.call("nfs_composite_bwd", ptr(rgb), ptr(den), ptr(z), ptr(rays_d), None, 0.0, ptr(g_rgb),
-                  ptr(g_depth), None, N_RAYS, N_SAMPLES, 0, 0, ptr(d_rgb), ptr(d_den), stream)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # clock record: NVML samples every 50 ms, so keep the GPU under the same load for ~0.3 s before and
-    # ~0.2 s after the (much shorter) timed region; the samples cover settle + timed region + tail.
-    clocks = ClockSampler(local_rank) if rank == 0 and not args.quick else None
-    t_settle = time.perf_counter()
-    while not args.quick and time.perf_counter() - t_settle < 0.3:
-        for _ in range(50):
-            fwd(); bwd()
-        torch.cuda.synchronize()
-    for _ in range(warmup):
-        fwd(); bwd()
-    sync_all()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    launches0 = _lib.launch_count()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # inputs (1.34 GB) + outputs (1.35 GB) per step far exceed the 126 MB L2: no flush needed
-    start.record()
-    for i in range(steps):
-        ev[i][0].record(); fwd(); ev[i][1].record(); bwd(); ev[i][2].record()
-    stop.record()
-    sync_all()
-    launches = _lib.launch_count() - launches0
-    elapsed_ms = start.elapsed_time(stop)
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    if clocks is not None:          # a few more samples under identical load, then stop
-        t_settle = time.perf_counter()
-        while time.perf_counter() - t_settle < 0.2:
-            for _ in range(50):
-                fwd(); bwd()
-            torch.cuda.synchronize()
-    clk = clocks.stop() if clocks is not None else None
-    value = world * N_RAYS * steps / (elapsed_ms * 1e-3)
-
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
-    vr = VolumeRenderer().eval()
-    host = {k: d[k].cpu().pin_memory() for k in ("rgb", "density", "z", "rays_d", "target", "depth_t")}
-    h_out = torch.empty(N_RAYS, 4, pin_memory=True)
-    h_loss = torch.empty(1, pin_memory=True)
-
-    def e2e_step():
-        r = host["rgb"].to(dev, non_blocking=True).requires_grad_()
-        s = host["density"].to(dev, non_blocking=True).requires_grad_()
-        zz = host["z"].to(dev, non_blocking=True)
-        dd = host["rays_d"].to(dev, non_blocking=True)
-        tg = host["target"].to(dev, non_blocking=True)
-        dt = host["depth_t"].to(dev, non_blocking=True)
-        o_rgb, o_depth, _ = vr(r, s, zz, dd)
-        loss = ((o_rgb - tg) ** 2).mean() + 0.1 * (o_depth - dt).abs().mean()
-        loss.backward()
-        h_out[:, :3].copy_(o_rgb.detach(), non_blocking=True)
-        h_out[:, 3].copy_(o_depth.detach(), non_blocking=True)
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-        return r.grad, s.grad
-
-    e2e_steps = 1 if args.quick else max(3, min(steps, 10))
-    for _ in range(0 if args.quick else 3):
-        e2e_step()
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_RAYS * e2e_steps / (float(t.item()) * 1e-3)
-    h2d = sum(host[k].numel() * 4 for k in host)
-    d2h = h_out.numel() * 4 + 4
-
+    tr = bench_train_step(T, world, args)
+    model, opt, bands = tr.pop("_keep")
     extras = None
     if not args.no_extras:
-        try:
-            extras = measure_extras(dev, rank, world, dist, args.quick)
-        except Exception as e:                      # the headline line must survive a failure of the extras
-            extras = {"error": repr(e)[:300]}
+        extras = {}
+        for name, fn in (("composite_cfg2", lambda: bench_composite(T, world, args)),
+                         ("dino_nerf_cfg4", lambda: bench_dino(T, world, args)),
+                         ("render_cfg5", lambda: bench_render(T, world, args, model, bands))):
+            try:
+                extras[name] = fn()
+            except Exception as e:                  # the headline line must survive a failure of an extra
+                extras[name] = {"error": repr(e)[:300]}
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    dom_ms, dom_bytes, dom = (bwd_ms, BWD_BYTES, "composite_bwd_staged_kernel") if bwd_ms >= fwd_ms else \
-        (fwd_ms, FWD_BYTES, "composite_fwd_kernel")
-    achieved = dom_bytes * N_RAYS / (dom_ms * 1e-3) / 1e9
+    ms = tr["ms"]
+    peak, peak_src = bf16_peak()
+    flops_step = TRAIN_RAYS * EVALS_PER_RAY * TRAIN_FLOP_PER_POINT          # per GPU
+    achieved = flops_step / (ms * 1e-3) / 1e12
+    burst = _peaks_file().get("bf16_tflops")
     line = {
-        "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "samples": N_SAMPLES,
-                   "l2": "inputs+outputs 2.7 GB per step >> 126 MB L2, no flush needed",
-                   "upstream_grads": "d/d(rgb,depth) of mse(rgb,target)+0.1*mean|depth-d*|"},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_launch": dom_bytes * N_RAYS, "ms_per_launch": dom_ms,
-                     "fwd": {"ms": fwd_ms, "gbs": FWD_BYTES * N_RAYS / (fwd_ms * 1e-3) / 1e9},
-                     "bwd": {"ms": bwd_ms, "gbs": BWD_BYTES * N_RAYS / (bwd_ms * 1e-3) / 1e9},
-                     "step_gbs": (FWD_BYTES + BWD_BYTES) * N_RAYS * steps / (elapsed_ms * 1e-3) / 1e9},
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "models.nerf_mlp.VolumeRenderer + autograd, pinned host buffers"},
-        "gpu_launches": int(launches),
-        "clocks": clk,
-        "extras": extras,
+        "metric": "rays/sec (train fwd+bwd)", "value": world * TRAIN_RAYS / (ms * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": TRAIN_RAYS, "coarse": N_COARSE, "fine": N_COARSE + N_IMPORTANCE,
+                   "model": "nerf_model.NeRFMLP 63->256x8->4 (random init), fp32 masters, bf16 operands, fp32 accumulate",
+                   "step": "sampler + encoding + MLP + compositing, coarse and fine, MSE on both, backward, fused Adam; "
+                           "one CUDA graph replay per step",
+                   "l2": "the step's working set (6.6 GB of saved activations / gradients of 1 048 576 points) >> 126 MB "
+                         "L2, no flush needed",
+                   "gradient_exchange": tr["allreduce"], "graphs_per_step": tr["graphs_per_step"],
+                   "n_params": tr["n_params"], "loss_after_run": tr["loss"]},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "flop_per_step": flops_step, "flop_per_point": TRAIN_FLOP_PER_POINT,
+                     "points_per_step": TRAIN_RAYS * EVALS_PER_RAY,
+                     "frac_of_burst_peak": (achieved / float(burst)) if burst else None,
+                     "scope": "whole step (all kernels of one graph replay) against the algorithmic MLP flops; "
+                              "per-kernel times under `kernels`"},
+        "e2e": {"value": world * TRAIN_RAYS / (tr["e2e_ms"] * 1e-3), "unit": "rays/s", "ms_per_step": tr["e2e_ms"],
+                "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
+                "api": "nfs_b200.pipeline.GraphedTrainStep.__call__(rays_o, rays_d, target) with pinned host tensors; "
+                       "the loss is read back to pinned host memory every step"},
+        "gpu_launches": tr["launches_per_step"] * args.steps,
+        "launches_per_step": tr["launches_per_step"],
+        "clocks": tr["clocks"],
     }
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if "kernels" in tr:
+        line["kernels"] = tr["kernels"]
+        line["kernels_total_us"] = tr["kernels_total_us"]
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_step.json")
     if os.path.exists(traffic_file):
         try:
-            line["roofline"]["traffic"] = json.load(open(traffic_file)).get(dom)
+            line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_step")
         except Exception:
             pass
     if not args.no_cpu_baseline and not args.quick:
         threads = os.cpu_count() or 1
-        sample = 1 << 17
-        rate, sec, best = cpu_reference_rate(sample, 8, threads)
+        rate, sec = cpu_train_step_rate(256, 8, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": "8 passes over 131072 of the 1048576 rays x 64 samples, fwd + autograd "
-                                          "bwd, %.2f s per pass" % sec}
+                                "sample": "8 steps over 256 of the 4096 rays x (64 + 192) evaluations, %.2f s per step" % sec}
+        if extras is not None:
+            for name, fn, sample in (("composite_cfg2", lambda: cpu_composite_rate(1 << 17, 4, threads), "4 passes over 131072 of 1048576 rays x 64, fwd + autograd bwd"),
+                                     ("dino_nerf_cfg4", lambda: cpu_dino_rate(128, 3, threads), "3 steps over 128 of 512 rays x 64 samples"),
+                                     ("render_cfg5", lambda: cpu_render_rate(1024, 2, threads), "2 passes over 1024 of 640000 rays x (64 + 192)")):
+                if isinstance(extras.get(name), dict) and "error" not in extras[name]:
+                    try:
+                        r, s = fn()
+                        extras[name]["cpu_baseline"] = {"value": r, "unit": "rays/s", "cores": threads, "kind": "port",
+                                                        "sample": sample + ", %.2f s each" % s}
+                    except Exception as e:
+                        extras[name]["cpu_baseline"] = {"error": repr(e)[:200]}
+    line["extras"] = extras
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

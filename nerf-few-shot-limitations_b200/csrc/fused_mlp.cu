@@ -1,610 +1,16 @@
-// K3 (fused multi-layer MLP, forward and dgrad) — a whole chain of dense layers per launch, activations
-// kept in shared memory / TMEM, weights streamed by TMA, every layer on tcgen05 tensor cores.
-//
-// Replaces the Linear(+ReLU) chain + heads of
-//   nerf_model.NeRFMLP.forward    /root/reference/src/models/nerf_model.py:16-24
-// (and any sub-chain of nerf_mlp.NeRFWithDINO, nerf_mlp.py:134-158) for 256 points per CTA step.
-//
-// Persistent CTA PAIRS (thread-block clusters of 2 = two SMs, tcgen05 cta_group::2): each CTA keeps two
-// 128-point tiles (A, B) in flight, so a pair works on four tiles.
-//   * act[A], act[B]  : 2 x 64 KB shared memory per CTA, the bf16 activations of the current layer in
-//                       the canonical K-major SWIZZLE_128B operand layout (4 slabs of [128 x 64]);
-//                       the epilogue overwrites them IN PLACE with the next layer's input;
-//   * weight ring     : 6 x 16 KB stages per CTA.  One tcgen05.mma.cta_group::2 multiplies the pair's
-//                       256 points (128 from each CTA) by all N output columns, and each CTA supplies
-//                       HALF of the weight rows: a stage is [N/2 x 64], a whole layer is 4 stages, so
-//                       the layer's weights stay resident while tile A and then tile B use them and
-//                       the next layer's first stages are prefetched.  Per-SM shared-memory traffic per
-//                       MMA drops from 12 KB to 8 KB and the MMA runs at its 128-cycle floor
-//                       (scripts/ubench/mma_2cta.cu; the single-CTA form is smem-bound at 161 cycles);
-//   * TMEM            : two 128 x 256 fp32 accumulators (512 columns) per CTA, one per tile.
-// The leader CTA's MMA thread runs tile-major - 16 MMAs on the pair's A tiles, 16 on the B tiles - so
-// A's accumulator completes half a layer (2048 cycles) before B's: A's epilogue (tcgen05.ld -> +bias ->
-// ReLU -> bf16 -> swizzled st.shared) overlaps B's MMAs and B's epilogue overlaps A's MMAs of the next
-// layer.  Barriers that gate the MMA thread (weights landed, tile ready, accumulator drained) live in
-// the leader CTA and count both CTAs (TMA .cta_group::2 completion, remote mbarrier arrives); barriers
-// the MMA thread signals (accumulator full, weight stage free) are multicast to both CTAs by
-// tcgen05.commit.
-// Three instantiations: inference forward (optionally computing the positional encoding of the points
-// in-kernel, K2 fused in), the forward of a training step (each epilogue warp TMA-stores the 32-row x
-// 64-column boxes it has just written, for wgrad, and writes one ReLU sign bit per activation, for the
-// backward), and the dgrad chain (ReLU backward from those sign bits).
-// The last layer of a forward chain is a narrow head (N = 64 padded) whose first `out_cols` columns are
-// written as fp32 with the reference's output activation.
-// Warp roles per CTA: 0 = TMA producer, 1 = TMEM owner (+ MMA issuer in the leader), 2..17 = epilogue
-// (four warps per TMEM lane quadrant, each draining a quarter of the columns of tile A, then of tile B).
-#include "tc_common.cuh"
+// K3 (fused multi-layer MLP, forward and dgrad): kernel instantiations + C ABI.  The kernel body lives in
+// fused_mlp_body.cuh (it is also the producer half of the merged backward kernel, backward.cu).
+#include "fused_mlp_body.cuh"
 
 namespace nfs {
 namespace {
 
-using namespace tc;
-
-constexpr int kFmThreads = 576;   // 18 warps
-constexpr int kFmMaxLayers = 12;
-constexpr int kActBytes = 128 * 256 * 2;
-constexpr int kActSlab = 128 * 128;
-constexpr int kWStage = 128 * 128;   // one weight stage: this CTA's half of the rows, [<= 128 x 64] bf16
-constexpr int kWStages = 6;
-
-struct FusedArgs {
-  long long P;
-  long long save_rows;                 // rows per layer in the saved-activation tensor (P rounded up to 128)
-  int n_layers;
-  int K[kFmMaxLayers], N[kFmMaxLayers], act[kFmMaxLayers], row0[kFmMaxLayers];
-  int has_bias;                        // the biases arrive as a tensor-core operand (tmap_b), see below
-  int x_save;                          // in-kernel encoding of a training forward: tmap_x stores the encoded operand
-  float *out;                          // [P, out_cols] fp32
-  int out_cols;
-  int save;
-  int head;                            // 1: last layer is the fp32 output head; 0: it is a regular (saved) layer
-  // ReLU sign bits, 256 per row = 8 words [layer][row][8]; in word w bit j (j < 16) is column 32w + 2j, bit 16 + j is
-  // column 32w + 2j + 1 (the two halves of packed pair j), so (word >> j) & 0x10001 times 0x3F80 is the pair's
-  // bf16x2 {1.0 | 0.0} multiplier.  bits_out: written by layers with act 1 (the forward chain of a training step);
-  // bits_in: read by layers with act 4 (the dgrad chain): result *= bit(mask_idx[l], row, col).
-  uint32_t *bits_out;
-  const uint32_t *bits_in;
-  long long bits_rows;                 // rows per layer of bits_in
-  int mask_idx[kFmMaxLayers];
-  const float *points;                 // in-kernel encoding mode: [P,3] fp32 sample positions (x_bf16 unused) | NULL
-  float freq0;                         // first frequency band; band k = freq0 * 2^k
-  int n_octaves;                       // number of bands (3 * (2 * n_octaves + 1) <= 64)
-  int dbg;                             // developer bisection switches (nfs_set_debug_flags), 0 in production
-  unsigned long long *trace;           // developer timeline of CTA 0 (nfs_set_debug_trace), NULL in production
-};
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c_inner, int c_outer) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(map), "r"(smem_u32(src)), "r"(c_inner), "r"(c_outer)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// ---- CTA-pair plumbing
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the pair
-__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// Barriers signalled from the peer CTA / by multicast commits are waited on with the default
-// (.acquire.cta) try_wait like every other barrier: a cluster-scope acquire costs ~400 cycles per wait
-// (measured with the timeline tracer) and the data these barriers guard is read through the async
-// proxy (UMMA operands, TMEM), which the arriving side orders with fence.proxy.async / tcgen05 fences.
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
-// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset): both CTAs of the
-// pair fill their own shared memory, one barrier in the leader counts all the bytes.
-__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// all prior MMAs of this thread -> one arrive on `bar` (same offset) in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
-// one lane of the (converged) warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ float fm_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// bf16x2 pack with the ReLU folded into the conversion
-__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// ReLU backward on packed pair j of a 32-column word of sign bits (layout above)
-__device__ __forceinline__ uint32_t relu_bits_bf16x2(uint32_t v, uint32_t word, int j) {
-  const uint32_t m = ((word >> j) & 0x00010001u) * 0x3F80u;     // bf16x2 {1.0 | 0.0, 1.0 | 0.0}
-  uint32_t r;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(m));
-  return r;
-}
-// sign bits of a post-ReLU packed pair (both halves are non-negative bf16: adding 0x7FFF carries into bit 15 / 31
-// exactly when the half is non-zero), placed at bit j and bit 16 + j
-__device__ __forceinline__ uint32_t relu_bits_of(uint32_t pk, int j) {
-  return (((pk + 0x7FFF7FFFu) >> 15) & 0x00010001u) << j;
-}
-
-// TMEM -> registers, 16 consecutive fp32 columns of this thread's lane, WITHOUT waiting: the
-// registers are valid after the next tmem_ld_wait().  Lets the load of chunk i+1 fly while chunk i
-// is being processed.
-__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// One epilogue chunk: 16 accumulator columns of one row (the bias is already in the accumulator, see the bias
-// MMA) -> ReLU | ReLU-backward mask | none
-// -> bf16 -> two 16-byte chunks of the row in the SWIZZLE_128B operand layout.
-template <bool kMasked, bool kTrain>
-__device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], int act, uint32_t bits_word, int j0,
-                                          uint32_t &bits_acc, uint8_t *srow, int ch, int r7, int dbg) {
-  uint32_t pk[8];
-  if (act == 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-  }
-  if (kMasked && act == 4) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = relu_bits_bf16x2(pk[j], bits_word, j0 + j);
-  }
-  if (kTrain && act == 1) {              // sign bits for the backward pass
-#pragma unroll
-    for (int j = 0; j < 8; ++j) bits_acc |= relu_bits_of(pk[j], j0 + j);
-  }
-  if (dbg & 32) {                       // bisection: keep the values alive without the shared-memory stores
-    uint32_t x = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x ^= pk[j];
-    if (x == 0x9e3779b9u) *reinterpret_cast<uint32_t *>(srow) = x;
-    return;
-  }
-  *reinterpret_cast<uint4 *>(srow + ((ch ^ r7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4 *>(srow + (((ch + 1) ^ r7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-}
-
-// Developer tools (bisection switches + timeline) are compiled in only with -DNFS_DEVTOOLS
-// (NFS_DEVTOOLS=1 python -m nfs_b200.build): they cost registers in a kernel that is short of them.
-#ifndef NFS_DEVTOOLS
-#define NFS_TRACE(code, l, t) do { } while (0)
-#define NFS_DBG(a) 0
-#else
-#define NFS_DBG(a) ((a).dbg)
-// Developer timeline: CTA 0 appends (clock << 16 | code << 12 | layer << 4 | tile) per warp.
-#define NFS_TRACE(code, l, t)                                                                       \
-  do {                                                                                              \
-    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 1023) {                     \
-      a.trace[warp * 1024 + 1 + trace_n++] =                                                        \
-          ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 12) | ((l) << 4) | (t); \
-      a.trace[warp * 1024] = trace_n;                                                               \
-    }                                                                                               \
-  } while (0)
-#endif
-
-// kMasked: dgrad chain (ReLU backward from sign bits).  kTrain: forward chain of a training step (saves activations
-// and sign bits).  Neither: inference forward (optionally with the positional encoding computed in-kernel).
 template <bool kMasked, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFmThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_save, const __grid_constant__ CUtensorMap tmap_b,
                  const FusedArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = smem_raw;                      // SWIZZLE_128B operands need 1024-byte alignment (checked below)
-  uint8_t *act[2] = {smem, smem + kActBytes};
-  uint8_t *wring = smem + 2 * kActBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(wring + kWStages * kWStage);
-  uint64_t *w_full = bars, *w_empty = bars + kWStages;
-  uint64_t *in_full = bars + 2 * kWStages;       // [2] input operand of the chain landed (TMA)
-  uint64_t *act_free = in_full + 2;              // [2] last layer's MMAs have read act[t]
-  uint64_t *act_ready = act_free + 2;            // [2] epilogue wrote next layer's operand into act[t]
-  uint64_t *acc_full = act_ready + 2;            // [2] accumulator of tile t complete
-  uint64_t *head_done = acc_full + 2;            // [2] this CTA's epilogue is done with act[t] / accumulator t (producer)
-  uint64_t *acc_free = head_done + 2;            // [2] leader: both CTAs' epilogues drained accumulator t (MMA thread)
-  uint64_t *in_ready = acc_free + 2;             // [2] leader: both CTAs' encoding warps wrote the chain input of tile t
-  uint64_t *bias_full = in_ready + 2;            // [1] leader: both CTAs' bias operands of the current layer landed (TMA)
-  uint64_t *bias_empty = bias_full + 1;          // [1] both bias MMAs of the layer have read the operand (commit, multicast)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_empty + 1);
-  // The bias enters the accumulator through the tensor core: one extra K = 16 MMA per tile and layer multiplies a
-  // constant "ones" operand (rows of [1,1,1,0,...]) by the layer's bias operand (row n = [hi, mid, lo, 0, ...], the
-  // fp32 bias split into three bf16 terms, exact to ~2^-24).  Both are un-swizzled K-major core matrices; every 8-row
-  // group of the ones operand aliases the same 128 bytes (SBO = 0) and the bias operand's second K core matrix
-  // aliases its first (LBO = 0: it only meets the zero half of the ones rows).  This takes 16 shared-memory loads and
-  // 32 adds per thread and tile out of the epilogue, which is the critical path (scripts/ubench/mma_2cta.cu).
-  uint8_t *s_ones = reinterpret_cast<uint8_t *>(bars + 32);          // 256 B
-  uint8_t *s_bias = s_ones + 256;                                    // [N/2 <= 128 rows x 16 B] of this CTA
-
-  // warp index through a shuffle: the compiler then treats it (and every branch on it) as warp-uniform and
-  // keeps the MMA / TMA operands in uniform registers instead of R2UR "waterfall" loops per instruction
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  unsigned trace_n = 0;
-  (void)trace_n;
-  const int L = a.n_layers;
-  const long long n_tiles = (a.P + 127) / 128;
-  const long long n_quads = (n_tiles + 3) / 4;          // a CTA pair works on 4 tiles: tile = 4*quad + 2*rank + t
-  const uint32_t rank = cluster_ctarank();
-  const long long quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) { printf("nfs_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(in_full + t, 1); mbar_init(act_free + t, 1); mbar_init(act_ready + t, 32);
-      mbar_init(acc_full + t, 1); mbar_init(head_done + t, 16); mbar_init(acc_free + t, 32);
-      mbar_init(in_ready + t, 8);
-    }
-    mbar_init(bias_full, 1); mbar_init(bias_empty, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tmap_x);
-    tma_prefetch_desc(&tmap_w);
-    if (a.save) tma_prefetch_desc(&tmap_save);
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 80) {      // the "ones" operand: core matrix 0 = rows of [1,1,1,0,...], core matrix 1 = 0
-    const int i = threadIdx.x - 64;
-    const uint32_t one2 = 0x3F803F80u, one1 = 0x00003F80u;           // bf16 {1,1}, {1,0}
-    *reinterpret_cast<uint4 *>(s_ones + i * 16) = i < 8 ? make_uint4(one2, one1, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    fence_proxy_async();
-  }
-  if (warp == 1) {                                 // the pair allocates together: warp 1 of both CTAs
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                              // both CTAs' barriers are initialised before anyone signals them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t wit = 0, iter = 0;
-      const int ks0 = a.K[0] >> 6;
-      for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
-        for (int t = 0; t < 2 && a.points == nullptr; ++t) {
-          mbar_wait_relaxed(act_free + t, (iter & 1) ^ 1);
-          mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);
-          if (rank == 0) mbar_expect_tx(in_full + t, (uint32_t)(2 * ks0 * kActSlab));     // both CTAs' tiles
-          for (int s = 0; s < ks0; ++s)
-            tma_load_2d_pair(act[t] + s * kActSlab, &tmap_x, in_full + t, s * 64, (int)((4 * quad + 2 * rank + t) * 128));
-        }
-        for (int l = 0; l < L; ++l) {
-          const int ks = a.K[l] >> 6, nh = a.N[l] >> 1;           // this CTA's half of the output rows
-          const int nb = (nh + 63) >> 6;                          // 64-row TMA boxes (a 32-row half loads a full box)
-          for (int s = 0; s < ks; ++s, ++wit) {
-            const uint32_t stage = wit % kWStages, ph = (wit / kWStages) & 1;
-            if ((NFS_DBG(a) & 2) && wit >= kWStages) continue;
-            mbar_wait_relaxed(w_empty + stage, ph ^ 1);
-            if (rank == 0) mbar_expect_tx(w_full + stage, (uint32_t)(2 * nb * 8192));
-            for (int b = 0; b < nb; ++b)
-              tma_load_2d_pair(wring + stage * kWStage + b * 8192, &tmap_w, w_full + stage, s * 64,
-                               a.row0[l] + (int)rank * nh + b * 64);
-            // The bias operand (single buffer) is released when the previous layer's B pass STARTS (its bias MMA
-            // is issued first), about when that layer's first weight stages come free: loading it here, between
-            // the weight stages, keeps the weight prefetch running ahead.
-            if (s == (ks > 1 ? 1 : 0) && a.has_bias && !(NFS_DBG(a) & 8)) {
-              const uint32_t gl = iter * (uint32_t)L + (uint32_t)l;
-              mbar_wait_relaxed(bias_empty, (gl & 1) ^ 1);
-              if (rank == 0) mbar_expect_tx(bias_full, 2u * 2048u);
-              tma_load_2d_pair(s_bias, &tmap_b, bias_full, 0, a.row0[l] + (int)rank * nh);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0) {                 // all 32 lanes walk the (warp-uniform) schedule; one elected lane issues
-      uint32_t wit = 0, iter = 0, n_ready[2] = {0, 0};
-      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(wring), 16, 1024);
-      const bool no_mma = (NFS_DBG(a) & 4) != 0;
-      const bool use_bias = a.has_bias && !(NFS_DBG(a) & 8);
-      const uint64_t ones_desc = umma_desc_noswizzle(smem_u32(s_ones), 128, 0);
-      const uint64_t bias_desc = umma_desc_noswizzle(smem_u32(s_bias), 0, 128);
-      for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
-        // Issue order per layer: tile major - 4*ks MMAs on the pair's A tiles, then 4*ks on the B tiles.
-        // Long runs on one accumulator (switching the D operand between consecutive MMAs costs
-        // ~150-270 cycles, scripts/ubench/mma_modes.cu); the layer's weights (ks stages of [N/2 x 64]
-        // per CTA) stay resident for both passes.
-        for (int l = 0; l < L; ++l) {
-          const int ks = a.K[l] >> 6;
-          const uint32_t idesc = umma_idesc_bf16(256, a.N[l], 0, 0);
-#pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            if (l == 0) {
-              mbar_wait_cluster(acc_free + t, (iter & 1) ^ 1);   // accumulators t drained by the previous quad's last layer
-              mbar_wait_cluster((a.points != nullptr ? in_ready : in_full) + t, iter & 1);
-            } else {
-              mbar_wait_cluster(act_ready + t, n_ready[t] & 1);
-              ++n_ready[t];
-            }
-            tc_fence_after();
-            NFS_TRACE(1, l, t);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
-            // descriptors differ only in their 14-bit start-address field: +2 per 32-byte K step
-            const uint64_t a_desc0 = umma_desc_sw128(smem_u32(act[0]) + (uint32_t)t * kActBytes, 16, 1024);
-            if (t == 1 && use_bias) {           // tile B: bias first, which frees the operand for the next layer
-              if (elect_one()) {
-                umma_bf16_pair(d_tmem, ones_desc, bias_desc, idesc, 0u);
-                umma_commit_pair(bias_empty);
-              }
-              __syncwarp();
-            }
-            for (int s = 0; s < ks; ++s) {
-              const uint32_t w = wit + s, stage = w % kWStages, wph = (w / kWStages) & 1;
-              if (t == 0) {
-                if (!((NFS_DBG(a) & 2) && w >= kWStages)) mbar_wait_cluster(w_full + stage, wph);
-                tc_fence_after();
-              }
-              const uint64_t ad = a_desc0 + (uint64_t)((s * kActSlab) >> 4);
-              const uint64_t bd = b_desc0 + (uint64_t)((stage * kWStage) >> 4);
-              if (elect_one()) {
-                if (!no_mma) {
-                  umma_bf16_pair(d_tmem, ad, bd, idesc, (uint32_t)(s != 0 || (t == 1 && use_bias)));
-                  umma_bf16_pair(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                  umma_bf16_pair(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                  umma_bf16_pair(d_tmem, ad + 6, bd + 6, idesc, 1u);
-                }
-                if (t == 1) umma_commit_pair(w_empty + stage);
-              }
-              __syncwarp();
-            }
-            if (t == 0 && use_bias) {           // tile A: bias last (its operand has had the whole pass to land)
-              mbar_wait_cluster(bias_full, (iter * (uint32_t)L + (uint32_t)l) & 1);
-              tc_fence_after();
-              if (elect_one()) umma_bf16_pair(d_tmem, ones_desc, bias_desc, idesc, 1u);
-              __syncwarp();
-            }
-            NFS_TRACE(2, l, t);
-            if (elect_one()) {
-              umma_commit_pair(acc_full + t);
-              if (l == L - 1) umma_commit_pair(act_free + t);
-            }
-            __syncwarp();
-          }
-          wit += ks;
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (16 warps)
-    // Each warp drains one (TMEM lane quadrant q) x (quarter of the columns) block of the accumulator
-    // with ONE tcgen05.ld (x64 for 256-wide layers), first for tile A then for tile B.
-    const int q = warp & 3;
-    const int cq = (warp - 2) >> 2;
-    const int r_in = q * 32 + lane;
-    uint32_t n_full[2] = {0, 0}, gl = 0;
-    uint2 b_n1 = make_uint2(0u, 0u), b_n2 = make_uint2(0u, 0u);   // sign bits of the next two epilogue steps
-    bool store_pending = false;
-    const uint32_t ready_bar[2] = {map_to_cta(act_ready, 0), map_to_cta(act_ready + 1, 0)};   // in the leader CTA
-    const uint32_t free_bar[2] = {map_to_cta(acc_free, 0), map_to_cta(acc_free + 1, 0)};
-    const uint32_t in_bar[2] = {map_to_cta(in_ready, 0), map_to_cta(in_ready + 1, 0)};
-    uint32_t iter = 0;
-    for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
-      if (!kMasked && a.points != nullptr && cq < 2) {
-        // K2 fused in: the warps with cq == t write the positional encoding of tile t (thread = point) straight
-        // into slab 0 of act[t] - [x | sin(x f_0) | cos(x f_0) | sin(x f_1) | ...], one accurate sincosf per
-        // coordinate and the double-angle recurrence for the higher octaves (identical arithmetic to
-        // posenc_bf16_kernel's octave path, so the result is bit-identical to the two-kernel route)
-        const int t = cq;
-        mbar_wait_relaxed(act_free + t, (iter & 1) ^ 1);       // the previous quad's last MMAs have read act[t]
-        mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);      // and every epilogue warp is done with it
-        const long long row = (4 * quad + 2 * rank + t) * 128 + r_in;
-        float x[3] = {0.f, 0.f, 0.f}, sn[3], cs[3];
-        if (row < a.P) { x[0] = __ldg(a.points + row * 3); x[1] = __ldg(a.points + row * 3 + 1); x[2] = __ldg(a.points + row * 3 + 2); }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) sincosf(__fmul_rn(x[d], a.freq0), &sn[d], &cs[d]);
-        uint8_t *srow = smem + t * kActBytes + r_in * 128;
-        float buf[8];
-        int nb = 0, chunk = 0;
-        auto push = [&](float v) {
-          buf[nb++] = v;
-          if (nb == 8) {
-            *reinterpret_cast<uint4 *>(srow + ((chunk ^ (r_in & 7)) << 4)) =
-                make_uint4(pack_bf16x2(buf[0], buf[1]), pack_bf16x2(buf[2], buf[3]), pack_bf16x2(buf[4], buf[5]),
-                           pack_bf16x2(buf[6], buf[7]));
-            nb = 0; ++chunk;
-          }
-        };
-        push(x[0]); push(x[1]); push(x[2]);
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-          if (k < a.n_octaves) {
-            push(sn[0]); push(sn[1]); push(sn[2]); push(cs[0]); push(cs[1]); push(cs[2]);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const float s2 = 2.f * sn[d] * cs[d], c2 = 1.f - 2.f * sn[d] * sn[d];
-              sn[d] = s2; cs[d] = c2;
-            }
-          } else {
-            push(0.f); push(0.f); push(0.f); push(0.f); push(0.f); push(0.f);
-          }
-        }
-        push(0.f);                                            // column 63: zero padding
-        tc_fence_before();
-        fence_proxy_async();
-        __syncwarp();
-        if (kTrain && a.x_save) {
-          // training: the first layer's weight gradient needs this operand - store the warp's 32 rows (4 KB) and
-          // wait until the TMA has read them (another warp overwrites them in layer 0's epilogue)
-          if (lane == 0) {
-            tma_store_2d(&tmap_x, smem + t * kActBytes + q * 32 * 128, 0, (int)((4 * quad + 2 * rank + t) * 128 + q * 32));
-            bulk_commit();
-            bulk_wait_read0();
-          }
-          __syncwarp();
-        }
-        if (lane == 0) mbar_arrive_cluster(in_bar[t]);
-      }
-      for (int l = 0; l < L; ++l, ++gl) {
-        const bool last = (l == L - 1);
-        const bool is_head = last && a.head != 0;
-        const int Nl = a.N[l], quarter = Nl >> 2, c0 = cq * quarter;
-        const int act_l = a.act[l];
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          const long long tile = 4 * quad + 2 * rank + t;
-          const long long row = tile * 128 + r_in;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
-          uint8_t *act_t = smem + t * kActBytes;
-          // ReLU-backward mask row (straight from HBM): issue the loads before blocking on the accumulator
-          // ReLU-backward sign bits of this thread's `quarter` columns (8 or 4 bytes per tile step): loaded two epilogue
-          // steps ahead (same tile, previous layer's step), so their latency never shows
-          const bool use_bits = kMasked && act_l == 4 && tile < n_tiles;
-          const int words = quarter >> 5;                       // 2 (256-wide layers) or 1 (128-wide)
-          auto load_bits = [&](int layer) -> uint2 {
-            const uint32_t *bp = a.bits_in + ((long long)a.mask_idx[layer] * a.bits_rows + row) * 8 + (c0 >> 5);
-            uint2 v = make_uint2(0u, 0u);
-            if (words == 2) v = __ldg(reinterpret_cast<const uint2 *>(bp));
-            else v.x = __ldg(bp);
-            return v;
-          };
-          uint2 b_cur = make_uint2(0u, 0u);
-          if (kMasked) {
-            if (use_bits) b_cur = (l == 0) ? load_bits(0) : b_n1;
-            b_n1 = b_n2;
-            if (l + 1 < L && a.act[l + 1] == 4 && tile < n_tiles) b_n2 = load_bits(l + 1);
-          }
-          uint32_t bits_acc[2] = {0u, 0u};
-          mbar_wait_relaxed(acc_full + t, n_full[t] & 1);
-          ++n_full[t];
-          tc_fence_after();
-          NFS_TRACE(3, l, t);
-          if (!is_head) {
-            // the TMA store this warp issued from act[t] one layer ago has finished READING the block that is
-            // overwritten below (the store issued for the other tile a moment ago may still be in flight)
-            // 128-wide layers: two warps (cq, cq^1) share one 64-column TMA-store box -> pair barriers
-            const bool do_save = (kTrain || kMasked) && a.save != 0;
-            const bool paired = do_save && quarter == 32;
-            const uint32_t pair_bar = 1u + (uint32_t)(q * 2 + (cq >> 1));
-            if (store_pending) {
-              if (lane == 0 && (!paired || (cq & 1) == 0)) bulk_wait_read1();
-              __syncwarp();
-              if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            }
-            uint8_t *srow = act_t + (c0 >> 6) * kActSlab + r_in * 128;
-            const int ch0 = (c0 & 63) >> 3;
-            if (NFS_DBG(a) & 1) {
-              // bisection: no TMEM drain, no math, no smem writes
-            } else {
-              // `quarter` (64 or 32) columns in chunks of 16 (small chunks leave registers for a whole chunk of
-              // bias values to be in flight at once; the other three warps of the scheduler hide the latencies)
-              const int n_chunks = quarter >> 4;
-              uint32_t va[16];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                if (c < n_chunks) {
-                  tmem_ld16_async(taddr + c0 + 16 * c, va);
-                  tmem_ld_wait();
-                  epi_chunk<kMasked, kTrain>(va, act_l, (c >> 1) ? b_cur.y : b_cur.x, 8 * (c & 1),
-                                     bits_acc[c >> 1], srow, ch0 + 2 * c, r_in & 7, NFS_DBG(a));
-                }
-              }
-            }
-            if (kTrain && a.bits_out != nullptr && act_l == 1 && tile < n_tiles) {
-              uint32_t *bp = a.bits_out + ((long long)l * a.save_rows + row) * 8 + (c0 >> 5);
-              if (words == 2) *reinterpret_cast<uint2 *>(bp) = make_uint2(bits_acc[0], bits_acc[1]);
-              else *bp = bits_acc[0];
-            }
-            NFS_TRACE(4, l, t);
-            tc_fence_before();
-            if (!(NFS_DBG(a) & 16)) fence_proxy_async();   // generic-proxy smem writes -> visible to UMMA / TMA
-            __syncwarp();
-            NFS_TRACE(5, l, t);
-            if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            if (lane == 0) {
-              if (!last) mbar_arrive_cluster(ready_bar[t]);
-              if (do_save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
-                tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
-                             (int)(l * a.save_rows + tile * 128 + q * 32));
-                bulk_commit();
-              }
-            }
-            store_pending = do_save;
-            if (last) {                          // chain ends in a regular layer: tile t is finished once the
-              if (lane == 0 && store_pending) bulk_wait_read0();   // stores have read act[t] (it is reloaded next)
-              __syncwarp();
-              if (lane == 0) { mbar_arrive(head_done + t); mbar_arrive_cluster(free_bar[t]); }
-            }
-          } else {
-            // head: first out_cols (<= 16) columns, fp32, reference output activation; quarter 0 only
-            if (cq == 0) {
-              float v[16];
-              tmem_ld16(taddr, v);
-              if (row < a.P) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  if (j < a.out_cols) {
-                    float x = v[j];
-                    if (act_l == 1) x = fmaxf(x, 0.f);
-                    else if (act_l == 3 || (act_l == 2 && j < 3)) x = fm_sigmoid(x);
-                    v[j] = x;
-                  }
-                }
-                if (a.out_cols == 4) {
-                  *reinterpret_cast<float4 *>(a.out + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (j < a.out_cols) a.out[row * a.out_cols + j] = v[j];
-                }
-              }
-            }
-            tc_fence_before();
-            if (store_pending && lane == 0) bulk_wait_read0();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(head_done + t); mbar_arrive_cluster(free_bar[t]); }
-          }
-        }
-        if (last) store_pending = false;
-      }
-    }
-    if (lane == 0) bulk_wait0();               // all saved activations are in global memory
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();          // the peer may still be signalling this CTA's barriers / reading its operands
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
+  chain_body<kMasked, kTrain>(&tmap_x, &tmap_w, &tmap_save, &tmap_b, a, blockIdx.x >> 1, gridDim.x >> 1, nullptr);
 }
 
 }  // namespace

@@ -42,6 +42,21 @@ def allreduce_sum_(flat, group=None):
     return flat
 
 
+class NcclAllreduce:
+    """Sum of the flat gradient over the ranks as one NCCL call (eager: GraphedStep then runs
+    [graph: render + backward] -> this -> [graph: Adam])."""
+    describe = "nccl sum-allreduce of the flat fp32 gradient, eager between two CUDA graphs"
+    in_graph = False
+
+    def __call__(self, flat):
+        return allreduce_sum_(flat)
+
+
+def make_allreduce(flat):
+    """The gradient exchange of a data-parallel training step for the flat fp32 gradient buffer `flat`."""
+    return NcclAllreduce()
+
+
 def loss_scale(local_count, global_count):
     """A mean over the global batch is the sum over ranks of local_sum / global_count: scale the
     local mean loss by local_count / global_count before backward, then sum-allreduce."""

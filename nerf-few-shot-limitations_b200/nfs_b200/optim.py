@@ -55,12 +55,22 @@ class FusedAdam:
         """Number of steps taken (reads the device counter: host sync; not for the hot loop)."""
         return int(self._step_dev.item())
 
+    def sync_lr(self):
+        """Push a changed learning rate (MultiStepLR: `optimizer.lr = ...`) to its device copy.  Called by the eager
+        step() and by GraphedStep.replay() - a captured nfs_adam_step_dev reads the rate from the device, so the
+        fill must happen outside the graph, before the replay."""
+        if float(self.lr) != self._lr_on_device:
+            self._state[2:3].fill_(float(self.lr))
+            self._lr_on_device = float(self.lr)
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.sync_lr()
+
     def step(self, grad_scale=1.0, gathered=False):
         if not gathered:
             self.gather_grads()
-        if float(self.lr) != self._lr_on_device:      # MultiStepLR moved the rate: refresh the device copy
-            self._state[2:3].fill_(float(self.lr))
-            self._lr_on_device = float(self.lr)
+        self.sync_lr()
         with torch.cuda.device(self.flat.device):
             _lib.call("nfs_adam_step_dev", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                       self.flat.numel(), float(self.betas[0]), float(self.betas[1]), float(self.eps),

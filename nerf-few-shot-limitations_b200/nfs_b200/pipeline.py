@@ -209,6 +209,7 @@ class GraphedStep:
         """One optimisation step on whatever the static input buffers hold; returns the loss tensor of this
         step (a static buffer, no host sync)."""
         from . import mlp
+        self.opt.sync_lr()           # a scheduler may have moved optimizer.lr since the capture: the graph reads the device copy
         self.g_step.replay()
         if self.g_update is not None:               # two-graph form: eager all-reduce between the graphs
             self.allreduce(self.opt.grad)
