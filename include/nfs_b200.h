@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NFS_B200_ABI_VERSION 3
+#define NFS_B200_ABI_VERSION 4
 
 /* negative return codes (argument errors) */
 #define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
@@ -232,6 +232,23 @@ typedef struct nfs_wgrad_job {
   float *colsum; int32_t colsum_of_v;
 } nfs_wgrad_job;
 int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, void *stream);
+
+/* nfs_mlp_backward_fused: the backward pass of a fused MLP chain in ONE persistent launch - the dgrad chain
+ *   (arguments as the backward use of nfs_mlp_chain below: X = dy_bf16 [n_points, k_dims[0]], transposed weights in
+ *   reverse order, act 4 = ReLU backward from relu_bits_in, every layer's output stored to dys_bf16
+ *   [n_layers, save_rows_per_layer, n_dims[0]]) runs on `producer_pairs` CTA pairs (0 = library default) while the
+ *   remaining CTAs compute the weight / bias gradients `jobs` (nfs_wgrad_job, as nfs_wgrad_multi_bf16), consuming the
+ *   chain's output quad by quad (512 rows) through L2 as soon as it has been stored.  job_waits[i] != 0 marks a job
+ *   whose operands are (partly) produced by this launch's chain (they are read only after the chain has published the
+ *   rows); 0 = operands complete before the launch.  quad_flags: >= ceil(n_points / 512) uint32 of device scratch
+ *   (zeroed by the call).  Replaces autograd's backward of nerf_model.NeRFMLP (src/models/nerf_model.py:16-24):
+ *   dX_l = (dY_l W_l) * ReLU'(h_l), dW_l = dY_l^T h_{l-1}, db_l = sum_p dY_l, for all points of a training step. */
+int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                           const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                           const void *wt_stack_bf16, int32_t w_rows, const void *relu_bits_in,
+                           int64_t bits_rows_per_layer, const int32_t *mask_idx, void *dys_bf16,
+                           int64_t save_rows_per_layer, const nfs_wgrad_job *jobs, int32_t n_jobs,
+                           const int32_t *job_waits, uint32_t *quad_flags, int32_t producer_pairs, void *stream);
 
 /* nfs_mlp_chain: a whole chain of dense layers in ONE launch (fused multi-layer MLP):
  *   h_0 = X;  h_{l+1} = act_l( h_l . W_l^T + b_l ),  l = 0 .. n_layers-1

@@ -621,3 +621,90 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
 
 }  // namespace
 }  // namespace nfs
+
+// ---------------------------------------------------------------- host: argument checks + tensor maps of a chain launch
+// returns 0, or 1 for an empty launch, or an error (< 0 / cudaError)
+// Boxes of the stacked weight tensor and of the saved activations differ from make_tmap_bf16's
+// default only in their row count (64 resp. 32).
+// points != NULL: in-kernel encoding; x_bf16 is then NULL (inference) or the [rows128, 64] bf16 buffer that RECEIVES the
+// encoded operand (training forward).
+static inline int chain_prepare(const char *fn, const void *x_bf16, const float *points, float freq0, int n_octaves,
+                        int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                        const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                        const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16,
+                        const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
+                        void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                        int32_t out_cols, nfs::FusedArgs *a_out, CUtensorMap *tx_out, CUtensorMap *tw_out,
+                        CUtensorMap *ts_out, CUtensorMap *tb_out) {
+  using namespace nfs;
+  if (n_points < 0 || n_layers < 2 || n_layers > kFmMaxLayers) return fail_arg(fn, NFS_E_BADARG, "need 2..12 layers");
+  if (n_points == 0) return 1;          // nothing to do
+  if ((!x_bf16 && !points) || !k_dims || !n_dims || !acts || !row0 || !w_stack_bf16 || (!out_f32 && !save_bf16))
+    return fail_arg(fn, NFS_E_BADARG, "null pointer");
+  FusedArgs a{};
+  a.P = n_points; a.n_layers = n_layers; a.has_bias = bias_terms_bf16 != nullptr; a.out = out_f32; a.out_cols = out_cols;
+  a.save = save_bf16 != nullptr; a.save_rows = save_rows_per_layer;
+  a.head = out_f32 != nullptr;
+  a.points = points; a.freq0 = freq0; a.n_octaves = n_octaves;
+  a.dbg = 0;
+  a.trace = nullptr;
+  a.bits_in = (const uint32_t *)relu_bits_in; a.bits_rows = bits_rows_per_layer;
+  a.bits_out = (uint32_t *)relu_bits_out;
+  for (int l = 0; l < n_layers; ++l) {
+    a.K[l] = k_dims[l]; a.N[l] = n_dims[l]; a.act[l] = acts[l]; a.row0[l] = row0[l];
+    a.mask_idx[l] = mask_idx ? mask_idx[l] : 0;
+    if (a.act[l] == 4 && (!relu_bits_in || !mask_idx || a.mask_idx[l] < 0))
+      return fail_arg(fn, NFS_E_BADARG, "act 4 (ReLU backward) needs relu_bits_in and mask_idx");
+    if ((a.act[l] == 4 || (a.act[l] == 1 && relu_bits_out)) && a.N[l] < 128 && !(out_f32 && l == n_layers - 1))
+      return fail_arg(fn, NFS_E_UNSUPPORTED, "ReLU sign bits need layers at least 128 wide");
+    if (a.act[l] < 0 || a.act[l] > 4) return fail_arg(fn, NFS_E_BADARG, "act must be 0..4");
+    if (a.K[l] % 64 || a.K[l] <= 0 || a.K[l] > 256 || a.N[l] % 64 || a.N[l] <= 0 || a.N[l] > 256 ||
+        a.row0[l] < 0 || a.row0[l] + a.N[l] > w_rows)
+      return fail_arg(fn, NFS_E_UNSUPPORTED, "layer dims must be multiples of 64 in [64,256] and fit the weight stack");
+    if (l > 0 && a.K[l] != a.N[l - 1]) return fail_arg(fn, NFS_E_BADARG, "layer l input width != layer l-1 output width");
+  }
+  if (a.head && (out_cols <= 0 || out_cols > a.N[n_layers - 1])) return fail_arg(fn, NFS_E_BADARG, "out_cols out of range");
+  const long long rows128 = ((n_points + 127) / 128) * 128;
+  if (a.save && save_rows_per_layer < rows128)
+    return fail_arg(fn, NFS_E_BADARG, "save_rows_per_layer must be >= n_points rounded up to 128");
+  if (relu_bits_in && bits_rows_per_layer < rows128)
+    return fail_arg(fn, NFS_E_BADARG, "bits_rows_per_layer must be >= n_points rounded up to 128");
+  if (relu_bits_out && (relu_bits_in || save_rows_per_layer < rows128))
+    return fail_arg(fn, NFS_E_BADARG, "relu_bits_out belongs to a forward chain (no relu_bits_in) with save_rows_per_layer >= rows");
+  const int n_saved = a.head ? n_layers - 1 : n_layers;
+  if (a.save)
+    for (int l = 0; l < n_saved; ++l)
+      if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal layer widths");
+
+  CUtensorMap tx{}, tw{}, ts{}, tb{};
+  int rc = 0;
+  if (points != nullptr) {
+    if (a.K[0] != 64 || n_octaves < 1 || n_octaves > 10)
+      return fail_arg(fn, NFS_E_UNSUPPORTED, "in-kernel encoding needs a 64-wide first layer and 1..10 octaves");
+    if (x_bf16 != nullptr) {
+      if (!a.save) return fail_arg(fn, NFS_E_BADARG, "the encoded operand is only stored by a training forward (save_bf16)");
+      a.x_save = 1;
+      rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)rows128, 64, 64, 32, fn);
+      if (rc) return rc;
+    }
+  } else {
+    rc = tc::make_tmap_bf16(&tx, x_bf16, (uint64_t)n_points, (uint64_t)a.K[0], (uint64_t)a.K[0], 128, fn);
+    if (rc) return rc;
+  }
+  rc = tc::make_tmap_bf16(&tw, w_stack_bf16, (uint64_t)w_rows, 256, 256, 64, fn);
+  if (rc) return rc;
+  if (bias_terms_bf16 != nullptr) {
+    rc = tc::make_tmap_rows16(&tb, bias_terms_bf16, (uint64_t)w_rows, 128, fn);
+    if (rc) return rc;
+  }
+  if (a.save) {
+    rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * n_saved), (uint64_t)a.N[0],
+                            (uint64_t)a.N[0], 32, fn);
+    if (rc) return rc;
+  }
+  *a_out = a; *tx_out = tx; *tw_out = tw; *ts_out = ts; *tb_out = tb;
+  return 0;
+}
+
+// dynamic shared memory of the chain body: tiles, weight ring, barriers, ones, bias operand
+static constexpr size_t kChainSmemBytes = 2 * nfs::kActBytes + nfs::kWStages * nfs::kWStage + 256 + 256 + 128 * 16;

@@ -37,6 +37,8 @@ SIGNATURES = {
     "nfs_wgrad_bf16": (ctypes.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _i64, _i64, _p, _i32, _p]),
     "nfs_wgrad_multi_bf16": (ctypes.c_int, [_p, _i32, _p]),
     "nfs_mlp_chain": (ctypes.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _i64, _p, _p, _p, _i64, _p, _i32, _p]),
+    "nfs_mlp_backward_fused": (ctypes.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p, _p, _i64, _p, _i32, _p, _p,
+                                              _i32, _p]),
     "nfs_pack_stack": (ctypes.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "nfs_pack_table": (ctypes.c_int, [_p, _i32, _i32, _p]),
     "nfs_bias_terms_bf16": (ctypes.c_int, [_p, _i32, _p, _p]),

@@ -515,8 +515,14 @@ class StepSession:
             self.head_w = torch.zeros((64, plan.h_pad), device=dev, dtype=torch.float32)
             self.head_b = torch.zeros(64, device=dev, dtype=torch.float32)
             self.w0_t = torch.zeros((plan.k0, plan.h_pad), device=dev, dtype=torch.float32)
+            self.quad_flags = torch.zeros(rows // 512 + 2, device=dev, dtype=torch.int32)
         self.cursor = 0
         self.pending = 0
+        # NFS_BWD_MERGED=1: one launch for the whole backward pass (nfs_mlp_backward_fused: dgrad chain on producer CTA
+        # pairs, weight gradients on consumer CTAs fed through L2).  Parity-green but SLOWER than the default route
+        # (dgrad chain per call + one weight-gradient launch per layer) on B200 - 4.6 vs 4.0 ms per cfg 3 step at the
+        # best split - so it stays opt-in.
+        self.merged = os.environ.get("NFS_BWD_MERGED", "0") != "0" and plan.h_pad == 256
         self.opt.grad.zero_()
         self.head_w.zero_()
         self.head_b.zero_()
@@ -546,12 +552,14 @@ class StepSession:
         if pad != P:
             self.dy[r0 + P:r0 + pad].zero_()
         dy = act_grad(out, g_out, 2, 64, dst=self.dy[r0:r0 + P])
+        self.pending -= 1
+        if self.merged:
+            return               # flush() runs the dgrad chain of ALL calls together with the weight gradients
         n_hidden = len(plan.packed)
         with torch.cuda.device(dy.device):
             _lib.call("nfs_mlp_chain", ptr(dy), P, n_hidden, plan.cb_k, plan.cb_n, plan.cb_act, plan.cb_row0,
                       ptr(plan.wt_stack), plan.wt_rows, None, ptr(self.bits[:, r0:]), self.rows_cap, plan.cb_mask,
                       ptr(self.dys[:, r0:]), None, self.rows_cap, None, 0, _stream())
-        self.pending -= 1
 
     def flush(self):
         """The weight / bias gradients of every call since begin(), into the optimizer's flat gradient."""
@@ -564,6 +572,8 @@ class StepSession:
             return
         n_layers, hd = len(plan.packed), plan.hidden
         dev = self.opt.grad.device
+        if self.merged:
+            return self._flush_merged(T)
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -589,6 +599,34 @@ class StepSession:
                                colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim)
                 v[0].add_(self.w0_t[:plan.in_dim, :hd].t())
         main.wait_stream(side)
+
+
+    def _flush_merged(self, T):
+        """dgrad chain over all T rows + the 1 + n_layers weight gradients, one persistent launch: producer CTA pairs run
+        the chain, consumer CTAs pick each 512-row quad of dY up from L2 as soon as it has been stored."""
+        plan, v = self.plan, self.views
+        n_layers, hd = len(plan.packed), plan.hidden
+        jobs = [dict(u=self.save[n_layers - 1, :T], v=self.dy[:T], dw=self.head_w, ld_m=1, ld_n=plan.h_pad,
+                     colsum=self.head_b, colsum_of_v=True)]
+        waits = [0]
+        for i in range(n_layers - 1, 0, -1):
+            jobs.append(dict(u=self.save[i - 1, :T], v=self.dys[n_layers - 1 - i, :T], dw=v[2 * i], ld_m=1, ld_n=hd,
+                             colsum=v[2 * i + 1], colsum_of_v=True, m_valid=hd, n_valid=hd))
+            waits.append(1)
+        jobs.append(dict(u=self.dys[n_layers - 1, :T], v=self.x16[:T], dw=self.w0_t, ld_m=1, ld_n=plan.h_pad, colsum=v[1],
+                         colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim))
+        waits.append(1)
+        arr, n, dev, kept = ops.wgrad_job_array(jobs, "nfs_mlp_backward_fused")
+        c_waits = (ctypes.c_int32 * n)(*[waits[i] for i in kept])
+        with torch.cuda.device(dev):
+            _lib.call("nfs_mlp_backward_fused", ptr(self.dy), T, n_layers, plan.cb_k, plan.cb_n, plan.cb_act, plan.cb_row0,
+                      ptr(plan.wt_stack), plan.wt_rows, ptr(self.bits), self.rows_cap, plan.cb_mask, ptr(self.dys),
+                      self.rows_cap, ctypes.byref(arr), n, c_waits, ptr(self.quad_flags), 0, _stream())
+        v[2 * n_layers + 0].add_(self.head_w[3:4, :hd])      # sigma_out.weight (head rows 0..2 rgb_out, 3 sigma_out)
+        v[2 * n_layers + 1].add_(self.head_b[3:4])
+        v[2 * n_layers + 2].add_(self.head_w[0:3, :hd])
+        v[2 * n_layers + 3].add_(self.head_b[0:3])
+        v[0].add_(self.w0_t[:plan.in_dim, :hd].t())
 
 
 class _G1Fn(torch.autograd.Function):

@@ -489,20 +489,20 @@ def wgrad_bf16(u, v, dw, ld_m, ld_n, colsum=None, colsum_of_v=True, m_valid=0, n
     return dw
 
 
-def wgrad_multi(jobs):
-    """Several wgrad_bf16 calls in one launch (nfs_wgrad_multi_bf16).  jobs: list of dicts with the keyword
-    arguments of wgrad_bf16 (u, v, dw, ld_m, ld_n, colsum, colsum_of_v, m_valid, n_valid)."""
+def wgrad_job_array(jobs, who="wgrad_multi"):
+    """list of dicts with the keyword arguments of wgrad_bf16 (u, v, dw, ld_m, ld_n, colsum, colsum_of_v, m_valid,
+    n_valid) -> (ctypes array of nfs_wgrad_job, number of non-empty jobs, device, indices of the kept jobs)."""
     arr = (_lib.WgradJob * max(len(jobs), 1))()
-    keep, n, dev = [], 0, None
-    for jb in jobs:
+    n, dev, kept = 0, None, []
+    for i, jb in enumerate(jobs):
         u, v, dw, colsum = jb["u"], jb["v"], jb["dw"], jb.get("colsum")
-        _need_cuda("wgrad_multi", u, v, dw, colsum)
+        _need_cuda(who, u, v, dw, colsum)
         if u.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or u.stride(1) != 1 or v.stride(1) != 1:
-            raise RuntimeError("wgrad_multi: operands must be bf16 with contiguous columns")
+            raise RuntimeError(who + ": operands must be bf16 with contiguous columns")
         if dw.dtype != torch.float32 or (colsum is not None and colsum.dtype != torch.float32):
-            raise RuntimeError("wgrad_multi: destinations must be fp32")
+            raise RuntimeError(who + ": destinations must be fp32")
         if v.shape[0] != u.shape[0]:
-            raise RuntimeError("wgrad_multi: operands disagree on the number of points")
+            raise RuntimeError(who + ": operands disagree on the number of points")
         if u.shape[0] == 0:
             continue
         dev = u.device
@@ -513,8 +513,15 @@ def wgrad_multi(jobs):
         a.dw, a.ld_m, a.ld_n = dw.data_ptr(), int(jb["ld_m"]), int(jb["ld_n"])
         a.colsum = colsum.data_ptr() if colsum is not None else None
         a.colsum_of_v = int(bool(jb.get("colsum_of_v", True)))
-        keep.append((u, v, dw, colsum))
+        kept.append(i)
         n += 1
+    return arr, n, dev, kept
+
+
+def wgrad_multi(jobs):
+    """Several wgrad_bf16 calls in one launch (nfs_wgrad_multi_bf16).  jobs: list of dicts with the keyword
+    arguments of wgrad_bf16 (u, v, dw, ld_m, ld_n, colsum, colsum_of_v, m_valid, n_valid)."""
+    arr, n, dev, _ = wgrad_job_array(jobs)
     if n:
         with torch.cuda.device(dev):
             _lib.call("nfs_wgrad_multi_bf16", ctypes.byref(arr), n, _stream())

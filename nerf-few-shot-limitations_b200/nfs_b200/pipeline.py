@@ -238,7 +238,7 @@ class GraphedTrainStep(GraphedStep):
         sess = _session_for(model, optimizer)
         plan = model._get_plan() if hasattr(model, "_get_plan") else None
         self._captured = [getattr(o, k, None) for o, keys in (
-            (sess, ("x16", "save", "bits", "dy", "dys", "head_w", "head_b", "w0_t")),
+            (sess, ("x16", "save", "bits", "dy", "dys", "head_w", "head_b", "w0_t", "quad_flags")),
             (plan, ("w_stack", "wt_stack", "b_stack", "_table"))) if o is not None for k in keys]
 
     def _forward_backward(self):

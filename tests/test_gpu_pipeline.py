@@ -181,21 +181,28 @@ def test_step_session_matches_per_call_gradients(cuda, monkeypatch, n_rays, n_co
     tgt = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(2)).to(cuda)
     bands = O.frequency_bands(10)
     res = {}
-    for mode in ("session", "per_call"):
-        monkeypatch.setenv("NFS_MLP_SESSION", "1" if mode == "session" else "0")
+    for mode in ("session", "session_merged", "per_call"):
+        monkeypatch.setenv("NFS_MLP_SESSION", "0" if mode == "per_call" else "1")
+        # "session": dgrad chain per call + a weight-gradient launch per layer (default); "session_merged": the whole
+        # backward pass is ONE launch (nfs_mlp_backward_fused: dgrad chain on producer CTA pairs, weight gradients on
+        # consumer CTAs fed through L2, opt-in)
+        monkeypatch.setenv("NFS_BWD_MERGED", "1" if mode == "session_merged" else "0")
         torch.manual_seed(3)
         model = NeRFMLP().to(cuda).train()
         with torch.no_grad():
             model.sigma_out.bias.fill_(0.3)
         opt = FusedAdam(model.parameters(), lr=5e-4)
-        assert (pipeline._session_for(model, opt) is not None) == (mode == "session")
+        assert (pipeline._session_for(model, opt) is not None) == (mode != "per_call")
         torch.manual_seed(11)
         loss = pipeline.train_step(model, opt, bands, ro, rd, tgt, 2.0, 6.0, n_coarse, n_imp)
         res[mode] = (float(loss), opt.grad.clone(), opt.flat.clone())
         assert getattr(model._get_plan(), "_session", None) is None
-    assert res["session"][0] == res["per_call"][0]
-    g_s, g_p = res["session"][1], res["per_call"][1]
+    assert res["session"][0] == res["per_call"][0] == res["session_merged"][0]
+    g_s, g_x, g_p = res["session"][1], res["session_merged"][1], res["per_call"][1]
     assert float(g_p.norm()) > 0
     rel = float((g_s - g_p).norm() / g_p.norm())
-    record("step_session_vs_per_call", n_rays=n_rays, n_coarse=n_coarse, n_imp=n_imp, grad_rel_l2=rel)
-    assert rel <= 1e-4, rel
+    rel_x = float((g_x - g_p).norm() / g_p.norm())
+    rel_sx = float((g_s - g_x).norm() / g_x.norm())
+    record("step_session_vs_per_call", n_rays=n_rays, n_coarse=n_coarse, n_imp=n_imp, grad_rel_l2=rel,
+           merged_grad_rel_l2=rel_x, merged_vs_split_rel_l2=rel_sx)
+    assert rel <= 1e-4 and rel_x <= 1e-4 and rel_sx <= 1e-4, (rel, rel_x, rel_sx)
