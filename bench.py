@@ -191,14 +191,24 @@ class Timer:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def _iters_for(self, fn, seconds):
+        """Number of calls of fn that fill `seconds` - the SAME number on every rank (fn may contain a cross-rank
+        exchange, so the ranks must make identical call sequences: never loop on the local clock)."""
+        if seconds <= 0 or self.quick:
+            return 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        per_call = self.max_over_ranks((time.perf_counter() - t0) / 3 * 1e3) * 1e-3
+        return max(1, min(2000, int(seconds / max(per_call, 1e-6))))
+
     def run(self, fn, steps, warmup, settle=0.3, tail=0.2, clocks=True):
         """-> (ms per step [max over ranks], clocks dict | None)"""
         sampler = ClockSampler(self.local_rank) if (clocks and self.rank == 0 and not self.quick) else None
-        t0 = time.perf_counter()
-        while not self.quick and time.perf_counter() - t0 < settle:
-            for _ in range(8):
-                fn()
-            torch.cuda.synchronize()
+        for _ in range(self._iters_for(fn, settle)):
+            fn()
         for _ in range(max(warmup, 3)):
             fn()
         self.sync_all()
@@ -209,12 +219,10 @@ class Timer:
         b.record()
         self.sync_all()
         ms = self.max_over_ranks(a.elapsed_time(b) / steps)
-        if sampler is not None:
-            t0 = time.perf_counter()
-            while time.perf_counter() - t0 < tail:
-                for _ in range(8):
-                    fn()
-                torch.cuda.synchronize()
+        if clocks and not self.quick and tail > 0:         # same condition and count on every rank
+            for _ in range(max(1, min(2000, int(tail / max(ms * 1e-3, 1e-6))))):
+                fn()
+            torch.cuda.synchronize()
         return ms, (sampler.stop() if sampler is not None else None)
 
 
@@ -394,7 +402,7 @@ def bench_train_step(T, world, args):
     n = TRAIN_RAYS
     ro, rd = lego_rays(n, seed=100 + rank)
     target = torch.rand(n, 3, generator=torch.Generator().manual_seed(100 + rank))
-    allreduce = nd.make_allreduce(opt.grad) if world > 1 else None
+    allreduce = nd.make_allreduce(opt) if world > 1 else None
     l0 = _lib.launch_count()
     step = pipeline.GraphedTrainStep(model, opt, bands, n, 2.0, 6.0, N_COARSE, N_IMPORTANCE, perturb=True,
                                      loss_scale=1.0 / world, allreduce=allreduce, warmup=3)
@@ -534,7 +542,7 @@ def bench_dino(T, world, args):
                                              pose_inv=pose4_inv)
         return torch.mean((o["rgb"] - tgt4) ** 2)
 
-    allreduce = nd.make_allreduce(opt3.grad) if world > 1 else None
+    allreduce = nd.make_allreduce(opt3) if world > 1 else None
     step4 = pipeline.GraphedStep(opt3, loss4, loss_scale=1.0 / world, allreduce=allreduce)
     ms4, clk = T.run(step4.replay, 5 if args.quick else 30, 3)
     flop4 = 64 * 5.51e6                          # ~5.51 MFLOP per point for G3 training

@@ -397,6 +397,35 @@ int nfs_rays_generate(int32_t height, int32_t width, float focal, const float *c
                       const int64_t *pix_idx, int64_t n_rays, const float *image,
                       float *rays_o, float *rays_d, float *target, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Data-parallel weight update over NVLink peer memory (the reference is single-device:
+ * this replaces optimizer.step() of src/training/train.py:286 for a ray-sharded batch).
+ *   Every rank owns one exchange buffer = [n_grad fp32 gradient | flags] allocated by nfs_dp_alloc (plain cudaMalloc,
+ *   zeroed), exports it with nfs_dp_ipc_export (64-byte CUDA IPC handle, sent to the peers by the host) and maps its
+ *   peers' buffers with nfs_dp_ipc_open.  peer_bases: HOST array of `world` device pointers, entry `rank` = the local
+ *   buffer.  The model's weight-gradient kernels accumulate into the local buffer's gradient part.
+ *   nfs_dp_adam_step: ONE kernel that (1) tells the peers this rank's gradient is complete, (2) waits for theirs,
+ *   (3) sums the `world` gradient buffers element-wise, reading the peers' over NVLink, and applies the Adam / AdamW
+ *   update of nfs_adam_step_dev to param / exp_avg / exp_avg_sq (replicated weights, every rank computes the same
+ *   update), (4) tells the peers it has finished reading.  epoch_dev / cta_counter: one zero-initialised uint32 each.
+ *   nfs_dp_wait_readers: waits until every peer has finished reading this rank's gradient of the last exchange; run it
+ *   before the gradient buffer is zeroed for the next step.  Both are stream-ordered, capturable in a CUDA graph, and
+ *   bounded (a missing peer raises a CUDA error after ~2 s).
+ * ------------------------------------------------------------------------- */
+uint64_t nfs_dp_flags_offset(int64_t n_grad);
+uint64_t nfs_dp_buffer_bytes(int64_t n_grad);
+int nfs_dp_alloc(int64_t n_grad, void **base_out);
+int nfs_dp_free(void *base);
+int nfs_dp_ipc_export(void *base, void *handle64);
+int nfs_dp_ipc_open(const void *handle64, void **base_out);
+int nfs_dp_ipc_close(void *base);
+int nfs_dp_wait_readers(void *const *peer_bases, int32_t world, int32_t rank, int64_t n_grad,
+                        const uint32_t *epoch_dev, void *stream);
+int nfs_dp_adam_step(float *param, void *const *peer_bases, int32_t world, int32_t rank, float *exp_avg,
+                     float *exp_avg_sq, int64_t n, float beta1, float beta2, float eps, float weight_decay,
+                     int32_t *step_counter, float *state, float grad_scale, int32_t decoupled,
+                     uint32_t *epoch_dev, uint32_t *cta_counter, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,16 @@ SIGNATURES = {
     "nfs_act_grad_bf16": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i64, _p, _p]),
     "nfs_adam_step": (ctypes.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _i32, _p]),
     "nfs_adam_step_dev": (ctypes.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p, _f32, _i32, _p]),
+    "nfs_dp_flags_offset": (ctypes.c_uint64, [_i64]),
+    "nfs_dp_buffer_bytes": (ctypes.c_uint64, [_i64]),
+    "nfs_dp_alloc": (ctypes.c_int, [_i64, _p]),
+    "nfs_dp_free": (ctypes.c_int, [_p]),
+    "nfs_dp_ipc_export": (ctypes.c_int, [_p, _p]),
+    "nfs_dp_ipc_open": (ctypes.c_int, [_p, _p]),
+    "nfs_dp_ipc_close": (ctypes.c_int, [_p]),
+    "nfs_dp_wait_readers": (ctypes.c_int, [_p, _i32, _i32, _i64, _p, _p]),
+    "nfs_dp_adam_step": (ctypes.c_int, [_p, _p, _i32, _i32, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p, _f32, _i32, _p, _p,
+                                        _p]),
     "nfs_sample_hierarchical": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -44,7 +44,7 @@ def allreduce_sum_(flat, group=None):
 
 class NcclAllreduce:
     """Sum of the flat gradient over the ranks as one NCCL call (eager: GraphedStep then runs
-    [graph: render + backward] -> this -> [graph: Adam])."""
+    [graph: render + backward] -> this -> [graph: Adam]).  Fallback of PeerExchange."""
     describe = "nccl sum-allreduce of the flat fp32 gradient, eager between two CUDA graphs"
     in_graph = False
 
@@ -52,9 +52,114 @@ class NcclAllreduce:
         return allreduce_sum_(flat)
 
 
-def make_allreduce(flat):
-    """The gradient exchange of a data-parallel training step for the flat fp32 gradient buffer `flat`."""
-    return NcclAllreduce()
+class PeerExchange:
+    """Gradient exchange fused into the optimizer step (csrc/dp.cu): every rank's flat fp32 gradient lives in a
+    CUDA-IPC-shared buffer; nfs_dp_adam_step sums the buffers of all ranks over NVLink while it applies Adam, with
+    flag-based hand-shakes inside the kernels - no NCCL call and no graph split on the step's path.
+
+    Construct it right after the FusedAdam and before anything captures optimizer.grad (StepSession, CUDA graphs):
+    it re-homes optimizer.grad into the shared buffer.  All ranks of `group` must construct it collectively."""
+    in_graph = True
+
+    def __init__(self, optimizer, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        self.opt, self.group = optimizer, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("PeerExchange: at most 8 ranks (one NVLink / NVSwitch box)")
+        dev = optimizer.flat.device
+        self.n = int(optimizer.flat.numel())
+        base = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.call("nfs_dp_alloc", self.n, ctypes.byref(base))
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.call("nfs_dp_ipc_export", base, handle)
+        self.base = base.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.bases = (ctypes.c_void_p * self.world)()
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.bases[r] = self.base
+                continue
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            out = ctypes.c_void_p()
+            with torch.cuda.device(dev):
+                _lib.call("nfs_dp_ipc_open", buf, ctypes.byref(out))
+            self.bases[r] = out.value
+            self._opened.append(out.value)
+        self.grad = _tensor_from_ptr(self.base, self.n, dev)
+        self.grad.zero_()
+        optimizer.grad = self.grad                       # weight-gradient kernels now accumulate into the shared buffer
+        self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.cta_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.describe = ("fused into the Adam kernel: every rank reads its %d peers' flat fp32 gradients (%d floats) over "
+                         "NVLink peer memory (CUDA IPC), flag hand-shake in-kernel, inside the step's CUDA graph"
+                         % (self.world - 1, self.n))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                        # every rank has mapped every buffer before the first kernel
+
+    def wait_readers(self):
+        """Before this rank's gradient buffer is written again: all peers have finished reading the last exchange."""
+        from . import _lib
+        from .ops import _stream
+        with torch.cuda.device(self.grad.device):
+            _lib.call("nfs_dp_wait_readers", self.bases, self.world, self.rank, self.n, _lib.ptr(self.epoch), _stream())
+
+    def fused_step(self, grad_scale=1.0):
+        """Sum over the ranks + Adam update, one kernel (optimizer.step() of the data-parallel step)."""
+        from . import _lib, mlp
+        from .ops import _stream
+        o = self.opt
+        o.sync_lr()
+        with torch.cuda.device(o.flat.device):
+            _lib.call("nfs_dp_adam_step", _lib.ptr(o.flat), self.bases, self.world, self.rank, _lib.ptr(o.exp_avg),
+                      _lib.ptr(o.exp_avg_sq), self.n, float(o.betas[0]), float(o.betas[1]), float(o.eps),
+                      float(o.weight_decay), _lib.ptr(o._step_dev), _lib.ptr(o._state), float(grad_scale),
+                      int(bool(o.decoupled)), _lib.ptr(self.epoch), _lib.ptr(self.cta_counter), _stream())
+        mlp.bump_weight_epoch()
+
+    def __call__(self, flat):
+        raise RuntimeError("PeerExchange has no stand-alone all-reduce: use wait_readers() / fused_step()")
+
+
+class _RawCuda:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _tensor_from_ptr(ptr, n, device):
+    """fp32 tensor of n elements over raw device memory (memory owned by the caller)."""
+    return torch.as_tensor(_RawCuda(ptr, n), device=device)
+
+
+def make_allreduce(optimizer, group=None):
+    """The gradient exchange of a data-parallel training step for `optimizer` (FusedAdam): the peer-memory exchange fused
+    into the Adam kernel when every rank can map every other rank's buffer (one box, CUDA IPC), else one NCCL
+    all-reduce.  NFS_DP_EXCHANGE=nccl forces the fallback.  Collective over the ranks of `group`."""
+    import os
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    ok, ex, err = 1, None, ""
+    if os.environ.get("NFS_DP_EXCHANGE", "p2p") == "nccl" or not hasattr(optimizer, "flat") or dist.get_world_size(group) > 8:
+        ok = 0
+    else:
+        try:
+            ex = PeerExchange(optimizer, group)
+        except Exception as e:            # e.g. IPC not permitted in this container: every rank must agree on the fallback
+            ok, err = 0, repr(e)[:200]
+    flag = torch.tensor([ok], device=optimizer.flat.device if hasattr(optimizer, "flat") else "cuda", dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        return ex
+    nccl = NcclAllreduce()
+    if err:
+        nccl.describe += " (peer exchange unavailable: %s)" % err
+    return nccl
 
 
 def loss_scale(local_count, global_count):

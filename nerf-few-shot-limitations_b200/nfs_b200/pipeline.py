@@ -63,6 +63,8 @@ def train_step(model, optimizer, freq_bands, rays_o, rays_d, target, near, far, 
     backward through the compositing and MLP kernels, optional gradient all-reduce, fused Adam.
     Returns the (detached) loss tensor - no host sync."""
     optimizer.zero_grad()
+    if getattr(allreduce, "in_graph", False):
+        allreduce.wait_readers()             # peers have finished reading the last step's gradient buffer
     sess = _session_for(model, optimizer)
     if sess is not None:
         sess.begin(rays_o.shape[0] * (n_coarse + (n_coarse + n_importance if n_importance > 0 else 0)))
@@ -86,10 +88,12 @@ def train_step(model, optimizer, freq_bands, rays_o, rays_d, target, near, far, 
             g = optimizer.grad
         else:
             g = optimizer.gather_grads()
-        scale = 1.0
-        if allreduce is not None:
-            allreduce(g)
-        optimizer.step(grad_scale=scale, gathered=True)
+        if getattr(allreduce, "in_graph", False):
+            allreduce.fused_step()           # sum over the ranks fused into the Adam kernel (peer memory)
+        else:
+            if allreduce is not None:
+                allreduce(g)
+            optimizer.step(grad_scale=1.0, gathered=True)
     else:
         optimizer.step()
     return loss.detach()
@@ -169,24 +173,27 @@ class GraphedStep:
         rng = torch.cuda.get_rng_state(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        self.fused_exchange = bool(getattr(allreduce, "in_graph", False))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):            # first launches: function attributes, caches, allocator
                 self._forward_backward()
-                if allreduce is not None:
+                if allreduce is not None and not self.fused_exchange:
                     allreduce(o.grad)
                 self._update()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # The all-reduce stays OUTSIDE the graphs: capturing the NCCL collective together with the step hung
         # on a 2-GPU box (round 1), so data parallel runs [graph] -> eager all-reduce -> [graph].
-        self.allreduce_in_graph = False
+        # With the peer-memory exchange (dist.PeerExchange) the reduction is part of the Adam kernel and the whole
+        # step is one graph; an NCCL all-reduce stays between two graphs.
+        self.allreduce_in_graph = self.fused_exchange
         self.g_step = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_step):
             self.loss = self._forward_backward()
-            if allreduce is None:
+            if allreduce is None or self.fused_exchange:
                 self._update()
         self.g_update = None
-        if allreduce is not None:
+        if allreduce is not None and not self.fused_exchange:
             self.g_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_update, pool=self.g_step.pool()):
                 self._update()
@@ -197,13 +204,18 @@ class GraphedStep:
 
     def _forward_backward(self):
         self.opt.zero_grad()
+        if self.fused_exchange:
+            self.allreduce.wait_readers()
         loss = self.closure()
         (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
         self.opt.gather_grads()
         return loss.detach()
 
     def _update(self):
-        self.opt.step(gathered=True)
+        if self.fused_exchange:
+            self.allreduce.fused_step()
+        else:
+            self.opt.step(gathered=True)
 
     def replay(self):
         """One optimisation step on whatever the static input buffers hold; returns the loss tensor of this
@@ -247,6 +259,8 @@ class GraphedTrainStep(GraphedStep):
             return super()._forward_backward()
         near, far, n_coarse, n_importance, perturb = self.cfg
         self.opt.zero_grad()
+        if self.fused_exchange:
+            self.allreduce.wait_readers()
         sess.begin(self.rays_o.shape[0] * (n_coarse + (n_coarse + n_importance if n_importance > 0 else 0)))
         try:
             loss = self.closure()
