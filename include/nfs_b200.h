@@ -233,6 +233,15 @@ typedef struct nfs_wgrad_job {
 } nfs_wgrad_job;
 int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, void *stream);
 
+/* nfs_composite_bwd_dy: the packed backward of nfs_composite_bwd with the derivative of the MLP head folded in
+ *   (nerf_model.py:22-24: rgb = sigmoid(.), sigma raw): instead of d(rgb_sigma) [N,S,4] fp32 it writes, per sample p,
+ *   dy[p*dy_pitch + 0..2] = d_rgb * rgb * (1 - rgb) and dy[p*dy_pitch + 3] = d_sigma as bf16 - columns 0..3 of the
+ *   zero-padded [P, dy_pitch] operand of the MLP's dgrad chain and head weight gradient (the other columns are left
+ *   untouched: keep them zero).  Bit-identical to nfs_composite_bwd followed by nfs_act_grad_bf16 (act 2). */
+int nfs_composite_bwd_dy(const float *rgb_sigma, const float *z_vals, const float *rays_d, const float *g_rgb,
+                         const float *g_depth, const float *g_weights, int64_t n_rays, int32_t n_samples,
+                         int32_t white_bkgd, void *dy_bf16, int64_t dy_pitch, void *stream);
+
 /* nfs_mlp_backward_fused: the backward pass of a fused MLP chain in ONE persistent launch - the dgrad chain
  *   (arguments as the backward use of nfs_mlp_chain below: X = dy_bf16 [n_points, k_dims[0]], transposed weights in
  *   reverse order, act 4 = ReLU backward from relu_bits_in, every layer's output stored to dys_bf16

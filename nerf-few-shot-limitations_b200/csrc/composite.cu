@@ -19,6 +19,7 @@
 // The kernel is HBM-bound: 24*S+28 B/ray forward, 36*S+28 (+4*S with g_weights)
 // backward (DESIGN.md "K1").
 #include "nfs_common.cuh"
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 namespace nfs {
@@ -35,12 +36,36 @@ struct CompositeArgs {
   // backward inputs / outputs
   const float *g_rgb, *g_depth, *g_w;
   float *d_rgb, *d_density;
+  // packed backward only (nfs_composite_bwd_dy): instead of d(rgb_sigma) as fp32 the kernel writes the gradient of the
+  // MLP head's pre-activations as the bf16 GEMM operand of the dgrad chain / head weight gradient:
+  // dy[p * dy_pitch + 0..2] = d_rgb * rgb (1 - rgb) (the head's sigmoid), dy[.. + 3] = d_sigma
+  __nv_bfloat16 *dy;
+  long long dy_pitch;
   // fused loss epilogue of the forward (nfs_composite_loss_fwd); target == nullptr: plain forward
   const float *target, *target_depth;
   float rgb_coef, depth_coef;          // rgb_weight * 2 / (3 N), depth_weight / N
   float *g_rgb_out, *g_depth_out;
   double *loss_sums;                   // [kLossSlots][2]: sum (rgb - target)^2, sum |depth - target_depth|
 };
+
+// The quotient R / q of the backward's closed form, q in (0, 1].  Three builds (scripts/dev/ab_k1_div.py, 2^20 rays x 64,
+// d_density against the reference's fp32 autograd with the 3 % floor / time of the staged backward on one box):
+//   __fdividef (2 ulp)                      1.01e-5   0.400 ms      (round 1)
+//   approximate reciprocal + one Newton step  (default)             one MUFU + three FMA-pipe instructions, <= 1 ulp
+//   __fdiv_rn (-DNFS_K1_EXACT_DIV)          0.71e-5   0.433 ms      (IEEE sequence, ~10 instructions + slow path)
+__device__ __forceinline__ float k1_div(float r, float q) {
+#if defined(NFS_K1_EXACT_DIV)
+  return __fdiv_rn(r, q);
+#elif defined(NFS_K1_FAST_DIV)
+  return __fdividef(r, q);
+#else
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(q));
+  const float x0 = r * rc;
+  return fmaf(fmaf(-x0, q, r), rc, x0);          // x0 + (r - x0 q) / q: the residual is exact in the FMA
+#endif
+}
+#define NFS_K1_DIV(a, b) k1_div((a), (b))
 
 constexpr int kLossSlots = 32;
 
@@ -393,14 +418,26 @@ __global__ void __launch_bounds__(kBlock, 5) composite_bwd_kernel(const Composit
     float ds[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float dalpha = Gi[j] * T[j] - __fdividef(R[j], al.q[j]);   // q in (0, 1]: 2-ulp quotient, 1/5 of the IEEE sequence
+      const float dalpha = Gi[j] * T[j] - NFS_K1_DIV(R[j], al.q[j]);   // q in (0, 1]: 2-ulp quotient, 1/5 of the IEEE sequence
       // d alpha / d density = dists * exp(-relu(density) dists) * [density > 0]
       ds[j] = (v.sg[j] > 0.f) ? dalpha * al.dist[j] * al.e[j] : 0.f;
     }
 
     if (ray_ok && s0 < S) {
       const long long base = ray * (long long)S + s0;
-      if (PACKED) {
+      if (PACKED && a.dy != nullptr) {
+        // the arithmetic of act_grad_kernel (act 2) on the values the fp32 route would have stored: bit-identical dY
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ALIGNED || s0 + j < S) {
+            const float r = v.col[3 * j], g = v.col[3 * j + 1], b = v.col[3 * j + 2];
+            const float dr = (w[j] * gr) * r * (1.f - r), dg = (w[j] * gg) * g * (1.f - g), db = (w[j] * gb) * b * (1.f - b);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(dr, dg), hi = __floats2bfloat162_rn(db, ds[j]);
+            *reinterpret_cast<uint2 *>(a.dy + (base + j) * a.dy_pitch) =
+                make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+          }
+        }
+      } else if (PACKED) {
         float *op = a.d_rgb + base * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -555,7 +592,7 @@ __global__ void __launch_bounds__(kBlock, 4) composite_bwd_staged_kernel(const C
     float ds[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float dalpha = Gi[j] * T[j] - __fdividef(R[j], al.q[j]);
+      const float dalpha = Gi[j] * T[j] - NFS_K1_DIV(R[j], al.q[j]);
       ds[j] = (v.sg[j] > 0.f) ? dalpha * al.dist[j] * al.e[j] : 0.f;
     }
     if (ray_ok && s0 < S) {
@@ -855,4 +892,21 @@ extern "C" int nfs_composite_bwd(const float *rgb, const float *density, const f
                        (packed || (aligned16(density) && aligned16(d_density))) &&
                        (!noise || aligned16(noise)) && (!g_weights || aligned16(g_weights)) && aligned16(d_rgb);
   return dispatch<false>(a, aligned, packed != 0, (cudaStream_t)stream);
+}
+
+extern "C" int nfs_composite_bwd_dy(const float *rgb_sigma, const float *z_vals, const float *rays_d, const float *g_rgb,
+                                    const float *g_depth, const float *g_weights, int64_t n_rays, int32_t n_samples,
+                                    int32_t white_bkgd, void *dy_bf16, int64_t dy_pitch, void *stream) {
+  const char *fn = "nfs_composite_bwd_dy";
+  if (n_rays < 0 || n_samples <= 0) return fail_arg(fn, NFS_E_BADARG, "n_rays < 0 or n_samples <= 0");
+  if (n_rays == 0) return 0;
+  if (!rgb_sigma || !z_vals || !rays_d || !g_rgb || !dy_bf16) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  if (dy_pitch < 4 || (dy_pitch & 3) || (reinterpret_cast<uintptr_t>(dy_bf16) & 7u))
+    return fail_arg(fn, NFS_E_ALIGN, "dy rows must start on 8-byte boundaries (pitch % 4 == 0)");
+  CompositeArgs a{};
+  a.rgb = rgb_sigma; a.z = z_vals; a.rays_d = rays_d; a.n_rays = n_rays; a.S = n_samples; a.white = white_bkgd;
+  a.g_rgb = g_rgb; a.g_depth = g_depth; a.g_w = g_weights;
+  a.dy = static_cast<__nv_bfloat16 *>(dy_bf16); a.dy_pitch = dy_pitch;
+  const bool aligned = (n_samples % 4 == 0) && aligned16(rgb_sigma) && aligned16(z_vals) && (!g_weights || aligned16(g_weights));
+  return dispatch<false>(a, aligned, true, (cudaStream_t)stream);
 }

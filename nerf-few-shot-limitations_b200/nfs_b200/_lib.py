@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnfs_b200.so")
+LIB_PATH = os.environ.get("NFS_B200_LIB") or os.path.join(_HERE, "libnfs_b200.so")     # NFS_B200_LIB: developer A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "nfs_b200.h")
 
 _p = ctypes.c_void_p
@@ -27,6 +27,7 @@ SIGNATURES = {
     "nfs_set_debug_trace": (None, [_p]),
     "nfs_composite_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "nfs_composite_bwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "nfs_composite_bwd_dy": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _p]),
     "nfs_composite_loss_fwd": (ctypes.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _f32, _f32, _i64, _i32, _i32, _i32,
                                               _p, _p, _p, _p, _p, _p, _p]),
     "nfs_rays_generate": (ctypes.c_int, [_i32, _i32, _f32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),

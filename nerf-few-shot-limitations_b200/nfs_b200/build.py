@@ -14,13 +14,6 @@ PKG_ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(HERE, "libnfs_b200.so")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
-    # sampler arithmetic is written with explicit __f*_rn intrinsics; everything
-    # else may contract.  No --use_fast_math anywhere (accurate sincosf / expf).
-]
 
 
 def sources():
@@ -36,14 +29,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+VARIANTS = {"exactdiv": ["-DNFS_K1_EXACT_DIV"], "fastdiv": ["-DNFS_K1_FAST_DIV"]}      # developer A/B builds: libnfs_b200_<variant>.so (NFS_B200_LIB selects it)
+
+
+def build(force=False, verbose=False, variant=None):
+    if variant is not None:
+        return _build(True, verbose, os.path.join(HERE, "libnfs_b200_%s.so" % variant), "build_" + variant, VARIANTS[variant])
     if not force and not needs_build():
         return LIB_PATH
+    return _build(force, verbose, LIB_PATH, "build", [])
+
+
+def _build(force, verbose, lib_path, objdir_name, extra):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libnfs_b200.so")
     objs = []
-    objdir = os.path.join(PKG_ROOT, "build")
+    objdir = os.path.join(PKG_ROOT, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in sources():
@@ -54,7 +56,7 @@ def build(force=False, verbose=False):
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > newest:
             continue
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+               "-Xcompiler", "-fPIC", "-c", src, "-o", obj] + list(extra)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         if os.environ.get("NFS_DEVTOOLS", "0") not in ("", "0"):
@@ -66,14 +68,15 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
         if verbose and out:
             print(out)
-    tmp = LIB_PATH + ".tmp"
+    tmp = lib_path + ".tmp"
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", tmp] + objs + ["-lcuda"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                variant=sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None))

@@ -518,6 +518,7 @@ class StepSession:
             self.quad_flags = torch.zeros(rows // 512 + 2, device=dev, dtype=torch.int32)
         self.cursor = 0
         self.pending = 0
+        self.dy_written = set()
         # NFS_BWD_MERGED=1: one launch for the whole backward pass (nfs_mlp_backward_fused: dgrad chain on producer CTA
         # pairs, weight gradients on consumer CTAs fed through L2).  Parity-green but SLOWER than the default route
         # (dgrad chain per call + one weight-gradient launch per layer) on B200 - 4.6 vs 4.0 ms per cfg 3 step at the
@@ -551,7 +552,10 @@ class StepSession:
         pad = _ceil_to(P, 128)
         if pad != P:
             self.dy[r0 + P:r0 + pad].zero_()
-        dy = act_grad(out, g_out, 2, 64, dst=self.dy[r0:r0 + P])
+        if r0 in self.dy_written:
+            dy = self.dy[r0:r0 + P]          # the compositing backward has already written this call's rows (ops.composite_loss)
+        else:
+            dy = act_grad(out, g_out.contiguous(), 2, 64, dst=self.dy[r0:r0 + P])
         self.pending -= 1
         if self.merged:
             return               # flush() runs the dgrad chain of ALL calls together with the weight gradients
@@ -660,7 +664,7 @@ class _G1Fn(torch.autograd.Function):
         if ctx.slot is not None:
             (out,) = ctx.saved_tensors
             sess, r0 = ctx.slot
-            sess.backward_call(out, g_out.contiguous(), r0)
+            sess.backward_call(out, g_out, r0)
             return (None, None, None, None) + (None,) * len(ctx.plan.params())
         if ctx.fused:
             out, x16, sv, bits = ctx.saved_tensors
@@ -679,6 +683,7 @@ def g1_forward(plan, x=None, points=None, freqs=None):
     reference's calling convention) or `points` (fp32 [P,3]) + `freqs` (encoding fused into the
     operand build, never materialised in fp32)."""
     plan.refresh()
+    plan._last_slot = None
     src = x if x is not None else points
     ops._need_cuda("NeRFMLP", src)
     if src.requires_grad and torch.is_grad_enabled():
@@ -707,9 +712,11 @@ def g1_forward(plan, x=None, points=None, freqs=None):
         enc_in_kernel = (fused_ok and len(plan.packed) >= 2 and plan.k0 == 64 and flat.shape[-1] == 3
                          and 1 <= int(freqs.numel()) <= 10 and bands_are_octaves(freqs)
                          and os.environ.get("NFS_MLP_FUSED_ENC", "1") != "0")
+        plan._last_slot = None
         if sess is not None:
             r0 = sess.take(P)
             extra = {"slot": (sess, r0)}
+            plan._last_slot = (sess, r0)      # pipeline.render_rays hands it to the compositing backward (dY written in place)
             dst = sess.x16[r0:r0 + P]
         elif enc_in_kernel:
             dst = torch.empty((_ceil_to(P, 128), plan.k0), device=flat.device, dtype=torch.bfloat16)[:P]

@@ -127,7 +127,7 @@ class _CompositeLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rgb, density, z_vals, rays_d, target, target_depth, rgb_weight, depth_weight, white_bkgd,
-                packed, want_weights):
+                packed, want_weights, dy_slot=None):
         n_samples = z_vals.shape[-1]
         n_rays = z_vals.numel() // n_samples
         dev = z_vals.device
@@ -148,6 +148,7 @@ class _CompositeLossFn(torch.autograd.Function):
         loss = rgb_weight * mse if l1 is None else rgb_weight * mse + depth_weight * l1
         ctx.save_for_backward(rgb, density, z_vals, rays_d, g_rgb, g_depth)
         ctx.cfg = (int(bool(white_bkgd)), int(bool(packed)), n_rays, n_samples)
+        ctx.dy_slot = dy_slot if packed else None
         outs = (loss, mse, l1, out_rgb, out_depth, out_w)
         ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
         ctx.set_materialize_grads(False)
@@ -157,12 +158,24 @@ class _CompositeLossFn(torch.autograd.Function):
     def backward(ctx, g_loss, *_unused):
         rgb, density, z_vals, rays_d, g_rgb, g_depth = ctx.saved_tensors
         white, packed, n_rays, n_samples = ctx.cfg
-        none = (None,) * 9
+        none = (None,) * 10
         if g_loss is None:
             return (None, None) + none
         g_rgb = g_rgb * g_loss
         if g_depth is not None:
             g_depth = g_depth * g_loss
+        if ctx.dy_slot is not None:
+            # `rgb` is the packed output of an MLP call that runs inside a mlp.StepSession: write the gradient of the
+            # head's pre-activations straight into the session's bf16 operand (nfs_composite_bwd_dy) - no fp32
+            # d(rgb_sigma) tensor, no nfs_act_grad_bf16 launch.  The MLP's backward only needs to be triggered: it
+            # receives a stride-0 placeholder.
+            sess, r0 = ctx.dy_slot
+            P = n_rays * n_samples
+            with torch.cuda.device(z_vals.device):
+                _lib.call("nfs_composite_bwd_dy", ptr(rgb), ptr(z_vals), ptr(rays_d), ptr(g_rgb), ptr(g_depth), None, n_rays,
+                          n_samples, white, ptr(sess.dy[r0:r0 + P]), int(sess.dy.stride(0)), _stream())
+            sess.dy_written.add(r0)
+            return (_placeholder(rgb), None) + none
         d_rgb = torch.empty_like(rgb)
         d_density = None if packed else torch.empty_like(density)
         with torch.cuda.device(z_vals.device):
@@ -171,8 +184,20 @@ class _CompositeLossFn(torch.autograd.Function):
         return (d_rgb, d_density) + none
 
 
+_PLACEHOLDERS = {}
+
+
+def _placeholder(like):
+    """A zero 'gradient' of like's shape that owns one element (stride 0 everywhere)."""
+    key = (str(like.device), like.dtype)
+    z = _PLACEHOLDERS.get(key)
+    if z is None:
+        z = _PLACEHOLDERS[key] = torch.zeros((), device=like.device, dtype=like.dtype)
+    return z.expand(like.shape)
+
+
 def composite_loss(rgb, density, z_vals, rays_d, target_rgb, target_depth=None, rgb_weight=1.0, depth_weight=0.1,
-                   white_bkgd=False, want_weights=False):
+                   white_bkgd=False, want_weights=False, dy_slot=None):
     """VolumeRenderer.forward (nerf_mlp.py:165-215) followed by the rgb / depth terms of NeRFLoss
     (nerf_mlp.py:225-258; train.py:36-44 is the rgb term alone) in ONE kernel.
 
@@ -196,7 +221,7 @@ def composite_loss(rgb, density, z_vals, rays_d, target_rgb, target_depth=None, 
         raise RuntimeError("composite_loss: empty batch (the mean of no pixels is undefined)")
     loss, mse, l1, o_rgb, o_depth, o_w = _CompositeLossFn.apply(
         _f32c(rgb), _f32c(density), _f32c(z_vals), _f32c(rays_d), _f32c(target_rgb), _f32c(target_depth),
-        float(rgb_weight), float(depth_weight), white_bkgd, packed, want_weights)
+        float(rgb_weight), float(depth_weight), white_bkgd, packed, want_weights, dy_slot)
     out = {"total": loss, "rgb": mse, "rgb_map": o_rgb, "depth_map": o_depth}
     if l1 is not None:
         out["depth"] = l1

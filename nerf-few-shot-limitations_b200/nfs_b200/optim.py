@@ -78,12 +78,41 @@ class FusedAdam:
                       int(bool(self.decoupled)), _stream())
         mlp.bump_weight_epoch()          # cached bf16 operand copies are stale now
 
-    def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+    def state_dict(self, torch_format=False):
+        """Flat form (default), or - torch_format=True - the layout of torch.optim.Adam.state_dict(): per-parameter
+        {'step', 'exp_avg', 'exp_avg_sq'} (slices of the flat moments) + one param_group, interchangeable with the
+        reference's optimizer (train.py:114-118, 378)."""
+        if not torch_format:
+            return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                    "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+        step, state, off = self.step_count, {}, 0
+        for i, (p, k) in enumerate(zip(self.params, self.sizes)):
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
+            off += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": bool(self.decoupled), "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
+        """Accepts both forms of state_dict() (and therefore torch.optim.Adam's)."""
+        if "param_groups" in sd:
+            st = sd["state"]
+            off, step = 0, 0
+            for i, (p, k) in enumerate(zip(self.params, self.sizes)):
+                if i in st:
+                    self.exp_avg[off:off + k].copy_(st[i]["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + k].copy_(st[i]["exp_avg_sq"].reshape(-1))
+                    step = int(float(st[i]["step"]))
+                else:
+                    self.exp_avg[off:off + k].zero_()
+                    self.exp_avg_sq[off:off + k].zero_()
+                off += k
+            self._step_dev.fill_(step)
+            self.set_lr(sd["param_groups"][0].get("lr", self.lr))
+            return
         self._step_dev.fill_(int(sd["step"]))
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.lr = sd.get("lr", self.lr)
+        self.set_lr(sd.get("lr", self.lr))

@@ -31,7 +31,8 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
     raw = model.forward_points(pts.reshape(-1, 3), freq_bands).reshape(N, n_coarse, 4)
     loss = None
     if target is not None:
-        c = ops.composite_loss(raw, None, z, rays_d, target, None, 1.0, 0.0, white_bkgd, want_weights=n_importance > 0)
+        c = ops.composite_loss(raw, None, z, rays_d, target, None, 1.0, 0.0, white_bkgd, want_weights=n_importance > 0,
+                               dy_slot=_dy_slot(model))
         rgb, depth, weights, loss = c["rgb_map"], c["depth_map"], c.get("weights"), c["total"]
     else:
         rgb, depth, weights = ops.composite_packed(raw, z, rays_d, white_bkgd=white_bkgd, want_aux=True)
@@ -46,7 +47,7 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
         S = n_coarse + n_importance
         raw_f = model.forward_points(pts_f.reshape(-1, 3), freq_bands).reshape(N, S, 4)
         if target is not None:
-            c = ops.composite_loss(raw_f, None, z_f, rays_d, target, None, 1.0, 0.0, white_bkgd)
+            c = ops.composite_loss(raw_f, None, z_f, rays_d, target, None, 1.0, 0.0, white_bkgd, dy_slot=_dy_slot(model))
             rgb_f, depth_f, w_f, loss = c["rgb_map"], c["depth_map"], None, loss + c["total"]
         else:
             rgb_f, depth_f, w_f = ops.composite_packed(raw_f, z_f, rays_d, white_bkgd=white_bkgd, want_aux=True)
@@ -54,6 +55,16 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
     if loss is not None:
         out["loss"] = loss
     return out
+
+
+def _dy_slot(model):
+    """(StepSession, first row) of the model's last forward_points call when it ran inside a step session and autograd
+    is recording: the compositing backward then writes the MLP head's bf16 gradient operand in place."""
+    import os
+    if not torch.is_grad_enabled() or os.environ.get("NFS_K1_BWD_DY", "1") == "0":
+        return None
+    get = getattr(model, "_get_plan", None)
+    return getattr(get(), "_last_slot", None) if get is not None else None
 
 
 def train_step(model, optimizer, freq_bands, rays_o, rays_d, target, near, far, n_coarse=64, n_importance=128,

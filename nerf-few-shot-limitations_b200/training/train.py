@@ -9,6 +9,10 @@ checkpoint keys (train.py:46-406) and applies the minimal repairs:
   B5     utils.ray_utils.get_rays builds its grid on the pose's device;
   B6     torchmetrics / lpips / imageio / wandb are absent offline: PSNR = -10 log10(mse), SSIM from a Gaussian
          window in torch, LPIPS not computed (NaN), PNGs through PIL when present, no wandb.
+Beyond the reference (which is single-device and launches every op eagerly): each optimisation step is captured
+once per batch shape into a CUDA graph and replayed (training.cuda_graph, default on), and under torchrun the
+batch of every step is sharded over the ranks (one process per GPU; every rank walks the same permutation, the
+weight gradient is summed in the fused peer-memory Adam step of nfs_b200.dist or by NCCL).
 Everything per ray runs on the CUDA kernels of this package (there is no CPU path); the Dinov2 feature
 extractor (per-view preprocessing, needs downloaded weights) is outside the hot path: with use_dino the
 trainer takes precomputed (1, Hp, Wp, C) feature maps through set_feature_maps().
@@ -30,7 +34,9 @@ from models.data_loader import load_blender_data  # noqa: E402
 from models.nerf_mlp import VolumeRenderer  # noqa: E402
 from models.nerf_model import NeRFMLP  # noqa: E402
 from models.ray_sampler import sample_points_along_rays  # noqa: E402
+from nfs_b200 import dist as _nd  # noqa: E402
 from nfs_b200 import ops as _ops  # noqa: E402
+from nfs_b200 import pipeline as _pipeline  # noqa: E402
 from nfs_b200.optim import FusedAdam  # noqa: E402
 from utils.ray_utils import get_rays  # noqa: E402
 
@@ -143,6 +149,16 @@ class NeRFDINOTrainer:
         self.near, self.far = near_far(config)
         self.epoch = 0
         self.best_psnr = 0.0
+        # data parallel: one process per GPU under torchrun, rays sharded per batch
+        self.rank, self.world = 0, 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.exchange = _nd.make_allreduce(self.optimizer) if self.world > 1 else None
+        self.use_graph = bool(config["training"].get("cuda_graph", True))
+        self._graphs = {}
+        self._perm_gen = torch.Generator(device=self.device)
+        self._perm_gen.manual_seed(int(config.get("experiment", {}).get("seed", 0)))      # same permutations on every rank
 
     # ------------------------------------------------------------------ data
     def load_data(self, data_path, split="train", max_views=None):
@@ -226,18 +242,65 @@ class NeRFDINOTrainer:
                 target = F.interpolate(target.permute(2, 0, 1).unsqueeze(0), size=(h_t, w_t), mode="bilinear",
                                        align_corners=False).squeeze(0).permute(1, 2, 0)
             target = target.contiguous()
-            perm = torch.randperm(h_t * w_t, device=self.device)
+            perm = torch.randperm(h_t * w_t, device=self.device, generator=self._perm_gen)
             for i in range(0, perm.shape[0], batch):
-                b = perm[i:i + batch]
-                ro_b, rd_b, tg_b = _ops.generate_rays(h_t, w_t, focal_t, self.poses[view_idx], pix_idx=b, image=target)
-                pred = self.render_rays(ro_b, rd_b, view_idx, n_samples)
-                loss = sum(self.criterion(pred, {"rgb": tg_b}).values())
-                self.optimizer.zero_grad()
-                loss.backward()
-                self.optimizer.step()
-                total += loss.detach()              # one host sync per epoch instead of one per batch (train.py:289)
+                n_global = min(batch, perm.shape[0] - i)
+                b = _nd.shard_batch(perm, i, batch, self.rank, self.world)       # this rank's rays of the global batch
+                loss = self._optimise(b, n_global, view_idx, h_t, w_t, focal_t, target, n_samples)
+                total += loss                       # one host sync per epoch instead of one per batch (train.py:289)
                 n_batches += 1
         return float(total) / n_batches if n_batches else 0.0
+
+    # ------------------------------------------------------------------ one optimisation step (train.py:280-287)
+    def _batch_loss(self, idx, view_idx, h_t, w_t, focal_t, target, n_samples, pose=None):
+        ro_b, rd_b, tg_b = _ops.generate_rays(h_t, w_t, focal_t, self.poses[view_idx] if pose is None else pose,
+                                              pix_idx=idx, image=target)
+        pred = self.render_rays(ro_b, rd_b, view_idx, n_samples)
+        return sum(self.criterion(pred, {"rgb": tg_b}).values())
+
+    def _optimise(self, idx, n_global, view_idx, h_t, w_t, focal_t, target, n_samples):
+        """zero_grad / loss / backward / (gradient exchange) / optimizer.step for this rank's `idx` pixels of a global
+        batch of n_global; the mean over the global batch is sum over ranks of local_mean * local/global.  Every batch
+        shape (the full batches' and the tail's of a permutation) replays a CUDA graph captured once; training.cuda_graph
+        = false and the feature-conditioned model launch eagerly.
+        Returns the detached local loss (a device tensor)."""
+        n_local = int(idx.numel())
+        scale = _nd.loss_scale(n_local, n_global)
+        ex = self.exchange
+        fused = bool(getattr(ex, "in_graph", False))
+        graphable = self.use_graph and n_local > 0 and not self.use_dino      # conditioned model: per-view maps vary in shape
+        if graphable:
+            key = (h_t, w_t, n_samples, n_local, n_global)
+            g = self._graphs.get(key)
+            if g is None:
+                st = {"idx": idx.clone(), "pose": self.poses[view_idx].clone(), "target": target.clone(), "view": -1}
+                closure = lambda: self._batch_loss(st["idx"], 0, h_t, w_t, focal_t, st["target"], n_samples, pose=st["pose"])
+                st["step"] = _pipeline.GraphedStep(self.optimizer, closure, loss_scale=scale, allreduce=ex)
+                g = self._graphs[key] = st
+            g["idx"].copy_(idx)
+            if g["view"] != (view_idx, self.epoch):
+                g["pose"].copy_(self.poses[view_idx])
+                g["target"].copy_(target)
+                g["view"] = (view_idx, self.epoch)
+            return g["step"].replay().clone()
+        opt = self.optimizer
+        opt.zero_grad()
+        if fused:
+            ex.wait_readers()
+        if n_local > 0:
+            loss = self._batch_loss(idx, view_idx, h_t, w_t, focal_t, target, n_samples)
+            (loss * scale if scale != 1.0 else loss).backward()
+            out = loss.detach()
+        else:
+            out = torch.zeros((), device=self.device)
+        opt.gather_grads()
+        if fused:
+            ex.fused_step()
+        else:
+            if ex is not None:
+                ex(opt.grad)
+            opt.step(gathered=True)
+        return out
 
     @torch.no_grad()
     def evaluate(self, epoch):
@@ -251,10 +314,11 @@ class NeRFDINOTrainer:
             ro, rd = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
             parts = [self.render_rays(ro[j:j + chunk], rd[j:j + chunk], 0, n_eval)["rgb"] for j in range(0, ro.shape[0], chunk)]
             img = torch.cat(parts, 0).reshape(self.H, self.W, 3)
-            mse = F.mse_loss(img.clamp(0, 1), target)
+            # metrics on the UNCLAMPED rendering, as train.py:321-326 computes them (data_range 1.0); only the PNG is clamped
+            mse = F.mse_loss(img, target)
             psnrs.append(float(-10.0 * torch.log10(mse.clamp_min(1e-12))))
-            ssims.append(ssim(img.clamp(0, 1).permute(2, 0, 1).unsqueeze(0), target.permute(2, 0, 1).unsqueeze(0)))
-            if i < 5:
+            ssims.append(ssim(img.permute(2, 0, 1).unsqueeze(0), target.permute(2, 0, 1).unsqueeze(0)))
+            if i < 5 and self.rank == 0:
                 try:
                     from PIL import Image
                     os.makedirs(out_dir, exist_ok=True)
@@ -270,29 +334,50 @@ class NeRFDINOTrainer:
             loss = self.train_step(epoch)
             self.sched_epoch += 1                                                          # scheduler.step()
             self.optimizer.lr = multistep_lr(self.base_lr, self.milestones, self.gamma, self.sched_epoch)
-            print("Epoch %d/%d | Train Loss: %.4f | LR: %.2e" % (epoch + 1, epochs, loss, self.optimizer.lr))
+            if self.rank == 0:
+                print("Epoch %d/%d | Train Loss: %.4f | LR: %.2e" % (epoch + 1, epochs, loss, self.optimizer.lr))
             if (epoch + 1) % self.config["output"]["val_freq"] == 0:
                 m = self.evaluate(epoch)
-                print("Validation PSNR: %.2f, SSIM: %.2f" % (m["psnr"], m["ssim"]))
+                if self.rank == 0:
+                    print("Validation PSNR: %.2f, SSIM: %.2f" % (m["psnr"], m["ssim"]))
                 if m["psnr"] > self.best_psnr:
                     self.best_psnr = m["psnr"]
-                    self.save_checkpoint("best_%s.pth" % self.config["experiment"]["name"])
-            if (epoch + 1) % self.config["output"]["save_freq"] == 0:
+                    if self.rank == 0:
+                        self.save_checkpoint("best_%s.pth" % self.config["experiment"]["name"])
+            if (epoch + 1) % self.config["output"]["save_freq"] == 0 and self.rank == 0:
                 self.save_checkpoint("epoch_%d.pth" % (epoch + 1))
-        print("Training completed. Best PSNR: %.2f" % self.best_psnr)
+        if self.rank == 0:
+            print("Training completed. Best PSNR: %.2f" % self.best_psnr)
 
     def save_checkpoint(self, filename):
-        """Same keys as train.py:374-389 (no 'dino_model_state_dict': the extractor is not part of this trainer)."""
+        """Same keys as train.py:374-389 (no 'dino_model_state_dict': the extractor is not part of this trainer).
+        optimizer_state_dict / scheduler_state_dict have the layouts of torch.optim.Adam.state_dict() and
+        MultiStepLR.state_dict(), so a checkpoint loads into the reference's optimizer / scheduler and vice versa."""
+        from collections import Counter
         ckpt = {"epoch": self.epoch, "best_psnr": self.best_psnr,
                 "nerf_model_state_dict": self.nerf_model.state_dict(),
-                "optimizer_state_dict": self.optimizer.state_dict(),
-                "scheduler_state_dict": {"last_epoch": self.sched_epoch, "milestones": self.milestones,
-                                         "gamma": self.gamma, "base_lr": self.base_lr},
+                "optimizer_state_dict": self.optimizer.state_dict(torch_format=True),
+                "scheduler_state_dict": {"milestones": Counter(self.milestones), "gamma": self.gamma,
+                                         "base_lrs": [self.base_lr], "last_epoch": self.sched_epoch,
+                                         "_step_count": self.sched_epoch + 1, "_get_lr_called_within_step": False,
+                                         "_last_lr": [self.optimizer.lr]},
                 "config": self.config}
         path = os.path.join(self.config["output"]["save_dir"], filename)
         os.makedirs(os.path.dirname(path), exist_ok=True)
         torch.save(ckpt, path)
         return path
+
+    def load_checkpoint(self, path):
+        """Resume from a checkpoint written by save_checkpoint() or by the reference's trainer (train.py:374-389)."""
+        ckpt = torch.load(path, map_location=self.device, weights_only=False)
+        self.nerf_model.load_state_dict(ckpt["nerf_model_state_dict"])
+        self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        sd = ckpt.get("scheduler_state_dict", {})
+        self.sched_epoch = int(sd.get("last_epoch", 0))
+        self.optimizer.set_lr(multistep_lr(self.base_lr, self.milestones, self.gamma, self.sched_epoch))
+        self.epoch = int(ckpt.get("epoch", -1)) + 1
+        self.best_psnr = float(ckpt.get("best_psnr", 0.0))
+        return ckpt
 
 
 def main():
@@ -305,7 +390,12 @@ def main():
     args = ap.parse_args()
     with open(args.config) as f:
         config = yaml.safe_load(f)
-    trainer = NeRFDINOTrainer(config)
+    rank, world, local_rank = _nd.world()
+    if world > 1:                                    # torchrun --nproc-per-node G: one process per GPU
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    trainer = NeRFDINOTrainer(config, device=torch.device("cuda", local_rank) if world > 1 else None)
     if args.synthetic:
         trainer.load_synthetic()
     else:

@@ -206,3 +206,56 @@ def test_step_session_matches_per_call_gradients(cuda, monkeypatch, n_rays, n_co
     record("step_session_vs_per_call", n_rays=n_rays, n_coarse=n_coarse, n_imp=n_imp, grad_rel_l2=rel,
            merged_grad_rel_l2=rel_x, merged_vs_split_rel_l2=rel_sx)
     assert rel <= 1e-4 and rel_x <= 1e-4 and rel_sx <= 1e-4, (rel, rel_x, rel_sx)
+
+
+@pytest.mark.parametrize("S,white", [(64, False), (192, True), (37, False)])
+def test_composite_bwd_dy_bit_identical_to_two_kernel_route(cuda, S, white):
+    """nfs_composite_bwd_dy (compositing backward + derivative of the MLP head, bf16 operand rows written in place)
+    against nfs_composite_bwd (packed) followed by nfs_act_grad_bf16: bit-identical columns 0..3, other columns untouched."""
+    from nfs_b200 import _lib, mlp, ops
+    from nfs_b200._lib import ptr
+    g = torch.Generator().manual_seed(S)
+    n = 1500
+    raw = torch.cat([torch.rand(n, S, 3, generator=g), torch.randn(n, S, 1, generator=g) * 5], -1).to(cuda)
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), -1).values.to(cuda)
+    _, rd = O.lego_rays(n, seed=S)
+    rd = rd.to(cuda)
+    g_rgb, g_depth = torch.randn(n, 3, generator=g).to(cuda), torch.randn(n, generator=g).to(cuda)
+    d_raw = torch.empty_like(raw)
+    stream = ops._stream()
+    _lib.call("nfs_composite_bwd", ptr(raw), None, ptr(z), ptr(rd), None, 0.0, ptr(g_rgb), ptr(g_depth), None, n, S, int(white), 1,
+              ptr(d_raw), None, stream)
+    want = mlp.act_grad(raw.reshape(-1, 4), d_raw.reshape(-1, 4), 2, 64)
+    got = torch.full((n * S, 64), 7.0, device=cuda, dtype=torch.bfloat16)
+    _lib.call("nfs_composite_bwd_dy", ptr(raw), ptr(z), ptr(rd), ptr(g_rgb), ptr(g_depth), None, n, S, int(white), ptr(got), 64,
+              stream)
+    assert torch.equal(got[:, :4].view(torch.int16), want[:, :4].view(torch.int16))
+    assert bool((got[:, 4:] == 7.0).all())
+
+
+def test_session_with_and_without_in_place_dy(cuda, monkeypatch):
+    """The training step with the compositing backward writing dY in place (default) against the fp32 d(rgb_sigma) +
+    nfs_act_grad_bf16 route: same loss, gradients equal up to the weight-gradient kernels' atomics."""
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import pipeline
+    from nfs_b200.optim import FusedAdam
+    n = 700
+    ro, rd = O.lego_rays(n, seed=8)
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    tgt = torch.rand(n, 3, generator=torch.Generator().manual_seed(4)).to(cuda)
+    bands = O.frequency_bands(10)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NFS_K1_BWD_DY", mode)
+        torch.manual_seed(3)
+        model = NeRFMLP().to(cuda).train()
+        with torch.no_grad():
+            model.sigma_out.bias.fill_(0.3)
+        opt = FusedAdam(model.parameters(), lr=5e-4)
+        torch.manual_seed(11)
+        loss = pipeline.train_step(model, opt, bands, ro, rd, tgt, 2.0, 6.0, 48, 80)
+        res[mode] = (float(loss), opt.grad.clone())
+    assert res["1"][0] == res["0"][0]
+    rel = float((res["1"][1] - res["0"][1]).norm() / res["0"][1].norm())
+    record("step_in_place_dy_vs_act_grad", grad_rel_l2=rel)
+    assert rel <= 1e-5, rel

@@ -111,3 +111,117 @@ def test_trainer_with_feature_maps(cuda, tmp_path):
     l0 = tr.train_step(0)
     l1 = tr.train_step(1)
     assert l1 == l1 and l1 < l0 * 1.5
+
+
+def _live_trainer(cfg, cuda, graph):
+    """A trainer whose random-init density is alive (see test_trainer_runs_baseline_config)."""
+    from training.train import NeRFDINOTrainer
+    cfg = copy.deepcopy(cfg)
+    cfg["training"]["cuda_graph"] = graph
+    for seed in range(40):
+        torch.manual_seed(seed)
+        tr = NeRFDINOTrainer(cfg, device=cuda)
+        probe = (torch.rand(4096, 3, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1)) - 0.5) * 2.5
+        with torch.no_grad():
+            _, den = tr.nerf_model(probe, torch.ones(4096, 3, device=cuda), None)
+        if float((den > 0).float().mean()) > 0.2:
+            return tr, seed
+    pytest.skip("no seed with a live initial density in 40 tries")
+
+
+@pytest.mark.gpu
+def test_trainer_graph_replay_matches_eager_and_resumes(cuda, tmp_path):
+    """training.cuda_graph: every full batch replays a CUDA graph captured once per batch shape - same losses as the
+    eager launches (up to the atomics of the weight-gradient kernels); a changed learning rate reaches the replays;
+    checkpoints carry torch.optim.Adam / MultiStepLR layouts and resume."""
+    cfg = copy.deepcopy(BASELINE)
+    cfg["data"]["resolution"] = 32
+    cfg["data"]["num_views"] = 2
+    cfg["training"]["batch_size"] = 200                 # 32*32 = 1024 pixels: two full batches of 400 + a tail of 224
+    cfg["output"] = {"save_dir": str(tmp_path), "val_freq": 100, "save_freq": 100}
+    losses = {}
+    for graph in (True, False):
+        tr, seed = _live_trainer(cfg, cuda, graph)
+        tr.load_synthetic(n_test=1)
+        torch.manual_seed(123)
+        losses[graph] = [tr.train_step(e) for e in range(3)]
+        if graph:
+            assert len(tr._graphs) == 2 and tr.use_graph          # the full batches' shape and the ragged tail's
+            tr_g = tr
+    a, b = torch.tensor(losses[True]), torch.tensor(losses[False])
+    assert float(((a - b).abs() / b.abs()).max()) <= 2e-2, (losses[True], losses[False])
+    assert losses[True][-1] < losses[True][0]
+    # learning rate: a scheduler step must reach the captured Adam kernel
+    w0 = tr_g.optimizer.flat.clone()
+    tr_g.optimizer.lr = 0.0
+    tr_g.train_step(3)
+    assert torch.equal(tr_g.optimizer.flat, w0), "lr = 0 must freeze the weights of a replayed step"
+    tr_g.optimizer.lr = 5e-4
+    # checkpoint: torch layouts, loadable by torch.optim.Adam on the oracle's restatement of the reference model
+    tr_g.sched_epoch = 7
+    path = tr_g.save_checkpoint("ck.pth")
+    ck = torch.load(path, weights_only=False)
+    from oracle import nerf_oracle as O
+    ref = O.ConditionedNeRF(dino_dim=0)
+    ref.load_state_dict(ck["nerf_model_state_dict"])
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    ref_opt.load_state_dict(ck["optimizer_state_dict"])
+    assert abs(ref_opt.param_groups[0]["lr"] - 5e-4) < 1e-12
+    sched = torch.optim.lr_scheduler.MultiStepLR(ref_opt, milestones=[100, 150], gamma=0.5)
+    sched.load_state_dict(ck["scheduler_state_dict"])
+    assert sched.last_epoch == 7
+    tr2, _ = _live_trainer(cfg, cuda, True)
+    tr2.load_checkpoint(path)
+    assert tr2.sched_epoch == 7 and tr2.optimizer.step_count == tr_g.optimizer.step_count
+    assert torch.equal(tr2.optimizer.flat, tr_g.optimizer.flat) and torch.equal(tr2.optimizer.exp_avg, tr_g.optimizer.exp_avg)
+
+
+def _ddp_trainer_worker(rank, world, port, cfg, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    import training.train as T
+    from training.train import NeRFDINOTrainer
+    sampler = T.sample_points_along_rays      # no stratified jitter: the draws would depend on the shard shapes
+    T.sample_points_along_rays = lambda ro, rd, near, far, n, perturb=True: sampler(ro, rd, near, far, n, perturb=False)
+    torch.manual_seed(cfg["experiment"]["seed"])
+    tr = NeRFDINOTrainer(cfg, device=torch.device("cuda", rank))
+    with torch.no_grad():                     # keep the random-init density alive (same value on every rank)
+        tr.nerf_model.density_mlp.density_head.bias.fill_(0.5)
+    tr.load_synthetic(n_test=1)
+    torch.manual_seed(5)
+    losses = [tr.train_step(e) for e in range(2)]
+    if world > 1:
+        t = torch.tensor(losses, device="cuda")
+        dist.all_reduce(t)                    # local losses are means over the local shard: average them
+        losses = (t / world).tolist()
+    if rank == 0:
+        torch.save({"losses": losses, "flat": tr.optimizer.flat.detach().cpu(),
+                    "exchange": getattr(tr.exchange, "describe", "none")}, out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_trainer_two_ranks_match_one(tmp_path):
+    """torchrun-style data parallel: 2 ranks, each with half of every batch (perturb off -> no rank-dependent draws),
+    end at the weights of 1 rank with the whole batch."""
+    import torch.multiprocessing as mp
+    cfg = copy.deepcopy(BASELINE)
+    cfg["experiment"]["seed"] = 3
+    cfg["data"]["resolution"] = 32
+    cfg["data"]["num_views"] = 2
+    cfg["training"]["batch_size"] = 256
+    cfg["output"] = {"save_dir": str(tmp_path), "val_freq": 100, "save_freq": 100}
+    res = {}
+    for world in (1, 2):
+        out = str(tmp_path / ("w%d.pt" % world))
+        mp.spawn(_ddp_trainer_worker, args=(world, 29650 + world, cfg, out), nprocs=world, join=True)
+        res[world] = torch.load(out)
+    a, b = res[2]["flat"], res[1]["flat"]
+    rel = float((a - b).norm() / b.norm())
+    assert rel <= 2e-2, (rel, res[1]["losses"], res[2]["losses"], res[2]["exchange"])
