@@ -233,6 +233,42 @@ typedef struct nfs_wgrad_job {
 } nfs_wgrad_job;
 int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, void *stream);
 
+/* nfs_mlp_chain_rays: nfs_mlp_chain_points[_train] with the SAMPLER fused in as well - point p is sample p % n_samples
+ *   of ray p / n_samples at rays_o + rays_d * z_vals[p] (ray_utils.py:82 / ray_sampler.py:58, evaluated un-contracted by
+ *   the warps that build the first layer's operand), so the (P,3) positions never exist in HBM.  x_bf16_out / save_bf16 /
+ *   relu_bits_out all NULL: inference; x_bf16_out + save_bf16 (+ relu_bits_out): forward of a training step. */
+int nfs_mlp_chain_rays(const float *rays_o, const float *rays_d, const float *z_vals, int64_t n_rays,
+                       int32_t n_samples, float freq0, int32_t n_octaves, int32_t n_layers,
+                       const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                       const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16, void *x_bf16_out,
+                       void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                       int32_t out_cols, void *stream);
+
+/* nfs_render_fused_fwd: the whole render path of a ray batch in one call (train.py:188-242 + ray_utils.py:86-143 for the
+ *   plain model): stratified depths (nfs_sample_stratified's tables / draws) -> sampler + encoding + MLP in one kernel
+ *   (nfs_mlp_chain_rays) -> compositing; with n_importance > 0 also inverse-CDF resampling on weights[..., :-1] (u,
+ *   u_stride as nfs_sample_hierarchical) -> MLP over the merged n_coarse + n_importance depths -> compositing.
+ *   model: the packed operands of the fused chain (HOST struct, fields as the nfs_mlp_chain arguments of the same name).
+ *   Workspace / outputs (device, caller-owned): z_coarse [N,Sc], raw_coarse [N,Sc,4], weights_coarse [N,Sc] (NULL allowed
+ *   when n_importance == 0), bin_weights [N,Sc-1] scratch, rgb_coarse [N,3], depth_coarse [N]|NULL; fine pass: z_fine
+ *   [N,Sf], raw_fine [N,Sf,4], weights_fine [N,Sf]|NULL, rgb_fine [N,3], depth_fine [N]|NULL (Sf = Sc + n_importance).
+ *   Sample positions, encodings and hidden activations never reach HBM. */
+typedef struct nfs_chain_model {
+  int32_t n_layers;
+  const int32_t *k_dims, *n_dims, *acts, *row0;
+  const void *w_stack_bf16;
+  int32_t w_rows;
+  const void *bias_terms_bf16;
+  float freq0;
+  int32_t n_octaves;
+} nfs_chain_model;
+int nfs_render_fused_fwd(const nfs_chain_model *model, const float *rays_o, const float *rays_d, int64_t n_rays,
+                         int32_t n_coarse, const float *z_base, const float *lower, const float *upper,
+                         const float *t_rand, int32_t n_importance, const float *u, int64_t u_stride,
+                         int32_t white_bkgd, float *z_coarse, float *raw_coarse, float *weights_coarse,
+                         float *bin_weights, float *rgb_coarse, float *depth_coarse, float *z_fine,
+                         float *raw_fine, float *weights_fine, float *rgb_fine, float *depth_fine, void *stream);
+
 /* nfs_composite_bwd_dy: the packed backward of nfs_composite_bwd with the derivative of the MLP head folded in
  *   (nerf_model.py:22-24: rgb = sigmoid(.), sigma raw): instead of d(rgb_sigma) [N,S,4] fp32 it writes, per sample p,
  *   dy[p*dy_pitch + 0..2] = d_rgb * rgb * (1 - rgb) and dy[p*dy_pitch + 3] = d_sigma as bf16 - columns 0..3 of the

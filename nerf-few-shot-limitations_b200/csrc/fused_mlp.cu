@@ -23,20 +23,8 @@ static unsigned long long *g_fm_trace = nullptr;
 extern "C" void nfs_set_debug_flags(int32_t flags) { g_fm_debug = flags; }
 extern "C" void nfs_set_debug_trace(void *buf) { g_fm_trace = (unsigned long long *)buf; }
 
-static int launch_chain(const char *fn, const void *x_bf16, const float *points, float freq0, int n_octaves,
-                        int64_t n_points, int32_t n_layers, const int32_t *k_dims,
-                        const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
-                        const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16,
-                        const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
-                        void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
-                        int32_t out_cols, void *stream) {
-  FusedArgs a{};
-  CUtensorMap tx{}, tw{}, ts{}, tb{};
-  int rc = chain_prepare(fn, x_bf16, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
-                         w_rows, bias_terms_bf16, relu_bits_in, bits_rows_per_layer, mask_idx, save_bf16, relu_bits_out,
-                         save_rows_per_layer, out_f32, out_cols, &a, &tx, &tw, &ts, &tb);
-  if (rc == 1) return 0;
-  if (rc) return rc;
+static int launch_prepared(const char *fn, FusedArgs a, const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &ts,
+                           const CUtensorMap &tb, bool train, void *stream, bool dgrad = false) {
   a.dbg = g_fm_debug;
   a.trace = g_fm_trace;
   const size_t smem = kChainSmemBytes;
@@ -53,16 +41,34 @@ static int launch_chain(const char *fn, const void *x_bf16, const float *points,
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_quads = ((n_points + 127) / 128 + 3) / 4;
+  const long long n_quads = ((a.P + 127) / 128 + 3) / 4;
   const long long max_pairs = sms / 2;
   const unsigned grid = 2u * (unsigned)(n_quads < max_pairs ? n_quads : max_pairs);   // whole CTA pairs
-  if (relu_bits_in != nullptr)
+  if (dgrad)
     fused_mlp_kernel<true, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
-  else if (a.save || relu_bits_out)
+  else if (train)
     fused_mlp_kernel<false, true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
   else
     fused_mlp_kernel<false, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
   return check_launch(fn);
+}
+
+
+static int launch_chain(const char *fn, const void *x_bf16, const float *points, float freq0, int n_octaves,
+                        int64_t n_points, int32_t n_layers, const int32_t *k_dims,
+                        const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                        const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16,
+                        const void *relu_bits_in, int64_t bits_rows_per_layer, const int32_t *mask_idx,
+                        void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                        int32_t out_cols, void *stream) {
+  FusedArgs a{};
+  CUtensorMap tx{}, tw{}, ts{}, tb{};
+  int rc = chain_prepare(fn, x_bf16, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
+                         w_rows, bias_terms_bf16, relu_bits_in, bits_rows_per_layer, mask_idx, save_bf16, relu_bits_out,
+                         save_rows_per_layer, out_f32, out_cols, &a, &tx, &tw, &ts, &tb);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  return launch_prepared(fn, a, tx, tw, ts, tb, a.save || relu_bits_out, stream, relu_bits_in != nullptr);
 }
 
 extern "C" int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,
@@ -96,4 +102,29 @@ extern "C" int nfs_mlp_chain_points_train(const float *points, float freq0, int3
   return launch_chain(fn, x_bf16_out, points, freq0, n_octaves, n_points, n_layers, k_dims, n_dims, acts, row0, w_stack_bf16,
                       w_rows, bias_terms_bf16, nullptr, 0, nullptr, save_bf16, relu_bits_out, save_rows_per_layer, out_f32,
                       out_cols, stream);
+}
+
+// Sampler + encoding + chain in one launch: the points are rays_o + rays_d * z_vals, evaluated by the warps that build the
+// first layer's operand.  x_bf16_out / save_bf16 / relu_bits_out != NULL: forward of a training step (as
+// nfs_mlp_chain_points_train); all NULL: inference.
+extern "C" int nfs_mlp_chain_rays(const float *rays_o, const float *rays_d, const float *z_vals, int64_t n_rays,
+                                  int32_t n_samples, float freq0, int32_t n_octaves, int32_t n_layers,
+                                  const int32_t *k_dims, const int32_t *n_dims, const int32_t *acts, const int32_t *row0,
+                                  const void *w_stack_bf16, int32_t w_rows, const void *bias_terms_bf16, void *x_bf16_out,
+                                  void *save_bf16, void *relu_bits_out, int64_t save_rows_per_layer, float *out_f32,
+                                  int32_t out_cols, void *stream) {
+  const char *fn = "nfs_mlp_chain_rays";
+  if (!rays_o || !rays_d || !z_vals || !out_f32 || n_rays < 0 || n_samples <= 0)
+    return fail_arg(fn, NFS_E_BADARG, "null pointer / bad sizes");
+  if ((x_bf16_out != nullptr) != (save_bf16 != nullptr))
+    return fail_arg(fn, NFS_E_BADARG, "a training forward needs both x_bf16_out and save_bf16");
+  FusedArgs a{};
+  CUtensorMap tx{}, tw{}, ts{}, tb{};
+  int rc = chain_prepare(fn, x_bf16_out, rays_o, freq0, n_octaves, n_rays * (int64_t)n_samples, n_layers, k_dims, n_dims, acts,
+                         row0, w_stack_bf16, w_rows, bias_terms_bf16, nullptr, 0, nullptr, save_bf16, relu_bits_out,
+                         save_rows_per_layer, out_f32, out_cols, &a, &tx, &tw, &ts, &tb);
+  if (rc == 1) return 0;
+  if (rc) return rc;
+  a.ray_z = z_vals; a.rays_o = rays_o; a.rays_d = rays_d; a.ray_S = n_samples;
+  return launch_prepared(fn, a, tx, tw, ts, tb, relu_bits_out != nullptr || save_bf16 != nullptr, stream);
 }

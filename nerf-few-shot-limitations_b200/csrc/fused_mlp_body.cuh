@@ -68,6 +68,10 @@ struct FusedArgs {
   long long bits_rows;                 // rows per layer of bits_in
   int mask_idx[kFmMaxLayers];
   const float *points;                 // in-kernel encoding mode: [P,3] fp32 sample positions (x_bf16 unused) | NULL
+  // in-kernel SAMPLER mode (points then aliases rays_o and only marks the encoding mode): point p = sample p % ray_S of
+  // ray p / ray_S, position = rays_o + rays_d * z_vals[p] evaluated here (un-contracted, as the sampler kernels do)
+  const float *ray_z, *rays_o, *rays_d;
+  int ray_S;
   float freq0;                         // first frequency band; band k = freq0 * 2^k
   int n_octaves;                       // number of bands (3 * (2 * n_octaves + 1) <= 64)
   int dbg;                             // developer bisection switches (nfs_set_debug_flags), 0 in production
@@ -431,7 +435,17 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
         mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);      // and every epilogue warp is done with it
         const long long row = (4 * quad + 2 * rank + t) * 128 + r_in;
         float x[3] = {0.f, 0.f, 0.f}, sn[3], cs[3];
-        if (row < a.P) { x[0] = __ldg(a.points + row * 3); x[1] = __ldg(a.points + row * 3 + 1); x[2] = __ldg(a.points + row * 3 + 2); }
+        if (row < a.P) {
+          if (a.ray_z != nullptr) {             // sampler fused in: the (P,3) positions never exist in HBM
+            const long long ray = row / a.ray_S;
+            const float zz = __ldg(a.ray_z + row);
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              x[d] = __fadd_rn(__ldg(a.rays_o + ray * 3 + d), __fmul_rn(__ldg(a.rays_d + ray * 3 + d), zz));   // ray_utils.py:82
+          } else {
+            x[0] = __ldg(a.points + row * 3); x[1] = __ldg(a.points + row * 3 + 1); x[2] = __ldg(a.points + row * 3 + 2);
+          }
+        }
 #pragma unroll
         for (int d = 0; d < 3; ++d) sincosf(__fmul_rn(x[d], a.freq0), &sn[d], &cs[d]);
         uint8_t *srow = smem + t * kActBytes + r_in * 128;

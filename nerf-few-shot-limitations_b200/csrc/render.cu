@@ -1,0 +1,54 @@
+// nfs_render_fused_fwd — the render path of one ray batch behind ONE C call:
+//   stratified depths -> [positions + sin/cos encoding + MLP] -> alpha compositing
+//   [-> inverse-CDF resampling -> positions + encoding + MLP -> alpha compositing]
+// i.e. NeRFDINOTrainer.render_rays (/root/reference/src/training/train.py:188-242) for the plain model, with the
+// hierarchical pass of utils.ray_utils.hierarchical_sampling (src/utils/ray_utils.py:86-143).
+//
+// What never reaches HBM: the sample positions (P,3) (the sampler's `o + d z` is evaluated by the chain kernel's operand
+// warps, fused_mlp_body.cuh), the (P,63) encodings and every hidden activation.  What does: the depths z (P floats, also an
+// input of the compositing and of the resampling), and the network's packed [r,g,b,sigma] rows (P,4): the compositing
+// scan runs over the S samples of a ray, which only coincide with the chain kernel's 128-row tiles when S divides 128 -
+// the fine pass (S = 192) does not - so K1 stays its own (HBM-bound, 2 % of the frame) launch.
+#include "nfs_common.cuh"
+
+using namespace nfs;
+
+extern "C" int nfs_render_fused_fwd(const nfs_chain_model *m, const float *rays_o, const float *rays_d, int64_t n_rays,
+                                    int32_t n_coarse, const float *z_base, const float *lower, const float *upper,
+                                    const float *t_rand, int32_t n_importance, const float *u, int64_t u_stride,
+                                    int32_t white_bkgd, float *z_coarse, float *raw_coarse, float *weights_coarse,
+                                    float *bin_weights, float *rgb_coarse, float *depth_coarse, float *z_fine,
+                                    float *raw_fine, float *weights_fine, float *rgb_fine, float *depth_fine,
+                                    void *stream) {
+  const char *fn = "nfs_render_fused_fwd";
+  if (!m || !rays_o || !rays_d || !z_base || !z_coarse || !raw_coarse || !rgb_coarse || n_rays < 0 || n_coarse < 2 ||
+      n_importance < 0)
+    return fail_arg(fn, NFS_E_BADARG, "null pointer / bad sizes");
+  if (n_importance > 0 && (!u || !weights_coarse || !bin_weights || !z_fine || !raw_fine || !rgb_fine))
+    return fail_arg(fn, NFS_E_BADARG, "the fine pass needs u, weights_coarse, bin_weights, z_fine, raw_fine, rgb_fine");
+  if (n_rays == 0) return 0;
+  int rc = nfs_sample_stratified(nullptr, nullptr, z_base, lower, upper, t_rand, n_rays, n_coarse, z_coarse, nullptr, stream);
+  if (rc) return rc;
+  rc = nfs_mlp_chain_rays(rays_o, rays_d, z_coarse, n_rays, n_coarse, m->freq0, m->n_octaves, m->n_layers, m->k_dims,
+                          m->n_dims, m->acts, m->row0, m->w_stack_bf16, m->w_rows, m->bias_terms_bf16, nullptr, nullptr,
+                          nullptr, 0, raw_coarse, 4, stream);
+  if (rc) return rc;
+  rc = nfs_composite_fwd(raw_coarse, nullptr, z_coarse, rays_d, nullptr, 0.f, n_rays, n_coarse, white_bkgd, 1, rgb_coarse,
+                         depth_coarse, weights_coarse, stream);
+  if (rc || n_importance == 0) return rc;
+  // weights[..., :-1]: the M = S - 1 bins between the S coarse depths (hierarchical_sampling's calling convention)
+  const int M = n_coarse - 1;
+  cudaError_t e = cudaMemcpy2DAsync(bin_weights, (size_t)M * 4, weights_coarse, (size_t)n_coarse * 4, (size_t)M * 4,
+                                    (size_t)n_rays, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(fn, e);
+  rc = nfs_sample_hierarchical(rays_o, rays_d, z_coarse, bin_weights, u, u_stride, nullptr, n_rays, M, n_importance, z_fine,
+                               nullptr, nullptr, nullptr, nullptr, stream);
+  if (rc) return rc;
+  const int S = n_coarse + n_importance;
+  rc = nfs_mlp_chain_rays(rays_o, rays_d, z_fine, n_rays, S, m->freq0, m->n_octaves, m->n_layers, m->k_dims, m->n_dims,
+                          m->acts, m->row0, m->w_stack_bf16, m->w_rows, m->bias_terms_bf16, nullptr, nullptr, nullptr, 0,
+                          raw_fine, 4, stream);
+  if (rc) return rc;
+  return nfs_composite_fwd(raw_fine, nullptr, z_fine, rays_d, nullptr, 0.f, n_rays, S, white_bkgd, 1, rgb_fine, depth_fine,
+                           weights_fine, stream);
+}

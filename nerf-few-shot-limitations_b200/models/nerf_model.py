@@ -53,3 +53,9 @@ class NeRFMLP(nn.Module):
         """points (...,3) fp32 -> (...,4) with the sin/cos expansion fused into the first layer's
         bf16 operand (the (P,63) fp32 encoding is never written).  Not part of the reference API."""
         return _mlp.g1_forward(self._get_plan(), points=points, freqs=freq_bands)
+
+    def forward_rays(self, rays_o, rays_d, z_vals, freq_bands):
+        """rays (N,3) + depths (N,S) -> (N,S,4): sampler (o + d z), encoding and all layers in ONE kernel
+        (nfs_mlp_chain_rays); neither the (N,S,3) positions nor their encodings are written.  Not part of the
+        reference API."""
+        return _mlp.g1_forward(self._get_plan(), rays=(rays_o, rays_d, z_vals), freqs=freq_bands)

@@ -46,6 +46,10 @@ SIGNATURES = {
     "nfs_mlp_chain_points": (ctypes.c_int, [_p, _f32, _i32, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _i32, _p]),
     "nfs_mlp_chain_points_train": (ctypes.c_int, [_p, _f32, _i32, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p,
                                                   _i64, _p, _i32, _p]),
+    "nfs_mlp_chain_rays": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i64,
+                                          _p, _i32, _p]),
+    "nfs_render_fused_fwd": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, _p,
+                                            _p, _p, _p, _p, _p, _p]),
     "nfs_posenc_bf16": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p]),
     "nfs_gate_bwd_bf16": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p]),
     "nfs_pack_linear_bf16": (ctypes.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
@@ -72,6 +76,12 @@ class WgradJob(ctypes.Structure):
     _fields_ = [("u_bf16", _p), ("u_pitch", _i64), ("v_bf16", _p), ("v_pitch", _i64), ("n_points", _i64),
                 ("m_dim", _i32), ("n_dim", _i32), ("m_valid", _i32), ("n_valid", _i32),
                 ("dw", _p), ("ld_m", _i64), ("ld_n", _i64), ("colsum", _p), ("colsum_of_v", _i32)]
+
+
+class ChainModel(ctypes.Structure):
+    """struct nfs_chain_model of include/nfs_b200.h."""
+    _fields_ = [("n_layers", _i32), ("k_dims", _p), ("n_dims", _p), ("acts", _p), ("row0", _p), ("w_stack_bf16", _p),
+                ("w_rows", _i32), ("bias_terms_bf16", _p), ("freq0", _f32), ("n_octaves", _i32)]
 
 
 _lib = None

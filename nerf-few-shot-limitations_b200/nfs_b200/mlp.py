@@ -324,7 +324,32 @@ class G1Plan:
                 self.wt_stack[rt:rt + p.k_pad, :p.n_pad].copy_(p.w16t)
         self.b_stack.copy_(bias_terms(b))
 
-    def run_forward_fused(self, x16, keep, slot=None, points=None, freqs=None):
+    def can_encode_in_kernel(self, freqs, dim=3):
+        """The chain kernel can build the first layer's operand itself (positions -> sin/cos encoding)."""
+        return (getattr(self, "fusable", False) and self.k0 == 64 and dim == 3 and 1 <= int(freqs.numel()) <= 10
+                and self.in_dim == 3 * (2 * int(freqs.numel()) + 1) and bands_are_octaves(freqs)
+                and os.environ.get("NFS_MLP_FUSED", "1") != "0" and os.environ.get("NFS_MLP_FUSED_ENC", "1") != "0")
+
+    def chain_model(self, freqs):
+        """struct nfs_chain_model for nfs_render_fused_fwd (host struct; the arrays it points to live in the plan)."""
+        return _lib.ChainModel(len(self.packed) + 1, ctypes.cast(self.c_k, ctypes.c_void_p), ctypes.cast(self.c_n, ctypes.c_void_p),
+                               ctypes.cast(self.c_act, ctypes.c_void_p), ctypes.cast(self.c_row0, ctypes.c_void_p),
+                               self.w_stack.data_ptr(), self.w_rows, self.b_stack.data_ptr(), float(first_band(freqs)),
+                               int(freqs.numel()))
+
+    def run_forward_rays(self, rays_o, rays_d, z, freqs):
+        """nfs_mlp_chain_rays, inference: sampler + encoding + all layers in one launch; z (N,S) -> out (N*S,4)."""
+        N, S = z.shape
+        out = torch.empty((N * S, 4), device=z.device, dtype=torch.float32)
+        if N * S:
+            n_hidden = len(self.packed)
+            with torch.cuda.device(z.device):
+                _lib.call("nfs_mlp_chain_rays", ptr(rays_o), ptr(rays_d), ptr(z), N, S, float(first_band(freqs)),
+                          int(freqs.numel()), n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0, ptr(self.w_stack),
+                          self.w_rows, ptr(self.b_stack), None, None, None, 0, ptr(out), 4, _stream())
+        return out
+
+    def run_forward_fused(self, x16, keep, slot=None, points=None, freqs=None, rays=None):
         """nfs_mlp_chain: all layers in one launch; hidden activations (for wgrad) and their ReLU sign bits
         (for the dgrad chain) are written to HBM only when the backward pass will need them.
         slot = (StepSession, first row): they go into the session's arenas at that row instead of fresh tensors.
@@ -343,7 +368,13 @@ class G1Plan:
             rows = _ceil_to(P, 128)
             save = torch.empty((n_hidden, rows, self.h_pad), device=dev, dtype=torch.bfloat16)
             bits = torch.empty((n_hidden, rows, 8), device=dev, dtype=torch.int32)
-        if P and points is not None:
+        if P and rays is not None:
+            ro, rd, z = rays
+            with torch.cuda.device(dev):
+                _lib.call("nfs_mlp_chain_rays", ptr(ro), ptr(rd), ptr(z), z.shape[0], z.shape[1], float(first_band(freqs)),
+                          int(freqs.numel()), n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0, ptr(self.w_stack),
+                          self.w_rows, ptr(self.b_stack), ptr(x16), ptr(save), ptr(bits), rows, ptr(out), 4, _stream())
+        elif P and points is not None:
             with torch.cuda.device(dev):
                 _lib.call("nfs_mlp_chain_points_train", ptr(points), float(first_band(freqs)), int(freqs.numel()), P,
                           n_hidden + 1, self.c_k, self.c_n, self.c_act, self.c_row0, ptr(self.w_stack), self.w_rows,
@@ -639,15 +670,15 @@ class _G1Fn(torch.autograd.Function):
         """extra: None, or dict(slot=(StepSession, row)|None, points=fp32 [P,3]|None, freqs=...) - where the saved
         tensors go and whether the chain kernel encodes the points itself."""
         extra = extra or {}
-        slot, points, freqs = extra.get("slot"), extra.get("points"), extra.get("freqs")
+        slot, points, freqs, rays = extra.get("slot"), extra.get("points"), extra.get("freqs"), extra.get("rays")
         if slot is not None:
-            out, _, _ = plan.run_forward_fused(x16, True, slot=slot, points=points, freqs=freqs)
+            out, _, _ = plan.run_forward_fused(x16, True, slot=slot, points=points, freqs=freqs, rays=rays)
             ctx.plan, ctx.slot, ctx.fused = plan, slot, True
             ctx.save_for_backward(out)
             return out
         ctx.slot = None
-        if points is not None:
-            out, acts, save = plan.run_forward_fused(x16, True, points=points, freqs=freqs)
+        if points is not None or rays is not None:
+            out, acts, save = plan.run_forward_fused(x16, True, points=points, freqs=freqs, rays=rays)
         else:
             out, acts, save = plan.run_forward(x16, keep)
         ctx.plan = plan
@@ -678,12 +709,15 @@ class _G1Fn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
-def g1_forward(plan, x=None, points=None, freqs=None):
+def g1_forward(plan, x=None, points=None, freqs=None, rays=None):
     """out [P,4] = [sigmoid rgb | raw sigma].  Either `x` (fp32 [P,in_dim], already encoded, the
     reference's calling convention) or `points` (fp32 [P,3]) + `freqs` (encoding fused into the
-    operand build, never materialised in fp32)."""
+    operand build, never materialised in fp32), or `rays` = (rays_o (N,3), rays_d (N,3), z_vals (N,S)) + `freqs`
+    (sampler AND encoding fused into the chain kernel: out is (N,S,4))."""
     plan.refresh()
     plan._last_slot = None
+    if rays is not None:
+        return _g1_forward_rays(plan, rays, freqs)
     src = x if x is not None else points
     ops._need_cuda("NeRFMLP", src)
     if src.requires_grad and torch.is_grad_enabled():
@@ -732,3 +766,28 @@ def g1_forward(plan, x=None, points=None, freqs=None):
     keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     out = _G1Fn.apply(plan, keep, x16, extra, *params)
     return out.reshape(*lead, 4)
+
+
+def _g1_forward_rays(plan, rays, freqs):
+    ro, rd, z = (ops._f32c(t) for t in rays)
+    ops._need_cuda("NeRFMLP", ro, rd, z)
+    if z.dim() != 2 or ro.shape != (z.shape[0], 3) or rd.shape != ro.shape:
+        raise RuntimeError("NeRFMLP.forward_rays: rays_o / rays_d must be (N,3) and z_vals (N,S)")
+    N, S = z.shape
+    P = N * S
+    keep = torch.is_grad_enabled() and any(p.requires_grad for p in plan.params())
+    if not plan.can_encode_in_kernel(freqs) or (keep and len(plan.packed) < 2) or P == 0:
+        pts = ro[:, None, :] + rd[:, None, :] * z[:, :, None]            # generic route: materialise the positions
+        return g1_forward(plan, points=pts.reshape(-1, 3), freqs=freqs).reshape(N, S, 4)
+    if not keep:
+        return plan.run_forward_rays(ro, rd, z, freqs).reshape(N, S, 4)
+    sess = getattr(plan, "_session", None)
+    extra = {"rays": (ro, rd, z), "freqs": freqs}
+    if sess is not None:
+        r0 = sess.take(P)
+        extra["slot"] = plan._last_slot = (sess, r0)
+        x16 = sess.x16[r0:r0 + P]
+    else:
+        x16 = torch.empty((_ceil_to(P, 128), plan.k0), device=z.device, dtype=torch.bfloat16)[:P]
+    out = _G1Fn.apply(plan, True, x16, extra, *plan.params())
+    return out.reshape(N, S, 4)

@@ -550,3 +550,39 @@ def wgrad_multi(jobs):
     if n:
         with torch.cuda.device(dev):
             _lib.call("nfs_wgrad_multi_bf16", ctypes.byref(arr), n, _stream())
+
+
+def render_fused(plan, freqs, rays_o, rays_d, near, far, n_coarse, n_importance=0, t_rand=None, u=None, white_bkgd=False,
+                 want_weights=False):
+    """nfs_render_fused_fwd: stratified depths -> sampler + encoding + MLP (one kernel) -> compositing
+    [-> inverse-CDF resampling -> MLP -> compositing] behind one C call (inference; plan = mlp.G1Plan of a
+    nerf_model.NeRFMLP whose first layer takes the 10-octave encoding).  t_rand (N,Sc)|None and u (N,Ni)|(Ni,) as
+    sample_stratified / sample_hierarchical.  Returns a dict like pipeline.render_rays."""
+    rays_o, rays_d, t_rand = _f32c(rays_o), _f32c(rays_d), _f32c(t_rand)
+    _need_cuda("render_fused", rays_o, rays_d, t_rand, u)
+    N = rays_o.shape[0]
+    dev = rays_o.device
+    Sc, Ni = int(n_coarse), int(n_importance)
+    Sf = Sc + Ni
+    z_base, lower, upper = _tables_on(dev, near, far, Sc, False)
+    f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    z_c, raw_c, w_c, rgb_c, dep_c = f(N, Sc), f(N, Sc, 4), f(N, Sc), f(N, 3), f(N)
+    out = {"rgb": rgb_c, "depth": dep_c, "weights": w_c, "z_vals": z_c}
+    z_f = raw_f = w_f = rgb_f = dep_f = bins = None
+    u_stride = 0
+    if Ni > 0:
+        if u is None:
+            raise RuntimeError("render_fused: u is required for the fine pass (draws or the linspace table)")
+        u = _f32c(u)
+        u_stride = 0 if u.dim() == 1 else Ni
+        z_f, raw_f, rgb_f, dep_f, bins = f(N, Sf), f(N, Sf, 4), f(N, 3), f(N), f(N, Sc - 1)
+        w_f = f(N, Sf) if want_weights else None
+        out = {"rgb": rgb_f, "depth": dep_f, "weights": w_f, "z_vals": z_f, "rgb_coarse": rgb_c, "depth_coarse": dep_c,
+               "weights_coarse": w_c, "z_coarse": z_c}
+    if N:
+        model = plan.chain_model(freqs)
+        with torch.cuda.device(dev):
+            _lib.call("nfs_render_fused_fwd", ctypes.byref(model), ptr(rays_o), ptr(rays_d), N, Sc, ptr(z_base), ptr(lower),
+                      ptr(upper), ptr(t_rand), Ni, ptr(u), u_stride, int(bool(white_bkgd)), ptr(z_c), ptr(raw_c), ptr(w_c),
+                      ptr(bins), ptr(rgb_c), ptr(dep_c), ptr(z_f), ptr(raw_f), ptr(w_f), ptr(rgb_f), ptr(dep_f), _stream())
+    return out

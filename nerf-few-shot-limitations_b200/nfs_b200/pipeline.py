@@ -8,6 +8,8 @@ Every stage is one of the library's CUDA kernels; tensors between stages stay in
 layout the next kernel wants (the MLP emits packed [r,g,b,sigma] rows, which is exactly the
 packed operand of the compositing kernel, so nothing is sliced or copied in between).
 """
+import os
+
 import torch
 
 from . import ops
@@ -27,8 +29,22 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
     dev = rays_o.device
     if perturb and t_rand is None:
         t_rand = torch.rand(N, n_coarse, device=dev)
-    pts, z = ops.sample_stratified(rays_o, rays_d, near, far, n_coarse, t_rand=t_rand if perturb else None)
-    raw = model.forward_points(pts.reshape(-1, 3), freq_bands).reshape(N, n_coarse, 4)
+    plan = model._get_plan() if hasattr(model, "_get_plan") else None
+    in_kernel = plan is not None and hasattr(model, "forward_rays") and (plan.refresh() or True) \
+        and getattr(plan, "can_encode_in_kernel", lambda f: False)(freq_bands) and os.environ.get("NFS_RENDER_FUSED", "1") != "0"
+    if in_kernel and target is None and not torch.is_grad_enabled():
+        # inference: the whole path behind one C call (nfs_render_fused_fwd); positions / encodings never reach HBM
+        if n_importance > 0 and u is None:
+            u = torch.rand(N, n_importance, device=dev) if perturb else ops.importance_table(dev, n_importance)
+        return ops.render_fused(plan, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance,
+                                t_rand=t_rand if perturb else None, u=u, white_bkgd=white_bkgd, want_weights=True)
+    if in_kernel:
+        # sampler fused into the chain kernel: only the depths are sampled here
+        _, z = ops.sample_stratified(rays_o, rays_d, near, far, n_coarse, t_rand=t_rand if perturb else None, want_pts=False)
+        raw = model.forward_rays(rays_o, rays_d, z, freq_bands)
+    else:
+        pts, z = ops.sample_stratified(rays_o, rays_d, near, far, n_coarse, t_rand=t_rand if perturb else None)
+        raw = model.forward_points(pts.reshape(-1, 3), freq_bands).reshape(N, n_coarse, 4)
     loss = None
     if target is not None:
         c = ops.composite_loss(raw, None, z, rays_d, target, None, 1.0, 0.0, white_bkgd, want_weights=n_importance > 0,
@@ -43,9 +59,12 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
             w_in = weights.detach()[:, :-1].contiguous()      # M = S-1 bins between the S coarse depths
             if u is None:
                 u = torch.rand(N, n_importance, device=dev) if perturb else ops.importance_table(dev, n_importance)
-            pts_f, z_f = ops.sample_hierarchical(rays_o, rays_d, z, w_in, n_importance, u=u)
+            pts_f, z_f = ops.sample_hierarchical(rays_o, rays_d, z, w_in, n_importance, u=u, want_pts=not in_kernel)
         S = n_coarse + n_importance
-        raw_f = model.forward_points(pts_f.reshape(-1, 3), freq_bands).reshape(N, S, 4)
+        if in_kernel:
+            raw_f = model.forward_rays(rays_o, rays_d, z_f, freq_bands)
+        else:
+            raw_f = model.forward_points(pts_f.reshape(-1, 3), freq_bands).reshape(N, S, 4)
         if target is not None:
             c = ops.composite_loss(raw_f, None, z_f, rays_d, target, None, 1.0, 0.0, white_bkgd, dy_slot=_dy_slot(model))
             rgb_f, depth_f, w_f, loss = c["rgb_map"], c["depth_map"], None, loss + c["total"]

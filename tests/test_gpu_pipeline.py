@@ -4,7 +4,7 @@ and a short training run.  Stated tolerance: rendered pixel abs <= 1e-2 (SURVEY.
 import pytest
 import torch
 
-from helpers import record
+from helpers import bit_equal, record
 from oracle import nerf_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -259,3 +259,54 @@ def test_session_with_and_without_in_place_dy(cuda, monkeypatch):
     rel = float((res["1"][1] - res["0"][1]).norm() / res["0"][1].norm())
     record("step_in_place_dy_vs_act_grad", grad_rel_l2=rel)
     assert rel <= 1e-5, rel
+
+
+@pytest.mark.parametrize("n_rays,S", [(300, 64), (257, 192), (5, 7)])
+def test_forward_rays_bit_identical_to_forward_points(cuda, n_rays, S):
+    """nfs_mlp_chain_rays (sampler o + d z evaluated inside the chain kernel) against sampling the positions first
+    (nfs_sample_stratified + nfs_mlp_chain_points): bit-identical outputs in inference and in a training forward, equal
+    gradients (up to the weight-gradient kernels' atomics)."""
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import ops
+    torch.manual_seed(1)
+    model = NeRFMLP().to(cuda)
+    bands = O.frequency_bands(10)
+    ro, rd = O.lego_rays(n_rays, seed=S)
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    t_rand = torch.rand(n_rays, S, generator=torch.Generator().manual_seed(2)).to(cuda)
+    pts, z = ops.sample_stratified(ro, rd, 2.0, 6.0, S, t_rand=t_rand)
+    with torch.no_grad():
+        a = model.forward_rays(ro, rd, z, bands)
+        b = model.forward_points(pts.reshape(-1, 3), bands).reshape(n_rays, S, 4)
+    assert bit_equal(a, b)
+    ga = torch.autograd.grad((model.forward_rays(ro, rd, z, bands) ** 2).mean(), list(model.parameters()))
+    gb = torch.autograd.grad((model.forward_points(pts.reshape(-1, 3), bands) ** 2).mean(), list(model.parameters()))
+    for x, y in zip(ga, gb):
+        assert float((x - y).norm()) <= 1e-5 * float(y.norm()) + 1e-12
+
+
+@pytest.mark.parametrize("n_imp,perturb", [(128, False), (40, True), (0, True)])
+def test_render_fused_matches_kernel_by_kernel_route(cuda, monkeypatch, n_imp, perturb):
+    """nfs_render_fused_fwd (one C call; sampler + encoding + MLP in one kernel) against the launch-by-launch route
+    with materialised positions: bit-identical depths, weights and pixels."""
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import pipeline
+    torch.manual_seed(2)
+    model = NeRFMLP().to(cuda).eval()
+    with torch.no_grad():
+        model.sigma_out.bias.fill_(0.3)
+    bands = O.frequency_bands(10)
+    n = 777
+    ro, rd = O.lego_rays(n, seed=3)
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    g = torch.Generator().manual_seed(5)
+    t_rand = torch.rand(n, 64, generator=g).to(cuda)
+    u = torch.rand(n, n_imp, generator=g).to(cuda) if (perturb and n_imp) else None
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NFS_RENDER_FUSED", mode)
+        with torch.no_grad():
+            outs[mode] = pipeline.render_rays(model, bands, ro, rd, 2.0, 6.0, 64, n_imp, perturb=perturb, t_rand=t_rand, u=u,
+                                              white_bkgd=True)
+    for k in ("rgb", "depth", "weights", "z_vals") + (("rgb_coarse", "weights_coarse") if n_imp else ()):
+        assert bit_equal(outs["1"][k], outs["0"][k]), k
