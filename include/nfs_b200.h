@@ -307,8 +307,8 @@ int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int32_t n_laye
  *   K_l, N_l multiples of 64 in [64,256], K_l == N_{l-1}.
  *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 4 ReLU backward: multiply by the sign bit
  *   relu_bits_in[mask_idx[l]][p][n] (layers >= 128 wide).
- *   ReLU sign bits: uint32 [layers, rows_per_layer, 8] = 256 bits per point; in word w bit j (j < 16) is column
- *   32w + 2j and bit 16 + j is column 32w + 2j + 1.  relu_bits_out (forward chain of a training step, NULL
+ *   ReLU mask bits: uint32 [layers, rows_per_layer, 8] = 256 bits per point (1 = the pre-activation was positive);
+ *   in word w bit 15 - j (j < 16) is column 32w + 2j and bit 31 - j is column 32w + 2j + 1.  relu_bits_out (forward chain of a training step, NULL
  *   otherwise) receives the bits of every act-1 layer's output, 32 bytes per point instead of the 512-byte
  *   activation row the backward would otherwise re-read; rows per layer = save_rows_per_layer.
  *   out_f32 != NULL: the LAST layer is an output head whose first out_cols columns are written

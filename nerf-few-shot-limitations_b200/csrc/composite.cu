@@ -767,6 +767,246 @@ int launch_fwd_staged(const CompositeArgs &a, cudaStream_t st) {
   return check_launch("nfs_composite_fwd");
 }
 
+// ------------------------------- staged kernels for long rays (S > 128) ------
+// The fine pass of BASELINE configs 3 / 5 composites 192 samples per ray: more than one 4 x 32-sample chunk, which the
+// generic backward handles by reading z / density twice from global memory (phase A: chunk-entry transmittances,
+// phase B: the chunks in reverse).  Here the same load pipeline as the staged kernels above brings a tile of 8 rays
+// (one warp per ray) into a 2-stage shared-memory ring and BOTH phases read from there: every input byte crosses the
+// memory system once.  Same arithmetic, chunk by chunk, as composite_fwd_kernel / composite_bwd_kernel<32>
+// (bit-identical results).
+constexpr int kLongG = 32;
+constexpr int kLongRays = kBlock / 32;           // rays per tile
+constexpr int kLongMaxChunks = 8;                // S <= 1024
+
+// one lane's 4 samples of chunk c0 of the warp's ray, from the stage
+__device__ __forceinline__ void load_lane_stage(const float *st, int S, int ray_in_tile, int s0, bool ok, bool with_rgb,
+                                                Lane4 &v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v.z[j] = 0.f; v.sg[j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) v.col[j] = 0.f;
+  if (!ok || s0 >= S) return;
+  const int o = ray_in_tile * S + s0;
+  const float4 dd = *reinterpret_cast<const float4 *>(st + kLongRays * S * 3 + o);
+  const float4 zz = *reinterpret_cast<const float4 *>(st + kLongRays * S * 4 + o);
+  v.sg[0] = dd.x; v.sg[1] = dd.y; v.sg[2] = dd.z; v.sg[3] = dd.w;
+  v.z[0] = zz.x; v.z[1] = zz.y; v.z[2] = zz.z; v.z[3] = zz.w;
+  if (with_rgb) {
+    const float4 c0 = *reinterpret_cast<const float4 *>(st + o * 3);
+    const float4 c1 = *reinterpret_cast<const float4 *>(st + o * 3 + 4);
+    const float4 c2 = *reinterpret_cast<const float4 *>(st + o * 3 + 8);
+    v.col[0] = c0.x; v.col[1] = c0.y; v.col[2] = c0.z; v.col[3] = c0.w;
+    v.col[4] = c1.x; v.col[5] = c1.y; v.col[6] = c1.z; v.col[7] = c1.w;
+    v.col[8] = c2.x; v.col[9] = c2.y; v.col[10] = c2.z; v.col[11] = c2.w;
+  }
+}
+__device__ __forceinline__ float next_z_stage(const float *st, const Lane4 &v, int S, int ray_in_tile, int c0, int lane, bool ok) {
+  float zn = __shfl_down_sync(kFullMask, v.z[0], 1, kLongG);
+  if (lane == kLongG - 1) {
+    const int sn = c0 + 4 * kLongG;
+    zn = (ok && sn < S) ? st[kLongRays * S * 4 + ray_in_tile * S + sn] : 0.f;
+  }
+  return zn;
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(kBlock, 3) composite_long_staged_kernel(const CompositeArgs a, const long long n_tiles) {
+  extern __shared__ __align__(128) unsigned char s_stage[];
+  const int S = a.S;
+  const bool has_gw = !FWD && a.g_w != nullptr;
+  const int per_sample = FWD ? 5 : (has_gw ? 6 : 5);              // rgb 3 | density | z | [g_w]
+  const int stage_floats = kLongRays * S * per_sample;
+  float *ring = reinterpret_cast<float *>(s_stage);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ring + kBwdStages * stage_floats);
+  float *t_entry = reinterpret_cast<float *>(full + kBwdStages);  // [kLongRays][kLongMaxChunks] chunk-entry transmittances
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chunks = (S + 4 * kLongG - 1) / (4 * kLongG);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBwdStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int stage) {                    // thread 0 only
+    const long long r0 = tile * kLongRays;
+    const long long nr = (a.n_rays - r0) < kLongRays ? (a.n_rays - r0) : kLongRays;
+    const uint32_t row = (uint32_t)(nr * S * 4);
+    float *st = ring + stage * stage_floats;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(full + stage)),
+                 "r"(row * (uint32_t)per_sample) : "memory");
+    bulk_g2s(st, a.rgb + r0 * S * 3, row * 3, full + stage);
+    bulk_g2s(st + kLongRays * S * 3, a.density + r0 * S, row, full + stage);
+    bulk_g2s(st + kLongRays * S * 4, a.z + r0 * S, row, full + stage);
+    if (has_gw) bulk_g2s(st + kLongRays * S * 5, a.g_w + r0 * S, row, full + stage);
+  };
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBwdStages; ++i)
+      if (first + i * step < n_tiles) issue(first + i * step, i);
+
+  uint32_t it = 0;
+  for (long long tile = first; tile < n_tiles; tile += step, ++it) {
+    const int stage = it % kBwdStages;
+    const uint32_t parity = (it / kBwdStages) & 1;
+    const long long ray = tile * kLongRays + warp;
+    const bool ray_ok = ray < a.n_rays;
+    float dnorm = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
+    if (ray_ok) {
+      const float dx = __ldg(a.rays_d + ray * 3), dy = __ldg(a.rays_d + ray * 3 + 1), dz = __ldg(a.rays_d + ray * 3 + 2);
+      dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (!FWD) {
+        gr = __ldg(a.g_rgb + ray * 3); gg = __ldg(a.g_rgb + ray * 3 + 1); gb = __ldg(a.g_rgb + ray * 3 + 2);
+        if (a.g_depth != nullptr) gd = __ldg(a.g_depth + ray);
+      }
+    }
+    {                                                               // wait for the tile
+      uint32_t ok = 0, spin = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(full + stage)), "r"(parity) : "memory");
+        if (++spin > (1u << 26)) { printf("nfs_b200: composite (long rays) tile wait timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+      }
+    }
+    const float *st = ring + stage * stage_floats;
+
+    if (FWD) {
+      float t_carry = 1.f;
+      float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_w = 0.f;
+      for (int c0 = 0; c0 < S; c0 += 4 * kLongG) {
+        const int s0 = c0 + 4 * lane;
+        Lane4 v;
+        load_lane_stage(st, S, warp, s0, ray_ok, true, v);
+        const float zn = next_z_stage(st, v, S, warp, c0, lane, ray_ok);
+        Alpha4 al;
+        alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+        const float p1 = al.q[0], p2 = p1 * al.q[1], p3 = p2 * al.q[2], p4 = p3 * al.q[3];
+        float chunk_all;
+        const float tb = t_carry * group_excl_prod<kLongG>(p4, lane, chunk_all);
+        const float T[4] = {tb, tb * p1, tb * p2, tb * p3};
+        t_carry *= chunk_all;
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[j] = al.alpha[j] * T[j];
+          acc_r += w[j] * v.col[3 * j];
+          acc_g += w[j] * v.col[3 * j + 1];
+          acc_b += w[j] * v.col[3 * j + 2];
+          acc_d += w[j] * v.z[j];
+          acc_w += w[j];
+        }
+        if (a.out_w != nullptr && ray_ok && s0 < S)
+          stg_stream4(a.out_w + ray * (long long)S + s0, make_float4(w[0], w[1], w[2], w[3]));
+      }
+      acc_r = group_sum<kLongG>(acc_r);
+      acc_g = group_sum<kLongG>(acc_g);
+      acc_b = group_sum<kLongG>(acc_b);
+      acc_d = group_sum<kLongG>(acc_d);
+      acc_w = group_sum<kLongG>(acc_w);
+      if (ray_ok && lane == 0) {
+        if (a.white) {
+          const float bg = 1.0f - acc_w;
+          acc_r += bg; acc_g += bg; acc_b += bg;
+        }
+        a.out_rgb[ray * 3] = acc_r; a.out_rgb[ray * 3 + 1] = acc_g; a.out_rgb[ray * 3 + 2] = acc_b;
+        if (a.out_depth != nullptr) a.out_depth[ray] = acc_d;
+      }
+      if (a.target != nullptr) loss_epilogue(a, ray, ray_ok && lane == 0, acc_r, acc_g, acc_b, acc_d, tile);
+    } else {
+      const float g_bg = a.white ? (gr + gg + gb) : 0.f;
+      float *my_t = t_entry + warp * kLongMaxChunks;
+      // phase A: transmittance at the entry of every chunk (z and density, from the stage)
+      float t_carry = 1.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int c0 = c * 4 * kLongG, s0 = c0 + 4 * lane;
+        if (lane == 0) my_t[c] = t_carry;
+        Lane4 v;
+        load_lane_stage(st, S, warp, s0, ray_ok, false, v);
+        const float zn = next_z_stage(st, v, S, warp, c0, lane, ray_ok);
+        Alpha4 al;
+        alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+        t_carry *= group_prod<kLongG>(al.q[0] * al.q[1] * al.q[2] * al.q[3]);
+      }
+      __syncwarp();
+      // phase B: chunks in reverse; r_carry = sum of G_k w_k over all later chunks
+      float r_carry = 0.f;
+      for (int c = n_chunks - 1; c >= 0; --c) {
+        const int c0 = c * 4 * kLongG, s0 = c0 + 4 * lane;
+        Lane4 v;
+        load_lane_stage(st, S, warp, s0, ray_ok, true, v);
+        float gw_in[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_gw && ray_ok && s0 < S) {
+          const float4 t = *reinterpret_cast<const float4 *>(st + kLongRays * S * 5 + warp * S + s0);
+          gw_in[0] = t.x; gw_in[1] = t.y; gw_in[2] = t.z; gw_in[3] = t.w;
+        }
+        const float zn = next_z_stage(st, v, S, warp, c0, lane, ray_ok);
+        Alpha4 al;
+        alpha_lane(v, zn, s0, S, ray_ok, dnorm, al);
+        const float p1 = al.q[0], p2 = p1 * al.q[1], p3 = p2 * al.q[2], p4 = p3 * al.q[3];
+        float chunk_all;
+        const float tb = my_t[c] * group_excl_prod<kLongG>(p4, lane, chunk_all);
+        const float T[4] = {tb, tb * p1, tb * p2, tb * p3};
+        float w[4], Gi[4], gwk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[j] = al.alpha[j] * T[j];
+          Gi[j] = gr * v.col[3 * j] + gg * v.col[3 * j + 1] + gb * v.col[3 * j + 2] + gd * v.z[j] + gw_in[j] - g_bg;
+          gwk[j] = Gi[j] * w[j];
+        }
+        const float e3 = 0.f, e2 = gwk[3], e1 = e2 + gwk[2], e0 = e1 + gwk[1];
+        float chunk_sum;
+        const float rb = r_carry + group_excl_suffix_sum<kLongG>(e0 + gwk[0], lane, chunk_sum);
+        const float R[4] = {rb + e0, rb + e1, rb + e2, rb + e3};
+        r_carry += chunk_sum;
+        float ds[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dalpha = Gi[j] * T[j] - NFS_K1_DIV(R[j], al.q[j]);
+          ds[j] = (v.sg[j] > 0.f) ? dalpha * al.dist[j] * al.e[j] : 0.f;
+        }
+        if (ray_ok && s0 < S) {
+          const long long base = ray * (long long)S + s0;
+          float *op = a.d_rgb + base * 3;
+          stg_stream4(op,     make_float4(w[0] * gr, w[0] * gg, w[0] * gb, w[1] * gr));
+          stg_stream4(op + 4, make_float4(w[1] * gg, w[1] * gb, w[2] * gr, w[2] * gg));
+          stg_stream4(op + 8, make_float4(w[2] * gb, w[3] * gr, w[3] * gg, w[3] * gb));
+          stg_stream4(a.d_density + base, make_float4(ds[0], ds[1], ds[2], ds[3]));
+        }
+      }
+    }
+    __syncthreads();                                                // everyone has read this stage
+    if (threadIdx.x == 0 && tile + kBwdStages * step < n_tiles) issue(tile + kBwdStages * step, stage);
+  }
+}
+
+static size_t long_staged_smem(const CompositeArgs &a, bool fwd) {
+  const int per_sample = fwd ? 5 : (a.g_w ? 6 : 5);
+  return sizeof(float) * (size_t)kBwdStages * kLongRays * a.S * per_sample + 8 * kBwdStages +
+         sizeof(float) * kLongRays * kLongMaxChunks + 64;
+}
+
+template <bool FWD>
+int launch_long_staged(const CompositeArgs &a, cudaStream_t st) {
+  const char *fn = FWD ? "nfs_composite_fwd" : "nfs_composite_bwd";
+  const long long n_tiles = (a.n_rays + kLongRays - 1) / kLongRays;
+  const size_t smem = long_staged_smem(a, FWD);
+  static PerDeviceOnce attr_once;
+  int attr_dev = 0;
+  if (attr_once.need(&attr_dev)) {
+    cudaError_t e = cudaFuncSetAttribute(composite_long_staged_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return fail_cuda(fn, e);
+    attr_once.mark(attr_dev);
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long max_blocks = (long long)sms * 3;
+  const unsigned grid = (unsigned)(n_tiles < max_blocks ? n_tiles : max_blocks);
+  composite_long_staged_kernel<FWD><<<grid, kBlock, smem, st>>>(a, n_tiles);
+  return check_launch(fn);
+}
+
 // ------------------------------- dispatch -----------------------------------
 int pick_group(int S) { return S <= 32 ? 8 : (S <= 64 ? 16 : 32); }
 
@@ -794,6 +1034,13 @@ int launch_bwd(const CompositeArgs &a, cudaStream_t st) {
 template <bool FWD>
 int dispatch(const CompositeArgs &a, bool aligned, bool packed, cudaStream_t st) {
   const int G = pick_group(a.S);
+  // long rays (the 192-sample fine pass): both phases of the backward / the chunked forward read a staged tile
+  if (aligned && !packed && a.noise == nullptr && a.S > 4 * kLongG && a.S <= 4 * kLongG * kLongMaxChunks &&
+      long_staged_smem(a, FWD) <= 96 * 1024 && getenv("NFS_K1_LONG_UNSTAGED") == nullptr) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if ((a.n_rays + kLongRays - 1) / kLongRays >= 2LL * sms * 3) return launch_long_staged<FWD>(a, st);
+  }
   if (!FWD && aligned && !packed && a.noise == nullptr && a.S <= 4 * G &&
       sizeof(float) * (size_t)kBwdStages * (kBlock / 32) * (32 / G) * a.S * (a.g_w ? 6 : 5) + 64 <= 96 * 1024) {
     if (G == 8) return launch_bwd_staged<8>(a, st);

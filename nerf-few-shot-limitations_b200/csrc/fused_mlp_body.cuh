@@ -59,10 +59,12 @@ struct FusedArgs {
   int out_cols;
   int save;
   int head;                            // 1: last layer is the fp32 output head; 0: it is a regular (saved) layer
-  // ReLU sign bits, 256 per row = 8 words [layer][row][8]; in word w bit j (j < 16) is column 32w + 2j, bit 16 + j is
-  // column 32w + 2j + 1 (the two halves of packed pair j), so (word >> j) & 0x10001 times 0x3F80 is the pair's
-  // bf16x2 {1.0 | 0.0} multiplier.  bits_out: written by layers with act 1 (the forward chain of a training step);
-  // bits_in: read by layers with act 4 (the dgrad chain): result *= bit(mask_idx[l], row, col).
+  // ReLU mask bits, 256 per row = 8 words [layer][row][8]; word w covers columns 32w .. 32w+31 as 16 packed pairs: bit
+  // 15 - j (j < 16) is column 32w + 2j, bit 31 - j is column 32w + 2j + 1 (the two halves of packed pair j; 1 = the
+  // pre-activation was positive), so (word >> (15 - j)) & 0x10001 times 0x3F80 is the pair's bf16x2 {1.0 | 0.0}
+  // multiplier.  bits_out: written by layers with act 1 (the forward chain of a training step) - three instructions per
+  // packed pair (push_mask); bits_in: read by layers with act 4 (the dgrad chain):
+  // result *= bit(mask_idx[l], row, col).
   uint32_t *bits_out;
   const uint32_t *bits_in;
   long long bits_rows;                 // rows per layer of bits_in
@@ -145,17 +147,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// ReLU backward on packed pair j of a 32-column word of sign bits (layout above)
+// ReLU backward on packed pair j (0..15) of a 32-column word of mask bits (layout in FusedArgs)
 __device__ __forceinline__ uint32_t relu_bits_bf16x2(uint32_t v, uint32_t word, int j) {
-  const uint32_t m = ((word >> j) & 0x00010001u) * 0x3F80u;     // bf16x2 {1.0 | 0.0, 1.0 | 0.0}
+  const uint32_t m = ((word >> (15 - j)) & 0x00010001u) * 0x3F80u;     // bf16x2 {1.0 | 0.0, 1.0 | 0.0}
   uint32_t r;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(m));
   return r;
 }
-// sign bits of a post-ReLU packed pair (both halves are non-negative bf16: adding 0x7FFF carries into bit 15 / 31
-// exactly when the half is non-zero), placed at bit j and bit 16 + j
-__device__ __forceinline__ uint32_t relu_bits_of(uint32_t pk, int j) {
-  return (((pk + 0x7FFF7FFFu) >> 15) & 0x00010001u) << j;
+// Mask bits of a post-ReLU packed pair shifted into `acc` from the right, both 16-bit lanes at once: one bf16x2 compare
+// (0xFFFF per half that is > 0 - exactly torch's relu'(x) = [x > 0], also for +-0), one shift, one LOP3.  After the 16
+// pairs of a word, pair j's bits sit at positions 15 - j (even column) and 31 - j (odd column).
+__device__ __forceinline__ uint32_t push_mask(uint32_t acc, uint32_t pk) {
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+  const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&pk), zero);
+  return (acc << 1) | (m & 0x00010001u);
 }
 
 // TMEM -> registers, 16 consecutive fp32 columns of this thread's lane, WITHOUT waiting: the
@@ -190,9 +195,9 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], int act, uint32_t b
 #pragma unroll
     for (int j = 0; j < 8; ++j) pk[j] = relu_bits_bf16x2(pk[j], bits_word, j0 + j);
   }
-  if (kTrain && act == 1) {              // sign bits for the backward pass
+  if (kTrain && act == 1) {              // mask bits for the backward pass
 #pragma unroll
-    for (int j = 0; j < 8; ++j) bits_acc |= relu_bits_of(pk[j], j0 + j);
+    for (int j = 0; j < 8; ++j) bits_acc = push_mask(bits_acc, pk[j]);
   }
   if (dbg & 32) {                       // bisection: keep the values alive without the shared-memory stores
     uint32_t x = 0;

@@ -4,6 +4,7 @@ the autograd glue.  Nothing here computes on the CPU; every function raises if t
 tensors are not CUDA tensors or the library is missing.
 """
 import ctypes
+import os
 
 import torch
 
@@ -74,10 +75,20 @@ class _CompositeFn(torch.autograd.Function):
         return d_rgb, d_density, None, None, None, None, None, None, None
 
 
+def _no_geometry_grads(who, z_vals, rays_d):
+    """The reference's autograd also differentiates through dists = diff(z_vals) * ||rays_d|| and depth = sum w z
+    (nerf_mlp.py:181-185,208); the CUDA backward returns gradients for rgb / density only.  No caller of the reference
+    asks for the others - if one does (learned poses, differentiable resampling) fail loudly instead of returning zeros."""
+    if torch.is_grad_enabled() and (z_vals.requires_grad or rays_d.requires_grad):
+        raise RuntimeError("%s: gradients w.r.t. z_vals / rays_d are not implemented by the CUDA compositing backward "
+                           "(detach them, or see INTEGRATION.md 'Differentiability')" % who)
+
+
 def composite(rgb, density, z_vals, rays_d, noise=None, noise_std=0.0, white_bkgd=False):
     """rgb (...,S,3), density (...,S,1)|(...,S), z_vals (...,S), rays_d (...,3)
     -> rgb_map (...,3), depth (...), weights (...,S)."""
     _need_cuda("composite", rgb, density, z_vals, rays_d, noise)
+    _no_geometry_grads("composite", z_vals, rays_d)
     lead = z_vals.shape[:-1]
     S = z_vals.shape[-1]
     if density.dim() == z_vals.dim() + 1:
@@ -105,6 +116,7 @@ def composite_packed(rgb_sigma, z_vals, rays_d, noise=None, noise_std=0.0, white
     """rgb_sigma (...,S,4), z_vals (...,S), rays_d (...,3) -> rgb_map (...,3)
     [, depth (...), weights (...,S) when want_aux]."""
     _need_cuda("composite_packed", rgb_sigma, z_vals, rays_d, noise)
+    _no_geometry_grads("composite_packed", z_vals, rays_d)
     lead = z_vals.shape[:-1]
     if rgb_sigma.shape[:-1] != z_vals.shape or rgb_sigma.shape[-1] != 4 or rays_d.shape != (*lead, 3):
         raise RuntimeError("composite_packed: shape mismatch rgb_sigma %s z_vals %s rays_d %s" % (
@@ -209,6 +221,7 @@ def composite_loss(rgb, density, z_vals, rays_d, target_rgb, target_depth=None, 
     ops.composite and apply models.nerf_mlp.NeRFLoss."""
     packed = density is None
     _need_cuda("composite_loss", rgb, density, z_vals, rays_d, target_rgb, target_depth)
+    _no_geometry_grads("composite_loss", z_vals, rays_d)
     if z_vals.dim() != 2 or z_vals.shape[1] < 2:
         raise RuntimeError("composite_loss: z_vals must be (N,S) with S >= 2")
     N, S = z_vals.shape
@@ -366,7 +379,15 @@ def sample_hierarchical(rays_o, rays_d, z_vals, weights, n_importance, u=None, c
         raise RuntimeError("sample_hierarchical: need at least one bin")
     Ni = int(n_importance)
     dev = z_vals.device
+    # The resampling is evaluated without autograd (the reference's is differentiable w.r.t. weights / z_vals through the
+    # interpolation, ray_utils.py:132-135; NeRF pipelines detach there and so does every caller in the reference):
+    # inputs are detached, INTEGRATION.md 'Differentiability'.
+    rays_o, rays_d, z_vals, weights, cdf = (t.detach() if t is not None else None for t in (rays_o, rays_d, z_vals, weights, cdf))
     rays_o, rays_d, z_vals, weights, cdf = _f32c(rays_o), _f32c(rays_d), _f32c(z_vals), _f32c(weights), _f32c(cdf)
+    if os.environ.get("NFS_DEBUG_CHECKS", "0") != "0" and z_vals.numel() and not bool((z_vals[:, 1:] >= z_vals[:, :-1]).all()):
+        # the kernel merges the new samples into z_vals by rank and needs z_vals ascending (every sampler of the
+        # reference produces ascending depths); the reference's torch.sort would also accept unsorted input
+        raise RuntimeError("sample_hierarchical: z_vals must be ascending along the last dimension")
     if u is None:
         raise RuntimeError("sample_hierarchical: u is required (draws or the linspace table)")
     u = _f32c(u)
