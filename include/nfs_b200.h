@@ -285,7 +285,7 @@ int nfs_composite_bwd_dy(const float *rgb_sigma, const float *z_vals, const floa
  *   remaining CTAs compute the weight / bias gradients `jobs` (nfs_wgrad_job, as nfs_wgrad_multi_bf16), consuming the
  *   chain's output quad by quad (512 rows) through L2 as soon as it has been stored.  job_waits[i] != 0 marks a job
  *   whose operands are (partly) produced by this launch's chain (they are read only after the chain has published the
- *   rows); 0 = operands complete before the launch.  quad_flags: >= ceil(n_points / 512) uint32 of device scratch
+ *   rows); 0 = operands complete before the launch.  quad_flags: >= 2 * ceil(n_points / 512) uint32 of device scratch
  *   (zeroed by the call).  Replaces autograd's backward of nerf_model.NeRFMLP (src/models/nerf_model.py:16-24):
  *   dX_l = (dY_l W_l) * ReLU'(h_l), dW_l = dY_l^T h_{l-1}, db_l = sum_p dY_l, for all points of a training step. */
 int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int32_t n_layers, const int32_t *k_dims,

@@ -20,7 +20,7 @@
 // bound by the SM (shared-memory / store bandwidth), the weight gradients by DRAM: run side by side they overlap, and a
 // dY tile is read back while it is still resident in the 126 MB L2.
 #include "fused_mlp_body.cuh"
-#include "wgrad_body.cuh"
+#include "wgrad_pair_body.cuh"
 
 #include <cstdlib>
 
@@ -34,27 +34,48 @@ struct alignas(64) BackwardJobs {
   WgradArgs a[kBwMaxJobs];
   unsigned cta0[kBwMaxJobs + 1];        // job j owns consumer CTAs cta0[j] .. cta0[j+1]
   int waits[kBwMaxJobs];                // 1: the job's operands are produced by the chain of this launch
+  int paired[kBwMaxJobs];               // 1: the job's CTAs work as pairs (wgrad_pair_body), 0: one by one (wgrad_body)
   int n_jobs;
   unsigned producer_ctas;
   unsigned int *quad_done;
   unsigned quad_target;                 // arrivals per quad: 16 epilogue warps x 2 CTAs
+  unsigned int *quad_consumed;          // back-pressure: jobs that have loaded the quad (NULL = off)
+  unsigned consumed_target;             // number of jobs that wait for the chain
+  long long window;                     // producers stay at most this many quads ahead of the consumers
+  int print_times;                      // developer switch NFS_BWD_TIMES: every CTA prints its role and start / end time
 };
+
+__device__ __forceinline__ unsigned long long bw_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFmThreads, 1)
 backward_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_save, const __grid_constant__ CUtensorMap tmap_b,
                       const FusedArgs a, const __grid_constant__ BackwardJobs jobs) {
+  const unsigned long long t_start = jobs.print_times ? bw_now() : 0ull;
   if (blockIdx.x < jobs.producer_ctas) {
     chain_body<true, false>(&tmap_x, &tmap_w, &tmap_save, &tmap_b, a, blockIdx.x >> 1, jobs.producer_ctas >> 1,
-                            jobs.quad_done);
+                            jobs.quad_done, jobs.quad_consumed, jobs.consumed_target, jobs.window);
   } else {
     const unsigned c = blockIdx.x - jobs.producer_ctas;
     if (c >= jobs.cta0[jobs.n_jobs]) return;          // the CTA that rounds the grid up to whole clusters
     int j = 0;
     while (j + 1 < jobs.n_jobs && c >= jobs.cta0[j + 1]) ++j;
-    wgrad_body(&jobs.tu[j], &jobs.tv[j], jobs.a[j], c - jobs.cta0[j], jobs.cta0[j + 1] - jobs.cta0[j],
-               jobs.waits[j] ? jobs.quad_done : nullptr, jobs.quad_target);
+    if (jobs.paired[j])
+      wgrad_pair_body(&jobs.tu[j], &jobs.tv[j], jobs.a[j], (c - jobs.cta0[j]) >> 1, (jobs.cta0[j + 1] - jobs.cta0[j]) >> 1,
+                      jobs.waits[j] ? jobs.quad_done : nullptr, jobs.quad_target,
+                      jobs.waits[j] ? jobs.quad_consumed : nullptr);
+    else
+      wgrad_body(&jobs.tu[j], &jobs.tv[j], jobs.a[j], c - jobs.cta0[j], jobs.cta0[j + 1] - jobs.cta0[j],
+                 jobs.waits[j] ? jobs.quad_done : nullptr, jobs.quad_target, jobs.waits[j] ? jobs.quad_consumed : nullptr);
+    if (jobs.print_times && threadIdx.x == 0)
+      printf("bwtimes consumer cta %u job %d of %u start %llu end %llu\n", c, j, jobs.cta0[j + 1] - jobs.cta0[j], t_start, bw_now());
+    return;
   }
+  if (jobs.print_times && threadIdx.x == 0) printf("bwtimes producer cta %u start %llu end %llu\n", blockIdx.x, t_start, bw_now());
 }
 
 }  // namespace
@@ -86,7 +107,6 @@ extern "C" int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int
   const long long n_quads = ((n_points + 127) / 128 + 3) / 4;
 
   BackwardJobs m{};
-  double bytes[kBwMaxJobs], total = 0.0;
   long long slabs[kBwMaxJobs];
   size_t smem = kChainSmemBytes;
   int k = 0;
@@ -99,46 +119,81 @@ extern "C" int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int
     if (rc == 1) continue;
     if (rc) return rc;
     if (sm > smem) smem = sm;
-    m.waits[k] = job_waits[i] != 0;
+    m.waits[k] = job_waits[i] != 0 && getenv("NFS_BWD_NOWAIT") == nullptr;   // (developer switch: timing only, wrong results)
     slabs[k] = ((j.n_points + kSlabP - 1) / kSlabP + 7) / 8;           // scheduling units: quads of 8 slabs
-    bytes[k] = (double)j.n_points * (j.m_dim + j.n_dim) * 2.0 + 8e5;    // + the fixed cost of a CTA, in byte-equivalents
-    total += bytes[k];
     ++k;
   }
   if (k == 0) return fail_arg(fn, NFS_E_BADARG, "no non-empty weight-gradient job");
   // Split of the CTA pairs between the chain (producers) and the weight gradients (consumers).  Default from the
   // measured balance on B200 (scripts/dev/ab_backward.py); NFS_BWD_PRODUCERS overrides it for experiments.
-  int prod = producer_pairs > 0 ? producer_pairs : 40;
+  int prod = producer_pairs > 0 ? producer_pairs : (pairs + 2) / 2;
   if (const char *e = getenv("NFS_BWD_PRODUCERS")) { if (atoi(e) > 0) prod = atoi(e); }
   if ((long long)prod > n_quads) prod = (int)n_quads;
-  int min_cons_pairs = (k + 1) / 2;
+  int min_cons_pairs = k;
   if (prod > pairs - min_cons_pairs) prod = pairs - min_cons_pairs;
   if (prod < 1) return fail_arg(fn, NFS_E_UNSUPPORTED, "too few SMs for the producer / consumer split");
-  const unsigned consumers = (unsigned)(2 * (pairs - prod));
+  // The consumer PAIRS are divided among the jobs in proportion to their cost (largest remainder, at least one pair
+  // each).  Cost per point, measured on B200 with the jobs confined to 16-36 SMs (scripts/dev/wgrad_pair.py): a pair
+  // takes a 64-point slab of a 256 x 256 job in 390 ns, of the first layer's job (N = 64, column sums on the tensor
+  // core) in 260 ns, of the head's (N = 64, column sums from shared memory) in 380 ns; jobs the pair body does not
+  // cover run CTA by CTA (wgrad_body) at about twice that.  Inside the merged kernel, with the chain running beside them,
+  // the three take ~470 / 370 / 515 ns (scripts/dev/bwd_times.py) - the weights below.
+  const int cons_pairs = pairs - prod;
+  double small_w = 0.8, head_w = 0.97;
+  if (const char *e = getenv("NFS_BWD_SMALL_W")) small_w = atof(e);
+  if (const char *e = getenv("NFS_BWD_HEAD_W")) head_w = atof(e);
+  double cost[kBwMaxJobs], cost_total = 0.0;
+  for (int i = 0; i < k; ++i) {
+    m.paired[i] = wgrad_pair_ok(m.a[i]) && getenv("NFS_BWD_NOPAIR") == nullptr;
+    if (m.paired[i] && kWpSmemBytes > smem) smem = kWpSmemBytes;
+    double w = 2.0 * (m.a[i].M + m.a[i].N) / 512.0;
+    if (m.paired[i]) w = m.a[i].N == 256 ? 1.0 : (m.a[i].colsum != nullptr && m.a[i].colsum_of_v ? head_w : small_w);
+    cost[i] = (double)m.a[i].P * w + 4e3;
+    cost_total += cost[i];
+  }
+  int counts[kBwMaxJobs], given = 0;
+  double frac[kBwMaxJobs];
+  for (int i = 0; i < k; ++i) {
+    const double want = cons_pairs * cost[i] / cost_total;
+    counts[i] = (int)want < 1 ? 1 : (int)want;
+    frac[i] = want - counts[i];
+    given += counts[i];
+  }
+  while (given < cons_pairs) {
+    int best = 0;
+    for (int i = 1; i < k; ++i) if (frac[i] > frac[best]) best = i;
+    ++counts[best]; frac[best] -= 1.0; ++given;
+  }
+  while (given > cons_pairs) {
+    int worst = -1;
+    for (int i = 0; i < k; ++i) if (counts[i] > 1 && (worst < 0 || frac[i] < frac[worst])) worst = i;
+    if (worst < 0) return fail_arg(fn, NFS_E_UNSUPPORTED, "more weight-gradient jobs than consumer pairs");
+    --counts[worst]; frac[worst] += 1.0; --given;
+  }
   unsigned used = 0;
   for (int i = 0; i < k; ++i) {
-    long long c = (long long)(consumers * bytes[i] / total);
-    if (c < 1) c = 1;
-    if (c > slabs[i]) c = slabs[i];
+    const long long units = slabs[i];                              // no more pairs / CTAs than scheduling units (quads)
+    long long c = 2LL * counts[i];
+    if (!m.paired[i] && c > units + (units & 1)) c = units + (units & 1);
+    if (m.paired[i] && c > 2 * units) c = 2 * units;
     m.cta0[i] = used;
     used += (unsigned)c;
   }
   m.cta0[k] = used;
-  if (used < consumers) {
-    // distribute the remainder: rebuild the ranges with +1 for the first (consumers - used) jobs that can take it
-    unsigned extra = consumers - used, counts[kBwMaxJobs];
-    for (int i = 0; i < k; ++i) counts[i] = m.cta0[i + 1] - m.cta0[i];
-    for (int pass = 0; pass < 8 && extra > 0; ++pass)
-      for (int i = 0; i < k && extra > 0; ++i)
-        if ((long long)counts[i] < slabs[i]) { ++counts[i]; --extra; }
-    used = 0;
-    for (int i = 0; i < k; ++i) { m.cta0[i] = used; used += counts[i]; }
-    m.cta0[k] = used;
-  }
   m.n_jobs = k;
   m.producer_ctas = (unsigned)(2 * prod);
   m.quad_done = quad_flags;
   m.quad_target = 32;
+  // back-pressure window (quads): the dY of `window` quads (1.8 MB each for 7 x 256-wide layers) should fit L2 beside the
+  // streamed activations; NFS_BWD_WINDOW=0 switches it off
+  long long window = 2LL * prod;
+  if (const char *e = getenv("NFS_BWD_WINDOW")) window = atoll(e);
+  int n_wait = 0;
+  for (int i = 0; i < k; ++i) n_wait += m.waits[i];
+  m.quad_consumed = window > 0 ? quad_flags + n_quads : nullptr;
+  m.consumed_target = (unsigned)n_wait;
+  m.window = window;
+  m.print_times = getenv("NFS_BWD_TIMES") != nullptr;
   unsigned grid = m.producer_ctas + used;
   grid += grid & 1u;                                  // whole clusters (the surplus CTA returns at once)
 
@@ -149,7 +204,7 @@ extern "C" int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int
     if (e != cudaSuccess) return fail_cuda(fn, e);
     attr_once.mark(attr_dev);
   }
-  cudaError_t e = cudaMemsetAsync(quad_flags, 0, (size_t)n_quads * sizeof(uint32_t), (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(quad_flags, 0, (size_t)2 * n_quads * sizeof(uint32_t), (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(fn, e);
   backward_fused_kernel<<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a, m);
   return check_launch(fn);

@@ -90,55 +90,6 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// ---- CTA-pair plumbing
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the pair
-__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// Barriers signalled from the peer CTA / by multicast commits are waited on with the default
-// (.acquire.cta) try_wait like every other barrier: a cluster-scope acquire costs ~400 cycles per wait
-// (measured with the timeline tracer) and the data these barriers guard is read through the async
-// proxy (UMMA operands, TMEM), which the arriving side orders with fence.proxy.async / tcgen05 fences.
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
-// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset): both CTAs of the
-// pair fill their own shared memory, one barrier in the leader counts all the bytes.
-__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int c_inner, int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// all prior MMAs of this thread -> one arrive on `bar` (same offset) in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
-// one lane of the (converged) warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 __device__ __forceinline__ float fm_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // bf16x2 pack with the ReLU folded into the conversion
@@ -237,7 +188,8 @@ template <bool kMasked, bool kTrain>
 __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CUtensorMap *tmap_w_p,
                                            const CUtensorMap *tmap_save_p, const CUtensorMap *tmap_b_p,
                                            const FusedArgs &a, const long long quad0, const long long quad_step,
-                                           unsigned int *quad_done) {
+                                           unsigned int *quad_done, const unsigned int *quad_consumed = nullptr,
+                                           const unsigned consumed_target = 0, const long long window = 0) {
   const CUtensorMap &tmap_x = *tmap_x_p, &tmap_w = *tmap_w_p, &tmap_save = *tmap_save_p, &tmap_b = *tmap_b_p;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw;                      // SWIZZLE_128B operands need 1024-byte alignment (checked below)
@@ -310,6 +262,18 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
       uint32_t wit = 0, iter = 0;
       const int ks0 = a.K[0] >> 6;
       for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
+        if (quad_consumed != nullptr && quad >= window) {
+          // back-pressure of the merged backward kernel (performance only, never correctness): stay at most `window`
+          // quads ahead of the weight-gradient consumers so that what this pair stores is still in L2 when they read
+          // it.  Gives up after ~2 ms: producers must never depend on consumers for progress.
+          const unsigned int *c = quad_consumed + (quad - window);
+          for (uint32_t spin = 0; spin < (1u << 12); ++spin) {
+            unsigned v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+            if (v >= consumed_target) break;
+            __nanosleep(100);
+          }
+        }
         for (int t = 0; t < 2 && a.points == nullptr; ++t) {
           mbar_wait_relaxed(act_free + t, (iter & 1) ^ 1);
           mbar_wait_relaxed(head_done + t, (iter & 1) ^ 1);

@@ -146,6 +146,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---------------------------------------------------------------- CTA-pair plumbing (clusters of 2, tcgen05 cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the pair
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Barriers signalled from the peer CTA / by multicast commits are waited on with the default
+// (.acquire.cta) try_wait like every other barrier: a cluster-scope acquire costs ~400 cycles per wait
+// (measured with the timeline tracer) and the data these barriers guard is read through the async
+// proxy (UMMA operands, TMEM), which the arriving side orders with fence.proxy.async / tcgen05 fences.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset): both CTAs of the
+// pair fill their own shared memory, one barrier in the leader counts all the bytes.
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all prior MMAs of this thread -> one arrive on `bar` (same offset) in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
 //   K-major operand : rows are MN, each row 64 bf16 (128 B), 8 rows = one 1024 B swizzle

@@ -1,6 +1,6 @@
 // K3 (weight gradients): kernel instantiations + C ABI; the body lives in wgrad_body.cuh (it is also the consumer
 // half of the merged backward kernel, backward.cu).
-#include "wgrad_body.cuh"
+#include "wgrad_pair_body.cuh"
 
 namespace nfs {
 namespace {
@@ -8,6 +8,13 @@ namespace {
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v, const WgradArgs a) {
   wgrad_body(&tmap_u, &tmap_v, a, blockIdx.x, gridDim.x);
+}
+
+// CTA-pair form (wgrad_pair_body.cuh): the consumer layout of the merged backward kernel, launchable on its own for
+// parity tests and per-SM throughput measurements (NFS_WGRAD_PAIR=1, developer switch).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_v, const WgradArgs a) {
+  wgrad_pair_body(&tmap_u, &tmap_v, a, blockIdx.x >> 1, gridDim.x >> 1);
 }
 
 // Several independent weight-gradient jobs in ONE launch (the ~21 layers of NeRFWithDINO at a few ten thousand
@@ -38,6 +45,8 @@ static int wgrad_attrs(const char *fn) {
   if (attr_once.need(&attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail_cuda(fn, e);
     attr_once.mark(attr_dev);
@@ -64,6 +73,12 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
   // points, so small launches want ALL SMs to keep the streaming part short (scripts/dev/wgrad_trace.py).
   long long g = n_slabs < sms ? n_slabs : sms;
   if (const char *force = getenv("NFS_WGRAD_GRID")) g = atoll(force) > 0 && atoll(force) < g ? atoll(force) : g;   // developer switch
+  if (getenv("NFS_WGRAD_PAIR") != nullptr && wgrad_pair_ok(a)) {       // developer switch: the CTA-pair body on its own
+    long long gp = n_slabs < sms / 2 ? n_slabs : sms / 2;
+    if (const char *force = getenv("NFS_WGRAD_GRID")) gp = atoll(force) / 2 > 0 && atoll(force) / 2 < gp ? atoll(force) / 2 : gp;
+    wgrad_pair_kernel<<<(unsigned)(2 * gp), kWgThreads, kWpSmemBytes, (cudaStream_t)stream>>>(tu, tv, a);
+    return check_launch(fn);
+  }
   wgrad_kernel<<<(unsigned)g, kWgThreads, smem, (cudaStream_t)stream>>>(tu, tv, a);
   return check_launch(fn);
 }

@@ -57,7 +57,8 @@ struct WgradArgs {
 // completed their stores of that 512-row quad).
 __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CUtensorMap *tmap_v_p, const WgradArgs &a,
                                            const unsigned cta, const unsigned n_cta,
-                                           const unsigned int *quad_done = nullptr, const unsigned quad_target = 0) {
+                                           const unsigned int *quad_done = nullptr, const unsigned quad_target = 0,
+                                           unsigned int *quad_consumed = nullptr) {
   const CUtensorMap &tmap_u = *tmap_u_p, &tmap_v = *tmap_v_p;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -72,9 +73,12 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
   const long long n_slabs = (a.P + kSlabP - 1) / kSlabP;
   const long long U = quad_done != nullptr ? 8 : 1;
   const bool do_colsum = a.colsum != nullptr;
+  // column-sum warps: 4 in the stand-alone kernels (6 warps per CTA), 16 in the merged backward kernel (CTAs of 18 warps),
+  // where a job confined to a few SMs must take a slab every ~1000 cycles: group g sums the rows [g, g + 1) * 64 / groups
+  const int cs_groups = (int)(blockDim.x >> 5) >= 18 ? 4 : 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, do_colsum ? 5 : 1); }
+    for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, do_colsum ? 1 + 4 * cs_groups : 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_u);
@@ -96,6 +100,7 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
       NFS_WG_FOR_SLABS(slab, it) {
         const uint32_t stage = it % S, ph = (it / S) & 1;
         if (quad_done != nullptr && (slab >> 3) != quad_seen) {
+          if (quad_consumed != nullptr && quad_seen >= 0) atomicAdd(quad_consumed + quad_seen, 1u);   // back-pressure credit
           // hand-off from the dgrad chain: acquire the quad's counter, then order the TMA (async proxy) loads after it
           const unsigned int *flag = quad_done + (slab >> 3);
           for (uint32_t spin = 0;; ++spin) {
@@ -119,6 +124,7 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
         for (int b = 0; b < mb; ++b) tma_load_2d(us + b * kBlockBytes, &tmap_u, full + stage, b * 64, row);
         for (int b = 0; b < nb; ++b) tma_load_2d(vs + b * kBlockBytes, &tmap_v, full + stage, b * 64, row);
       }
+      if (quad_consumed != nullptr && quad_seen >= 0) atomicAdd(quad_consumed + quad_seen, 1u);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -144,8 +150,9 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
       }
       umma_commit(acc_full);
     }
-  } else if (warp < 6) {                      // (the merged backward kernel runs this body in CTAs of 18 warps)
-    const int et = threadIdx.x - 64;          // 0..127
+  } else if (warp < 2 + 4 * cs_groups) {
+    const int et = (threadIdx.x - 64) & 127;  // 0..127
+    const int grp = (warp - 2) >> 2, rows_per = kSlabP / cs_groups;
     if (do_colsum) {
       // thread owns columns 2*et, 2*et+1 of the summed operand (<= 256 columns)
       const int ncols = a.colsum_of_v ? a.N : a.M;
@@ -160,7 +167,7 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
         if (active && !(a.dbg & 2)) {
           const uint8_t *base = smem + stage * stage_bytes + (a.colsum_of_v ? mb * kBlockBytes : 0) + blk * kBlockBytes;
 #pragma unroll 8
-          for (int p = 0; p < kSlabP; ++p) {
+          for (int p = grp * rows_per; p < (grp + 1) * rows_per; ++p) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(base + p * 128 + ((((cc >> 3) ^ (p & 7))) << 4) + (cc & 7) * 2);
             s0 += __uint_as_float(w << 16);
             s1 += __uint_as_float(w & 0xFFFF0000u);
@@ -172,7 +179,9 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
       const int cvalid = a.colsum_of_v ? a.n_valid : a.m_valid;
       if (active && col < cvalid) atomicAdd(a.colsum + col, s0);
       if (active && col + 1 < cvalid) atomicAdd(a.colsum + col + 1, s1);
+      if (cs_groups > 1) asm volatile("bar.sync 2, 512;" ::: "memory");   // all sixteen have finished reading the ring
     }
+    if (warp >= 6) goto wg_done;              // the four drain warps (TMEM lane quadrants) are warps 2..5
     // drain the accumulators
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -235,6 +244,7 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
     }
   }
 
+wg_done:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -546,15 +546,16 @@ class StepSession:
             self.head_w = torch.zeros((64, plan.h_pad), device=dev, dtype=torch.float32)
             self.head_b = torch.zeros(64, device=dev, dtype=torch.float32)
             self.w0_t = torch.zeros((plan.k0, plan.h_pad), device=dev, dtype=torch.float32)
-            self.quad_flags = torch.zeros(rows // 512 + 2, device=dev, dtype=torch.int32)
+            self.quad_flags = torch.zeros(2 * (rows // 512 + 2), device=dev, dtype=torch.int32)
         self.cursor = 0
         self.pending = 0
         self.dy_written = set()
-        # NFS_BWD_MERGED=1: one launch for the whole backward pass (nfs_mlp_backward_fused: dgrad chain on producer CTA
-        # pairs, weight gradients on consumer CTAs fed through L2).  Parity-green but SLOWER than the default route
-        # (dgrad chain per call + one weight-gradient launch per layer) on B200 - 4.6 vs 4.0 ms per cfg 3 step at the
-        # best split - so it stays opt-in.
-        self.merged = os.environ.get("NFS_BWD_MERGED", "0") != "0" and plan.h_pad == 256
+        # One launch for the whole backward pass (nfs_mlp_backward_fused: dgrad chain on producer CTA pairs, weight
+        # gradients on consumer CTA pairs fed through L2) when the step is large enough to fill the persistent grid
+        # (3.9 vs 4.1-4.3 ms per cfg 3 step); small steps and other widths take the dgrad chain per
+        # call + one weight-gradient launch per layer.  NFS_BWD_MERGED=0 / 1 forces either route.
+        force = os.environ.get("NFS_BWD_MERGED", "")
+        self.merged = plan.h_pad == 256 and (force not in ("", "0") if force != "" else rows >= 65536)
         self.opt.grad.zero_()
         self.head_w.zero_()
         self.head_b.zero_()
