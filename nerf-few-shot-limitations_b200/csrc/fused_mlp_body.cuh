@@ -168,13 +168,20 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&r)[16], int act, uint32_t b
 #define NFS_DBG(a) 0
 #else
 #define NFS_DBG(a) ((a).dbg)
-// Developer timeline: CTA 0 appends (clock << 16 | code << 12 | layer << 4 | tile) per warp.
+// Developer timeline: CTAs 0 and 1 (one pair) append (time << 16 | code << 12 | layer << 4 | tile) per warp; time =
+// clock64 of the SM, or (debug flag 64) the global nanosecond timer, which both CTAs of the pair share.
+__device__ __forceinline__ unsigned long long fm_trace_time(int dbg) {
+  unsigned long long t;
+  if (dbg & 64) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  else t = (unsigned long long)clock64();
+  return t;
+}
 #define NFS_TRACE(code, l, t)                                                                       \
   do {                                                                                              \
-    if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 1023) {                     \
-      a.trace[warp * 1024 + 1 + trace_n++] =                                                        \
-          ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 12) | ((l) << 4) | (t); \
-      a.trace[warp * 1024] = trace_n;                                                               \
+    if (a.trace != nullptr && blockIdx.x < 2 && lane == 0 && trace_n < 1023) {                      \
+      unsigned long long *tb_ = a.trace + blockIdx.x * 18 * 1024 + warp * 1024;                     \
+      tb_[1 + trace_n++] = (fm_trace_time(a.dbg) << 16) | ((unsigned long long)(code) << 12) | ((l) << 4) | (t); \
+      tb_[0] = trace_n;                                                                             \
     }                                                                                               \
   } while (0)
 #endif
@@ -314,6 +321,19 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
       const bool use_bias = a.has_bias && !(NFS_DBG(a) & 8);
       const uint64_t ones_desc = umma_desc_noswizzle(smem_u32(s_ones), 128, 0);
       const uint64_t bias_desc = umma_desc_noswizzle(smem_u32(s_bias), 0, 128);
+      // the barriers a tile step (layer l, tile t) needs before its first MMA.  (Acquiring them one slab EARLY, while the
+      // previous step's last MMAs are still queued, was tried and is slower - 0.61 vs 0.56 ms for the inference chain: the
+      // tile's epilogue + hand-off completes just about when the other tile's MMAs have been issued, so an early wait
+      // holds that last slab back.  scripts/trace_fused.py, gpurun_out/r2_ab_lookahead.log)
+      auto wait_input = [&](int l, int t) {
+        if (l == 0) {
+          mbar_wait_cluster(acc_free + t, (iter & 1) ^ 1);   // accumulator t drained by the previous quad's last layer
+          mbar_wait_cluster((a.points != nullptr ? in_ready : in_full) + t, iter & 1);
+        } else {
+          mbar_wait_cluster(act_ready + t, n_ready[t] & 1);
+          ++n_ready[t];
+        }
+      };
       for (long long quad = quad0; quad < n_quads; quad += quad_step, ++iter) {
         // Issue order per layer: tile major - 4*ks MMAs on the pair's A tiles, then 4*ks on the B tiles.
         // Long runs on one accumulator (switching the D operand between consecutive MMAs costs
@@ -324,14 +344,10 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
           const uint32_t idesc = umma_idesc_bf16(256, a.N[l], 0, 0);
 #pragma unroll 1
           for (int t = 0; t < 2; ++t) {
-            if (l == 0) {
-              mbar_wait_cluster(acc_free + t, (iter & 1) ^ 1);   // accumulators t drained by the previous quad's last layer
-              mbar_wait_cluster((a.points != nullptr ? in_ready : in_full) + t, iter & 1);
-            } else {
-              mbar_wait_cluster(act_ready + t, n_ready[t] & 1);
-              ++n_ready[t];
-            }
-            tc_fence_after();
+            wait_input(l, t);
+            NFS_TRACE(14, l, t);
+            NFS_TRACE(15, l, t);
+            if (!(NFS_DBG(a) & 128)) tc_fence_after();
             NFS_TRACE(1, l, t);
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
             // descriptors differ only in their 14-bit start-address field: +2 per 32-byte K step
@@ -348,6 +364,7 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
               if (t == 0) {
                 if (!((NFS_DBG(a) & 2) && w >= kWStages)) mbar_wait_cluster(w_full + stage, wph);
                 tc_fence_after();
+                NFS_TRACE(10 + s, l, t);
               }
               const uint64_t ad = a_desc0 + (uint64_t)((s * kActSlab) >> 4);
               const uint64_t bd = b_desc0 + (uint64_t)((stage * kWStage) >> 4);
@@ -361,6 +378,7 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
                 if (t == 1) umma_commit_pair(w_empty + stage);
               }
               __syncwarp();
+              NFS_TRACE(6 + s, l, t);
             }
             if (t == 0 && use_bias) {           // tile A: bias last (its operand has had the whole pass to land)
               mbar_wait_cluster(bias_full, (iter * (uint32_t)L + (uint32_t)l) & 1);
@@ -374,6 +392,7 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
               if (l == L - 1) umma_commit_pair(act_free + t);
             }
             __syncwarp();
+            NFS_TRACE(0, l, t);
           }
           wit += ks;
         }
@@ -387,6 +406,9 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
     const int cq = (warp - 2) >> 2;
     const int r_in = q * 32 + lane;
     uint32_t n_full[2] = {0, 0}, gl = 0;
+#ifdef NFS_DEVTOOLS
+    uint32_t n_arr[2] = {0, 0};          // tracer probe: phases of act_ready this warp has arrived on
+#endif
     uint2 b_n1 = make_uint2(0u, 0u), b_n2 = make_uint2(0u, 0u);   // sign bits of the next two epilogue steps
     bool store_pending = false;
     const uint32_t ready_bar[2] = {map_to_cta(act_ready, 0), map_to_cta(act_ready + 1, 0)};   // in the leader CTA
@@ -489,6 +511,7 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
             if (l + 1 < L && a.act[l + 1] == 4 && tile < n_tiles) b_n2 = load_bits(l + 1);
           }
           uint32_t bits_acc[2] = {0u, 0u};
+          NFS_TRACE(15, l, t);
           mbar_wait_relaxed(acc_full + t, n_full[t] & 1);
           ++n_full[t];
           tc_fence_after();
@@ -505,13 +528,17 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
               __syncwarp();
               if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             }
+            NFS_TRACE(14, l, t);
             uint8_t *srow = act_t + (c0 >> 6) * kActSlab + r_in * 128;
             const int ch0 = (c0 & 63) >> 3;
             if (NFS_DBG(a) & 1) {
               // bisection: no TMEM drain, no math, no smem writes
             } else {
               // `quarter` (64 or 32) columns in chunks of 16 (small chunks leave registers for a whole chunk of
-              // bias values to be in flight at once; the other three warps of the scheduler hide the latencies)
+              // bias values to be in flight at once; the other three warps of the scheduler hide the latencies).
+              // Software-pipelining the chunks over two register buffers (chunk c + 1 in flight from TMEM while chunk c
+              // is converted) was measured on one box against this form: inference chain 0.495 vs 0.485 ms, dgrad chain
+              // 0.89 vs 0.77 ms - slower (96 registers), gpurun_out/r2_ab_libs1.log.
               const int n_chunks = quarter >> 4;
               uint32_t va[16];
 #pragma unroll
@@ -537,6 +564,16 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
             if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             if (lane == 0) {
               if (!last) mbar_arrive_cluster(ready_bar[t]);
+#ifdef NFS_DEVTOOLS
+              if (!last) {
+                // tracer probe (leader CTA, one warp): when does the act_ready phase this warp just arrived on complete?
+                if (a.trace != nullptr && blockIdx.x == 0 && warp == 2) {
+                  for (int spin = 0; spin < 100000 && !mbar_try_wait(act_ready + t, n_arr[t] & 1); ++spin) { }
+                  NFS_TRACE(13, l, t);
+                }
+                ++n_arr[t];
+              }
+#endif
               if (do_save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
                 tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
                              (int)(l * a.save_rows + tile * 128 + q * 32));
