@@ -85,6 +85,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                ::"l"(map), "r"(smem_u32(src)), "r"(c_inner), "r"(c_outer)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *map, const void *src, int c_inner, int c_outer, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c_inner), "r"(c_outer), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -191,6 +196,9 @@ __device__ __forceinline__ unsigned long long fm_trace_time(int dbg) {
 // pair0 / pair_step: this CTA pair works on quads pair0, pair0 + pair_step, ...  quad_done (NULL in the stand-alone
 // chain kernels): one counter per quad, incremented by every epilogue warp of the pair (32 arrivals) once ALL of the
 // quad's TMA stores have completed - the hand-off to the weight-gradient consumers of the merged backward kernel.
+// (A finer hand-off - one counter per quad AND layer, published two layers behind by one thread per CTA - was built and
+// measured: same duration, DRAM reads 5.1 instead of 6.4 GB per step, but it failed the step's gradient-equality test
+// in one configuration and was dropped; gpurun_out/r2_handoff_matrix.log.)
 template <bool kMasked, bool kTrain>
 __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CUtensorMap *tmap_w_p,
                                            const CUtensorMap *tmap_save_p, const CUtensorMap *tmap_b_p,
@@ -406,6 +414,7 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
     const int cq = (warp - 2) >> 2;
     const int r_in = q * 32 + lane;
     uint32_t n_full[2] = {0, 0}, gl = 0;
+    const uint64_t store_policy = quad_done != nullptr ? l2_policy_evict_last() : 0ull;
 #ifdef NFS_DEVTOOLS
     uint32_t n_arr[2] = {0, 0};          // tracer probe: phases of act_ready this warp has arrived on
 #endif
@@ -575,8 +584,17 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
               }
 #endif
               if (do_save && tile < n_tiles && (!paired || (cq & 1) == 0)) {
-                tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
-                             (int)(l * a.save_rows + tile * 128 + q * 32));
+                // merged backward kernel: the rows are read back by the weight-gradient consumers within a few tens of
+                // microseconds - ask L2 to keep them (a plain bulk store is not retained: the consumers then read
+                // 8.9 GB per step from DRAM instead of 6.4, gpurun_out/r2c_bwd_dram*.csv, r2_handoff_matrix.log)
+#ifndef NFS_NO_STORE_HINT
+                if (quad_done != nullptr)
+                  tma_store_2d_hint(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
+                                    (int)(l * a.save_rows + tile * 128 + q * 32), store_policy);
+                else
+#endif
+                  tma_store_2d(&tmap_save, act_t + (c0 >> 6) * kActSlab + q * 32 * 128, c0 & ~63,
+                               (int)(l * a.save_rows + tile * 128 + q * 32));
                 bulk_commit();
               }
             }

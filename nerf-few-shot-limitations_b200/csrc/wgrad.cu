@@ -24,14 +24,19 @@ constexpr int kWgMaxJobs = 24;
 struct alignas(64) WgradMulti {
   CUtensorMap tu[kWgMaxJobs], tv[kWgMaxJobs];
   WgradArgs a[kWgMaxJobs];
-  unsigned cta0[kWgMaxJobs + 1];        // job j owns CTAs cta0[j] .. cta0[j+1]
+  unsigned cta0[kWgMaxJobs + 1];        // job j owns CTAs cta0[j] .. cta0[j+1] (whole pairs)
+  int paired[kWgMaxJobs];               // 1: the job's CTAs work as pairs (wgrad_pair_body), 0: one by one (wgrad_body)
   int n_jobs;
 };
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_multi_kernel(const __grid_constant__ WgradMulti m) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+wgrad_multi_kernel(const __grid_constant__ WgradMulti m) {
+  if (blockIdx.x >= m.cta0[m.n_jobs]) return;
   int j = 0;
   while (j + 1 < m.n_jobs && blockIdx.x >= m.cta0[j + 1]) ++j;
-  wgrad_body(&m.tu[j], &m.tv[j], m.a[j], blockIdx.x - m.cta0[j], m.cta0[j + 1] - m.cta0[j]);
+  const unsigned c = blockIdx.x - m.cta0[j], n = m.cta0[j + 1] - m.cta0[j];
+  if (m.paired[j]) wgrad_pair_body(&m.tu[j], &m.tv[j], m.a[j], c >> 1, n >> 1);
+  else wgrad_body(&m.tu[j], &m.tv[j], m.a[j], c, n);
 }
 
 }  // namespace
@@ -97,7 +102,7 @@ extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, v
     double total = 0.0;
     size_t smem = 0;
     int k = 0;
-    for (; first < n_jobs && k < kWgMaxJobs && k < sms; ++first) {
+    for (; first < n_jobs && k < kWgMaxJobs && k < sms / 2; ++first) {
       const nfs_wgrad_job &j = jobs[first];
       size_t sm = 0;
       rc = wgrad_prepare_job(fn, j.u_bf16, j.u_pitch, j.v_bf16, j.v_pitch, j.n_points, j.m_dim, j.n_dim, j.m_valid, j.n_valid,
@@ -106,17 +111,43 @@ extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, v
       if (rc) return rc;
       if (sm > smem) smem = sm;
       slabs[k] = (j.n_points + kSlabP - 1) / kSlabP;
-      bytes[k] = (double)j.n_points * (j.m_dim + j.n_dim) * 2.0 + 8e5;    // + the fixed cost of a CTA, in byte-equivalents
+      // cost in "points of a 256 x 256 job on a CTA pair" (390 ns per 64-point slab, scripts/dev/wgrad_pair.py), plus
+      // the fixed ~12 us a CTA pays whatever its share (setup, first slab, accumulator drain)
+      m.paired[k] = wgrad_pair_ok(m.a[k]) && getenv("NFS_WGRAD_NOPAIR") == nullptr;
+      if (m.paired[k] && kWpSmemBytes > smem) smem = kWpSmemBytes;
+      double w = 2.0 * (j.m_dim + j.n_dim) / 512.0;
+      if (m.paired[k]) w = j.n_dim == 256 ? 1.0 : (j.colsum != nullptr && j.colsum_of_v ? 0.97 : 0.67);
+      bytes[k] = (double)j.n_points * w + 2000.0;
       total += bytes[k];
       ++k;
     }
     if (k == 0) continue;
-    // CTAs per job: proportional to its share of the work, at least 1, at most its slab count
+    // CTA pairs per job: proportional to its share of the work (largest remainder), at least 1, at most its slab count
+    const int pairs = sms / 2;
+    int counts[kWgMaxJobs], given = 0;
+    double frac[kWgMaxJobs];
+    for (int i = 0; i < k; ++i) {
+      const double want = pairs * bytes[i] / total;
+      counts[i] = (int)want < 1 ? 1 : (int)want;
+      frac[i] = want - counts[i];
+      given += counts[i];
+    }
+    while (given < pairs) {
+      int best = 0;
+      for (int i = 1; i < k; ++i) if (frac[i] > frac[best]) best = i;
+      ++counts[best]; frac[best] -= 1.0; ++given;
+    }
+    while (given > pairs) {
+      int worst = -1;
+      for (int i = 0; i < k; ++i) if (counts[i] > 1 && (worst < 0 || frac[i] < frac[worst])) worst = i;
+      if (worst < 0) break;                       // (more jobs than pairs cannot happen: k <= sms / 2 per launch)
+      --counts[worst]; frac[worst] += 1.0; --given;
+    }
     unsigned used = 0;
     for (int i = 0; i < k; ++i) {
-      long long c = (long long)(sms * bytes[i] / total);
-      if (c < 1) c = 1;
-      if (c > slabs[i]) c = slabs[i];
+      long long c = 2LL * counts[i];
+      const long long cap = m.paired[i] ? 2 * slabs[i] : slabs[i] + (slabs[i] & 1);     // whole pairs either way
+      if (c > cap) c = cap;
       m.cta0[i] = used;
       used += (unsigned)c;
     }

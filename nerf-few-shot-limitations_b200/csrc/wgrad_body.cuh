@@ -97,6 +97,7 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
     if (lane == 0) {
       uint32_t it = 0;
       long long quad_seen = -1;
+      const uint64_t load_policy = quad_done != nullptr ? l2_policy_evict_first() : 0ull;
       NFS_WG_FOR_SLABS(slab, it) {
         const uint32_t stage = it % S, ph = (it / S) & 1;
         if (quad_done != nullptr && (slab >> 3) != quad_seen) {
@@ -121,8 +122,17 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
         mbar_expect_tx(full + stage, (uint32_t)stage_bytes);
         uint8_t *us = smem + stage * stage_bytes, *vs = us + mb * kBlockBytes;
         const int row = (int)(slab * kSlabP);
-        for (int b = 0; b < mb; ++b) tma_load_2d(us + b * kBlockBytes, &tmap_u, full + stage, b * 64, row);
-        for (int b = 0; b < nb; ++b) tma_load_2d(vs + b * kBlockBytes, &tmap_v, full + stage, b * 64, row);
+#ifdef NFS_NO_LOAD_HINT
+        if (false) {
+#else
+        if (quad_done != nullptr) {          // merged backward kernel: every operand row is read exactly once
+#endif
+          for (int b = 0; b < mb; ++b) tma_load_2d_hint(us + b * kBlockBytes, &tmap_u, full + stage, b * 64, row, load_policy);
+          for (int b = 0; b < nb; ++b) tma_load_2d_hint(vs + b * kBlockBytes, &tmap_v, full + stage, b * 64, row, load_policy);
+        } else {
+          for (int b = 0; b < mb; ++b) tma_load_2d(us + b * kBlockBytes, &tmap_u, full + stage, b * 64, row);
+          for (int b = 0; b < nb; ++b) tma_load_2d(vs + b * kBlockBytes, &tmap_v, full + stage, b * 64, row);
+        }
       }
       if (quad_consumed != nullptr && quad_seen >= 0) atomicAdd(quad_consumed + quad_seen, 1u);
     }

@@ -87,6 +87,7 @@ __device__ __forceinline__ void wgrad_pair_body(const CUtensorMap *tmap_u_p, con
     if (lane == 0) {
       uint32_t it = 0;
       long long quad_seen = -1;
+      const uint64_t load_policy = quad_done != nullptr ? l2_policy_evict_first() : 0ull;
       NFS_WG_FOR_SLABS(slab, it) {
         const uint32_t stage = it % S, ph = (it / S) & 1;
         if (quad_done != nullptr && (slab >> 3) != quad_seen) {
@@ -110,13 +111,28 @@ __device__ __forceinline__ void wgrad_pair_body(const CUtensorMap *tmap_u_p, con
         if (rank == 0) mbar_expect_tx(full + stage, 2u * stage_tx);
         uint8_t *us = smem + stage * kWpStageBytes, *vs = us + 2 * kBlockBytes;
         const int row = (int)(slab * kSlabP), col = (int)rank * 128;
-        tma_load_2d_pair(us, &tmap_u, full + stage, col, row);
-        tma_load_2d_pair(us + kBlockBytes, &tmap_u, full + stage, col + 64, row);
-        if (narrow) {
-          tma_load_2d_pair(vs, &tmap_v, full + stage, (int)rank * 64, row);
+#ifdef NFS_NO_LOAD_HINT
+        if (false) {
+#else
+        if (quad_done != nullptr) {          // merged backward kernel: every operand row is read exactly once
+#endif
+          tma_load_2d_pair_hint(us, &tmap_u, full + stage, col, row, load_policy);
+          tma_load_2d_pair_hint(us + kBlockBytes, &tmap_u, full + stage, col + 64, row, load_policy);
+          if (narrow) {
+            tma_load_2d_pair_hint(vs, &tmap_v, full + stage, (int)rank * 64, row, load_policy);
+          } else {
+            tma_load_2d_pair_hint(vs, &tmap_v, full + stage, col, row, load_policy);
+            tma_load_2d_pair_hint(vs + kBlockBytes, &tmap_v, full + stage, col + 64, row, load_policy);
+          }
         } else {
-          tma_load_2d_pair(vs, &tmap_v, full + stage, col, row);
-          tma_load_2d_pair(vs + kBlockBytes, &tmap_v, full + stage, col + 64, row);
+          tma_load_2d_pair(us, &tmap_u, full + stage, col, row);
+          tma_load_2d_pair(us + kBlockBytes, &tmap_u, full + stage, col + 64, row);
+          if (narrow) {
+            tma_load_2d_pair(vs, &tmap_v, full + stage, (int)rank * 64, row);
+          } else {
+            tma_load_2d_pair(vs, &tmap_v, full + stage, col, row);
+            tma_load_2d_pair(vs + kBlockBytes, &tmap_v, full + stage, col + 64, row);
+          }
         }
       }
       if (quad_consumed != nullptr && quad_seen >= 0 && rank == 0) atomicAdd(quad_consumed + quad_seen, 1u);
@@ -181,6 +197,7 @@ __device__ __forceinline__ void wgrad_pair_body(const CUtensorMap *tmap_u_p, con
     }
     mbar_wait_relaxed(acc_full, 0);
     tc_fence_after();
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // every drain warp has finished its column sums: they read the ring
     if (has_work) {
       float *stage0 = reinterpret_cast<float *>(smem);       // the operand ring is idle: every MMA has completed
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);

@@ -29,7 +29,8 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-VARIANTS = {"exactdiv": ["-DNFS_K1_EXACT_DIV"], "fastdiv": ["-DNFS_K1_FAST_DIV"], "devtools": ["-DNFS_DEVTOOLS"]}      # developer A/B builds: libnfs_b200_<variant>.so (NFS_B200_LIB selects it)
+VARIANTS = {"exactdiv": ["-DNFS_K1_EXACT_DIV"], "fastdiv": ["-DNFS_K1_FAST_DIV"], "devtools": ["-DNFS_DEVTOOLS"],
+            "noloadhint": ["-DNFS_NO_LOAD_HINT"], "nostorehint": ["-DNFS_NO_STORE_HINT"]}      # developer A/B builds: libnfs_b200_<variant>.so (NFS_B200_LIB selects it)
 
 
 def build(force=False, verbose=False, variant=None):

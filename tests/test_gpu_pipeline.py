@@ -261,6 +261,49 @@ def test_session_with_and_without_in_place_dy(cuda, monkeypatch):
     assert rel <= 1e-5, rel
 
 
+@pytest.mark.parametrize("in_place", ["1", "0"])
+def test_merged_backward_reads_no_stale_rows(cuda, monkeypatch, in_place):
+    """Hand-off check of the merged backward kernel (nfs_mlp_backward_fused): the same step is run again from the same
+    seeds after the dY arena has been filled with NaN.  A weight-gradient consumer that loads a row before the dgrad
+    chain has stored it - or a drain that overwrites a staged slab another warp is still summing - shows up as NaN / a
+    changed gradient; equal seeds alone would hide it (the stale rows of the previous run hold the same values)."""
+    from models.nerf_model import NeRFMLP
+    from nfs_b200 import pipeline
+    from nfs_b200.optim import FusedAdam
+    monkeypatch.setenv("NFS_K1_BWD_DY", in_place)
+    monkeypatch.setenv("NFS_BWD_MERGED", "1")
+    n = 700
+    ro, rd = O.lego_rays(n, seed=8)
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    tgt = torch.rand(n, 3, generator=torch.Generator().manual_seed(4)).to(cuda)
+    bands = O.frequency_bands(10)
+    torch.manual_seed(3)
+    model = NeRFMLP().to(cuda).train()
+    with torch.no_grad():
+        model.sigma_out.bias.fill_(0.3)
+    opt = FusedAdam(model.parameters(), lr=0.0)
+    ref, worst = None, 0.0
+    for rep in range(4):
+        sess = pipeline._session_for(model, opt)
+        if rep > 0:
+            sess.dys.fill_(float("nan"))
+        torch.manual_seed(11)
+        pipeline.train_step(model, opt, bands, ro, rd, tgt, 2.0, 6.0, 48, 80)
+        assert sess.merged
+        g = opt.grad.clone()
+        if ref is None:
+            ref = g
+            continue
+        assert not bool(torch.isnan(g).any()), "a consumer read dY rows the chain had not stored yet"
+        off = 0
+        for p in model.parameters():        # per tensor: the head's bias gradients are tiny next to the weights'
+            a, b = g[off:off + p.numel()], ref[off:off + p.numel()]
+            worst = max(worst, float((a - b).norm() / b.norm().clamp_min(1e-20)))
+            off += p.numel()
+    record("merged_backward_poisoned_arena", in_place_dy=in_place, worst_tensor_rel_l2=worst)
+    assert worst <= 1e-5, worst
+
+
 @pytest.mark.parametrize("n_rays,S", [(300, 64), (257, 192), (5, 7)])
 def test_forward_rays_bit_identical_to_forward_points(cuda, n_rays, S):
     """nfs_mlp_chain_rays (sampler o + d z evaluated inside the chain kernel) against sampling the positions first
