@@ -12,6 +12,12 @@ KEYS = [
     ("sm_pct_of_peak", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("tensor_pipe_active_pct", "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
     ("tmem_inst_pct", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active"),
+    # metrics that DO see tcgen05 cta_group::2 MMAs (the pct above under-reports them):
+    ("tensor_hmma_subpipe_cycles", "TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"),
+    ("tensor_ops_bf16_pct_of_peak", "sm__ops_path_tensor_src_bf16_dst_fp32.avg.pct_of_peak_sustained_elapsed"),
+    ("utcmma_inst", "smsp__sass_inst_executed_op_utcmma.sum"),
+    ("sm_cycles_elapsed", "sm__cycles_elapsed.avg"),
+    ("l1_to_l2_write_MB", "l1tex__m_l1tex2xbar_write_bytes.sum"),
     ("l2_hit_pct", "lts__t_sector_hit_rate.pct"),
     ("regs", "launch__registers_per_thread"), ("smem_dyn_KB", "launch__shared_mem_per_block_dynamic"),
     ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
@@ -61,6 +67,9 @@ def summarize(rep, name):
                 stalls.append((float(r[i]), hdr[i].split("stalled_")[1].split("_per_issue")[0]))
             except ValueError:
                 pass
+        if "tensor_hmma_subpipe_cycles" in rec and rec.get("sm_cycles_elapsed"):
+            # the sub-pipe counter is summed over the SM's four sub-partitions
+            rec["tensor_active_frac"] = round(rec["tensor_hmma_subpipe_cycles"] / 4.0 / rec["sm_cycles_elapsed"], 3)
         rec["top_stalls_per_issue"] = [[n, round(v, 2)] for v, n in sorted(stalls, reverse=True)[:4]]
         out.append(rec)
     path = os.path.join(OUT, "%s_%s_ncu_full_summary.json" % (TAG, name))
@@ -95,7 +104,10 @@ def launches(csv_path, name):
     print("wrote", path)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 3:
+    # python scripts/summarize_ncu.py <tag> <report.ncu-rep> <name>
+    summarize(sys.argv[2], sys.argv[3])
+elif __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     for name in ("k1", "k3"):
         rep = os.path.join(g, "prof_%s.ncu-rep" % name)
