@@ -59,6 +59,44 @@ def test_wgrad_vs_torch(cuda, P, M, N):
     assert float((dw3.double() - u.double().t() @ wide[:, 64:].double()).abs().max()) <= 1e-4 * scale
 
 
+@pytest.mark.parametrize("P,N,colsum_of_v,n_valid", [(64, 256, True, 256), (1000, 256, False, 200), (70001, 256, True, 256),
+                                                     (4097, 64, True, 63), (70001, 64, False, 63), (5, 64, True, 4)])
+def test_wgrad_cta_pair_body_vs_single_cta(cuda, monkeypatch, P, N, colsum_of_v, n_valid):
+    """The CTA-pair weight-gradient body (wgrad_pair_body.cuh: cta_group::2 MMAs, bias gradient as an N = 16 MMA against
+    a block of ones, N = 64 jobs as N = 128 with an out-of-bounds zero box) launched on its own (NFS_WGRAD_PAIR=1)
+    against the single-CTA kernel and against fp64: it is the consumer side of nfs_mlp_backward_fused and the body of
+    nfs_wgrad_multi_bf16's 256-wide jobs."""
+    from helpers import record
+    from nfs_b200 import ops
+    g = torch.Generator().manual_seed(P + N)
+    u = torch.randn(P, 256, generator=g).to(torch.bfloat16).to(cuda)
+    v = torch.randn(P, N, generator=g).to(torch.bfloat16).to(cuda)
+    res = {}
+    for pair in ("0", "1"):
+        if pair == "1":
+            monkeypatch.setenv("NFS_WGRAD_PAIR", "1")
+        else:
+            monkeypatch.delenv("NFS_WGRAD_PAIR", raising=False)
+        dw = torch.full((N, 256), 0.5, device=cuda)                  # accumulates on top of existing content
+        db = torch.zeros(256, device=cuda)
+        ops.wgrad_bf16(u, v, dw, 1, 256, colsum=db, colsum_of_v=colsum_of_v, n_valid=n_valid)
+        torch.cuda.synchronize()
+        res[pair] = (dw.double() - 0.5, db.double())
+    ref = v.double().t() @ u.double()
+    ref[n_valid:] = 0
+    cref = torch.zeros(256, dtype=torch.float64, device=cuda)
+    if colsum_of_v:
+        cref[:n_valid] = v.double().sum(0)[:n_valid]
+    else:
+        cref = u.double().sum(0)
+    scale, cscale = float(ref.abs().max()) + 1e-30, float(cref.abs().max()) + 1.0
+    for pair in ("0", "1"):
+        assert float((res[pair][0] - ref).abs().max()) <= 1e-4 * scale, pair
+        assert float((res[pair][1] - cref).abs().max()) <= 1e-4 * cscale, pair
+    record("wgrad_pair_vs_single", P=P, N=N, dw_rel=float((res["1"][0] - res["0"][0]).abs().max() / scale),
+           colsum_rel=float((res["1"][1] - res["0"][1]).abs().max() / cscale))
+
+
 def _g1_case(cuda, kwargs, P, seed):
     """Oracle (fp32, CPU) vs drop-in module (bf16 tensor cores) from the same seed / state_dict."""
     from models.nerf_model import NeRFMLP
