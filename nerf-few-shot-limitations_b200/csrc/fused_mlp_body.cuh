@@ -207,6 +207,12 @@ __device__ __forceinline__ unsigned long long fm_trace_time(int dbg) {
 // pair0 / pair_step: this CTA pair works on quads pair0, pair0 + pair_step, ...  quad_done (NULL in the stand-alone
 // chain kernels): one counter per quad, incremented by every epilogue warp of the pair (32 arrivals) once ALL of the
 // quad's TMA stores have completed - the hand-off to the weight-gradient consumers of the merged backward kernel.
+// (Two other ways of getting the saved rows out were built and measured on a same-box A/B and dropped: ONE store thread per
+// CTA issuing all TMA stores, the epilogue warps only arriving on / waiting for mbarriers: training forward 1.06-1.11 vs
+// 0.81 ms, dgrad 1.0 vs 0.78 ms - a tile's 64 KB then has to be READ by the TMA before the tile's next layer may
+// overwrite it, which takes longer than the 2000 cycles between them, while per-warp 4 KB stores overlap it
+// (gpurun_out/r2_ab_libs_storethread.log); and st.global straight from the epilogue's registers for half / all of the
+// warps: 1.24 / 1.88 vs 0.83 ms (gpurun_out/r2_ab_direct_store.log).)
 // (A finer hand-off - one counter per quad AND layer, published two layers behind by one thread per CTA - was built and
 // measured: same duration, DRAM reads 5.1 instead of 6.4 GB per step, but it failed the step's gradient-equality test
 // in one configuration and was dropped; gpurun_out/r2_handoff_matrix.log.)
