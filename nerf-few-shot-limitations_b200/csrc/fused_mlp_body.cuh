@@ -213,6 +213,9 @@ __device__ __forceinline__ unsigned long long fm_trace_time(int dbg) {
 // overwrite it, which takes longer than the 2000 cycles between them, while per-warp 4 KB stores overlap it
 // (gpurun_out/r2_ab_libs_storethread.log); and st.global straight from the epilogue's registers for half / all of the
 // warps: 1.24 / 1.88 vs 0.83 ms (gpurun_out/r2_ab_direct_store.log).)
+// (Issuing the stores from the elected lane with uniform operands removes the R2UR waterfall loop the compiler builds around
+// the UTMASTG inside `if (lane == 0)` - its exit branch shows 6 % of the training forward's stall samples - but the other
+// lanes only wait there for lane 0's arrive + store: no change on a same-box A/B, gpurun_out/r2_ab_libs_elect.log.)
 // (A finer hand-off - one counter per quad AND layer, published two layers behind by one thread per CTA - was built and
 // measured: same duration, DRAM reads 5.1 instead of 6.4 GB per step, but it failed the step's gradient-equality test
 // in one configuration and was dropped; gpurun_out/r2_handoff_matrix.log.)

@@ -66,3 +66,22 @@ for l in range(9):
         rd, cm = span(1, 2, 1, l, t), span(1, 2, 2, l, t)
         print("L%d %s | %7d %7d | %7d..%7d  %7d..%7d | %7d..%7d  %7d..%7d" % ((l, "AB"[t], rd[0], cm[0]) + span(2, 18, 3, l, t) + span(2, 18, 5, l, t)
               + span(20, 36, 3, l, t) + span(20, 36, 5, l, t)))
+
+# per-warp phases of two steady-state tile steps (training forward / dgrad: where does the skew between warps come from?)
+print("per-warp phases (cycles): lateness of 'acc_full seen' against the first warp | store-read wait | math + st.shared | fence | to next step begin")
+for (l, t) in ((4, 0), (4, 1)):
+    ev_lt = {}
+    for c, w, code, ll, tt in ev:
+        if lo <= c < hi and 2 <= w < 18 and ll == l and tt == t:
+            ev_lt.setdefault(w, {})[code] = c
+    nxt = {}
+    for c, w, code, ll, tt in ev:
+        if 2 <= w < 18 and code == 15 and ((ll == l and tt == 1 and t == 0) or (ll == l + 1 and tt == 0 and t == 1)) and lo <= c < hi + 30000:
+            nxt.setdefault(w, c)
+    first = min(v.get(3, 1 << 62) for v in ev_lt.values())
+    print("L%d %s" % (l, "AB"[t]))
+    for w in sorted(ev_lt):
+        v = ev_lt[w]
+        if all(k in v for k in (3, 14, 4, 5)):
+            print("  warp %2d (q %d, cq %d): late %5d | %5d | %5d | %5d | %5d" % (w, w % 4, (w - 2) // 4, v[3] - first, v[14] - v[3], v[4] - v[14], v[5] - v[4],
+                  nxt.get(w, v[5]) - v[5]))
