@@ -27,7 +27,14 @@ struct alignas(64) WgradMulti {
   unsigned cta0[kWgMaxJobs + 1];        // job j owns CTAs cta0[j] .. cta0[j+1] (whole pairs)
   int paired[kWgMaxJobs];               // 1: the job's CTAs work as pairs (wgrad_pair_body), 0: one by one (wgrad_body)
   int n_jobs;
+  int print_times;                      // developer switch NFS_WGRAD_TIMES: every CTA prints its job and start / end time
 };
+
+__device__ __forceinline__ unsigned long long wg_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
 wgrad_multi_kernel(const __grid_constant__ WgradMulti m) {
@@ -35,8 +42,12 @@ wgrad_multi_kernel(const __grid_constant__ WgradMulti m) {
   int j = 0;
   while (j + 1 < m.n_jobs && blockIdx.x >= m.cta0[j + 1]) ++j;
   const unsigned c = blockIdx.x - m.cta0[j], n = m.cta0[j + 1] - m.cta0[j];
+  const unsigned long long t0 = m.print_times ? wg_now() : 0ull;
   if (m.paired[j]) wgrad_pair_body(&m.tu[j], &m.tv[j], m.a[j], c >> 1, n >> 1);
   else wgrad_body(&m.tu[j], &m.tv[j], m.a[j], c, n);
+  if (m.print_times && threadIdx.x == 0 && c == 0)
+    printf("wgtimes job %d paired %d ctas %u M %d N %d P %lld start %llu end %llu\n", j, m.paired[j], n, m.a[j].M, m.a[j].N,
+           m.a[j].P, t0, wg_now());
 }
 
 }  // namespace
@@ -115,7 +126,9 @@ extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, v
       // the fixed ~12 us a CTA pays whatever its share (setup, first slab, accumulator drain)
       m.paired[k] = wgrad_pair_ok(m.a[k]) && getenv("NFS_WGRAD_NOPAIR") == nullptr;
       if (m.paired[k] && kWpSmemBytes > smem) smem = kWpSmemBytes;
-      double w = 2.0 * (j.m_dim + j.n_dim) / 512.0;
+      // CTA by CTA, measured inside this launch at cfg 4 (scripts/dev/wgrad_multi_times.py), in units of the pair body's
+      // ~1000 CTA-ns per slab: 128 x 64 0.95, 128 x 128 0.98, 256 x 128 1.27, 256 x 192 1.6
+      double w = 0.5 + 1.25 * (j.m_dim + j.n_dim) / 512.0;
       if (m.paired[k]) w = j.n_dim == 256 ? 1.0 : (j.colsum != nullptr && j.colsum_of_v ? 0.97 : 0.67);
       bytes[k] = (double)j.n_points * w + 2000.0;
       total += bytes[k];
@@ -153,6 +166,7 @@ extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, v
     }
     m.cta0[k] = used;
     m.n_jobs = k;
+    m.print_times = getenv("NFS_WGRAD_TIMES") != nullptr;
     wgrad_multi_kernel<<<used, kWgThreads, smem, (cudaStream_t)stream>>>(m);
     rc = check_launch(fn);
     if (rc) return rc;

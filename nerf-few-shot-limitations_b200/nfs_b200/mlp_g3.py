@@ -349,11 +349,15 @@ class G3Plan:
         lins = self.linears()
         ps = self.params()
         sizes = [p.numel() for p in ps]
-        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
-        views, off = [], 0
-        for p, n in zip(ps, sizes):
-            views.append(flat[off:off + n].view(p.shape))
-            off += n
+        # every gradient starts on a 16-byte boundary of one zeroed buffer: the weight-gradient kernels drain their
+        # accumulators with the TMA bulk reduction (and run on CTA pairs) only into 16-byte aligned destinations - a
+        # two-element bias in front (attention[2].bias) otherwise sends every later layer down the per-thread atomic drain
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 3) // 4 * 4
+        flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        views = [flat[o:o + n].view(p.shape) for p, n, o in zip(ps, sizes, offs)]
         gw = {id(l): (views[2 * i], views[2 * i + 1]) for i, l in enumerate(lins)}
 
         # every weight gradient of the step is collected and issued as ONE multi-job launch at the end (a launch
