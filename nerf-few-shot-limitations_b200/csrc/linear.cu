@@ -15,7 +15,10 @@
 //   * four epilogue warps read the accumulator with tcgen05.ld (each thread = one point),
 //     add the bias, apply ReLU / sigmoid / the ReLU-backward mask and store bf16 (next layer's
 //     operand, also the saved activation) and/or fp32.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue: two warps per TMEM lane quadrant, each
+// taking every other 32-column chunk (at the few ten thousand points of NeRFWithDINO a CTA sees one or two tiles, and
+// the four-warp epilogue - 8 chunks x (tcgen05.ld, 32 bias loads, activation, mask, 4 stores) per thread - was the
+// longest part of the launch); the bias is staged in shared memory once per CTA.
 // Per layer the kernel is HBM-bound (reads 2K, writes 2N bytes per point against 2KN flop).
 #include "tc_common.cuh"
 
@@ -24,7 +27,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kLinThreads = 192;
+constexpr int kLinThreads = 320;      // warps 0 / 1 = TMA / MMA, 2..9 = epilogue (two per TMEM lane quadrant)
 constexpr int kTileM = 128;
 constexpr int kSlabBytesX = kTileM * 128;   // [128 x 64] bf16
 
@@ -51,18 +54,19 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   uint8_t *x_smem = w_smem + ks * w_slab_bytes;
   uint64_t *full = reinterpret_cast<uint64_t *>(x_smem + S * kSlabBytesX);
   uint64_t *empty = full + S;
-  uint64_t *w_full = empty + S;
-  uint64_t *tmem_full = w_full + 1;
+  uint64_t *w_full = empty + S;                  // [ks <= 5] weight slab s landed
+  uint64_t *tmem_full = w_full + 5;
   uint64_t *tmem_empty = tmem_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *s_bias = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(full) + 256);      // [N] fp32
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = (a.P + kTileM - 1) / kTileM;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    for (int i = 0; i < 5; ++i) mbar_init(w_full + i, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
@@ -71,6 +75,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < N; i += kLinThreads) s_bias[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -78,12 +83,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      // weights: resident for the whole kernel
-      mbar_expect_tx(w_full, (uint32_t)(ks * w_slab_bytes));
-      for (int s = 0; s < ks; ++s) tma_load_2d(w_smem + s * w_slab_bytes, &tmap_w, w_full, s * 64, 0);
+      // weights: resident for the whole kernel, one barrier per 64-column slab so that the first tile's MMAs start when
+      // the first slab (and the first activation slab, requested right behind it) has landed
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int s = 0; s < ks; ++s, ++it) {
+          if (tile == (long long)blockIdx.x) {
+            mbar_expect_tx(w_full + s, (uint32_t)w_slab_bytes);
+            tma_load_2d(w_smem + s * w_slab_bytes, &tmap_w, w_full + s, s * 64, 0);
+          }
           const uint32_t stage = it % S, ph = (it / S) & 1;
           mbar_wait(empty + stage, ph ^ 1);
           mbar_expect_tx(full + stage, kSlabBytesX);
@@ -94,8 +102,6 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kTileM, N, 0, 0);
-      mbar_wait(w_full, 0);
-      tc_fence_after();
       uint32_t it = 0, t = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t & 1, aph = (t >> 1) & 1;
@@ -104,6 +110,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
         for (int s = 0; s < ks; ++s, ++it) {
           const uint32_t stage = it % S, ph = (it / S) & 1;
+          if (t == 0) mbar_wait(w_full + s, 0);
           mbar_wait(full + stage, ph);
           tc_fence_after();
           const uint32_t xa = smem_u32(x_smem + stage * kSlabBytesX);
@@ -121,6 +128,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     }
   } else {
     const int q = warp & 3;                       // TMEM lane quadrant this warp may touch
+    const int half = (warp - 2) >> 2;             // which of the quadrant's two warps: even or odd 32-column chunks
     const int row_in_tile = q * 32 + lane;
     uint32_t t = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
@@ -130,12 +138,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
       const long long row = tile * kTileM + row_in_tile;
       const bool ok = row < a.P;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)N;
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = 32 * half; c0 < N; c0 += 64) {
         float v[32];
         tmem_ld32(taddr + c0, v);
         if (a.bias != nullptr) {
+          const float4 *bp = reinterpret_cast<const float4 *>(s_bias + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + c0 + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = bp[j];
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
         }
         if (a.act == 1) {
 #pragma unroll
@@ -239,7 +251,7 @@ extern "C" int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const flo
   a.y_bf16 = (__nv_bfloat16 *)y_bf16; a.y_f32 = y_f32;
   a.P = n_points; a.y_pitch = y_pitch; a.K = k_dim; a.N = n_dim; a.act = act; a.out_cols = out_cols;
   const int w_bytes = (k_dim / 64) * n_dim * 128;
-  const int budget = 227 * 1024 - 1024 - 256 - w_bytes;
+  const int budget = 227 * 1024 - 1024 - 256 - 1024 - w_bytes;        // alignment slack, barriers, bias
   int stages = budget / kSlabBytesX;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail_arg(fn, NFS_E_TOOLARGE, "weights leave no room for the activation ring");
@@ -247,7 +259,7 @@ extern "C" int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const flo
   int cols = 32;
   while (cols < 2 * n_dim) cols <<= 1;
   a.tmem_cols = cols;
-  const size_t smem = 1024 + (size_t)w_bytes + (size_t)stages * kSlabBytesX + 256;
+  const size_t smem = 1024 + (size_t)w_bytes + (size_t)stages * kSlabBytesX + 256 + 1024;
   static PerDeviceOnce attr_once;
   int attr_dev = 0;
   if (attr_once.need(&attr_dev)) {
