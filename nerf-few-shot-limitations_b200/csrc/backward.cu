@@ -120,6 +120,13 @@ extern "C" int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int
     if (rc) return rc;
     if (sm > smem) smem = sm;
     m.waits[k] = job_waits[i] != 0 && getenv("NFS_BWD_NOWAIT") == nullptr;   // (developer switch: timing only, wrong results)
+    if (m.waits[k] && getenv("NFS_BWD_NODISCARD") == nullptr) {
+      // which operand lies in the chain's output tensor (256-wide rows: whole 128-byte lines per CTA of a pair)?
+      const uint8_t *lo = reinterpret_cast<const uint8_t *>(dys_bf16);
+      const uint8_t *hi = lo + (size_t)n_layers * (size_t)save_rows_per_layer * (size_t)n_dims[0] * 2;
+      if (m.a[k].u_ptr >= lo && m.a[k].u_ptr < hi && j.m_dim == 256 && j.u_pitch == 256) m.a[k].discard = 1;
+      else if (m.a[k].v_ptr >= lo && m.a[k].v_ptr < hi && j.n_dim == 256 && j.v_pitch == 256) m.a[k].discard = 2;
+    }
     slabs[k] = ((j.n_points + kSlabP - 1) / kSlabP + 7) / 8;           // scheduling units: quads of 8 slabs
     ++k;
   }

@@ -42,6 +42,11 @@ struct WgradArgs {
   int n_stages, tmem_cols;
   int dbg;            // developer bisection switches (NFS_WGRAD_DBG): 1 = no MMAs, 2 = no column sums, 4 = one TMA per operand
   int bulk_drain;     // destination is a contiguous n-major [n_valid x M] block: drain through smem + TMA bulk reduce
+  // merged backward kernel (CTA-pair body): operands that the dgrad chain of the same launch produced are dead once their
+  // slab has been loaded - their L2 lines are discarded so that they are never written back to DRAM
+  const uint8_t *u_ptr, *v_ptr;       // the operands themselves (row-major bf16) and their row pitches in bytes
+  long long u_pitch_b, v_pitch_b;
+  int discard;                        // bit 0: U, bit 1: V
 };
 
 // Slabs of a CTA, in order: units (runs of `U` consecutive slabs) cta, cta + n_cta, ...   U = 1 in the stand-alone
@@ -284,6 +289,8 @@ static inline int wgrad_prepare_job(const char *fn, const void *u_bf16, int64_t 
   nfs::WgradArgs a{};
   a.P = n_points; a.M = m_dim; a.N = n_dim; a.dw = dw; a.ld_m = ld_m; a.ld_n = ld_n;
   a.colsum = colsum; a.colsum_of_v = colsum_of_v;
+  a.u_ptr = reinterpret_cast<const uint8_t *>(u_bf16); a.v_ptr = reinterpret_cast<const uint8_t *>(v_bf16);
+  a.u_pitch_b = u_pitch * 2; a.v_pitch_b = v_pitch * 2; a.discard = 0;
   a.dbg = getenv("NFS_WGRAD_DBG") ? atoi(getenv("NFS_WGRAD_DBG")) : 0;
   a.m_valid = (m_valid <= 0 || m_valid > m_dim) ? m_dim : m_valid;
   a.n_valid = (n_valid <= 0 || n_valid > n_dim) ? n_dim : n_valid;

@@ -195,6 +195,23 @@ __device__ __forceinline__ void wgrad_pair_body(const CUtensorMap *tmap_u_p, con
       }
       if (c < a.n_valid) atomicAdd(a.colsum + c, cs_sum);
     }
+    if (a.discard != 0 && quad_done != nullptr && !(cs_lds && rank == 0)) {
+      // dY rows of the chain are dead once this pair has loaded them (one job reads each plane): discard their L2 lines
+      // as soon as the slab's MMAs have completed (`empty`: the loads have landed long before), so that the dirty lines
+      // are dropped instead of written back - the 4.2 GB per step of DRAM writes that remained of the dY round trip.
+      // One 128-byte line per thread and slab: this CTA loaded columns [128 rank, 128 rank + 128) = 2 lines of 64 rows.
+      const int et = threadIdx.x - 64, drow = et >> 1, dline = et & 1;
+      const uint8_t *base = (a.discard & 1) ? a.u_ptr : a.v_ptr;
+      const long long pitch = (a.discard & 1) ? a.u_pitch_b : a.v_pitch_b;
+      uint32_t it = 0;
+      NFS_WG_FOR_SLABS(slab, it) {
+        const uint32_t stage = it % S, ph = (it / S) & 1;
+        mbar_wait_relaxed(empty + stage, ph);
+        const long long row = slab * kSlabP + drow;
+        if (row < a.P)
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + row * pitch + (long long)rank * 256 + dline * 128) : "memory");
+      }
+    }
     mbar_wait_relaxed(acc_full, 0);
     tc_fence_after();
     asm volatile("bar.sync 1, 128;" ::: "memory");            // every drain warp has finished its column sums: they read the ring
