@@ -49,6 +49,47 @@ def test_render_rays_vs_oracle(cuda):
     assert e_c <= 1e-2 and e_f <= 1e-2 and e_d <= 5e-2, (e_c, e_f, e_d)
 
 
+def test_full_size_train_step_vs_oracle(cuda):
+    """The bench workload itself (BASELINE config 3: 4096 rays, 64 coarse + 192 fine evaluations, 1 048 576 points, the
+    merged backward kernel) against the CPU oracle on the same draws: loss and every parameter gradient.  The draws are
+    torch's CUDA generator's, reproduced by seeding (render_rays draws t_rand (N,64), then u (N,128))."""
+    from nfs_b200 import pipeline
+    from nfs_b200.optim import FusedAdam
+    ref, mod = _models(cuda, seed=9)
+    with torch.no_grad():
+        for m in (ref, mod):
+            m.sigma_out.bias.fill_(0.3)                   # a live density at random init
+    n, S, Ni = 4096, 64, 128
+    ro, rd = O.lego_rays(n, seed=3)
+    tgt = torch.rand(n, 3, generator=torch.Generator().manual_seed(6))
+    torch.manual_seed(21)
+    t_rand = torch.rand(n, S, device=cuda)
+    u = torch.rand(n, Ni, device=cuda)
+    opt = FusedAdam(mod.parameters(), lr=0.0)
+    torch.manual_seed(21)
+    loss = pipeline.train_step(mod.train(), opt, O.frequency_bands(10), ro.to(cuda), rd.to(cuda), tgt.to(cuda), 2.0, 6.0, S, Ni)
+    sess = pipeline._session_for(mod, opt)
+    assert sess is not None and sess.merged, "the bench-size step must take the merged backward kernel"
+    g = opt.grad.detach().cpu()
+    rgb_c, rgb_f, _ = _oracle_render(ref, ro, rd, t_rand.cpu(), u.cpu(), Ni)
+    loss_ref = torch.mean((rgb_f - tgt) ** 2) + torch.mean((rgb_c - tgt) ** 2)
+    g_ref = torch.autograd.grad(loss_ref, list(ref.parameters()))
+    e_loss = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+    off, worst, worst_name = 0, 0.0, ""
+    top = max(float(t.norm()) for t in g_ref)
+    for (name, p), t in zip(ref.named_parameters(), g_ref):
+        a = g[off:off + p.numel()].view_as(t)
+        off += p.numel()
+        rel = float((a - t).norm() / (t.norm() + 2e-4 * top))
+        if rel > worst:
+            worst, worst_name = rel, name
+    flat_rel = float((g - torch.cat([t.reshape(-1) for t in g_ref])).norm() / torch.cat([t.reshape(-1) for t in g_ref]).norm())
+    record("full_size_train_step_vs_oracle", loss_rel=e_loss, grad_flat_rel_l2=flat_rel, grad_worst_tensor_rel_l2=worst,
+           worst=worst_name)
+    assert e_loss <= 2e-3, e_loss
+    assert flat_rel <= 5e-2 and worst <= 1e-1, (flat_rel, worst, worst_name)
+
+
 def test_fused_adam_matches_torch(cuda):
     from nfs_b200.optim import FusedAdam
     torch.manual_seed(0)
