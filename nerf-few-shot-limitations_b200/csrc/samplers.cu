@@ -184,6 +184,26 @@ __global__ void __launch_bounds__(128) hierarchical_kernel(
     }
   }
 
+  // The merge below needs the coarse depths ascending, as every caller in the reference provides them.  The reference
+  // itself sorts the concatenation (ray_utils.py:139), so an unsorted row must still give the sorted multiset: check,
+  // and sort the row in place when needed (odd-even transposition; the sampling above used the original order, as the
+  // reference's gather does).  NaN depths are outside the contract (torch.sort puts them last; NFS_DEBUG_CHECKS=1
+  // validates the input in ops.sample_hierarchical).
+  {
+    bool z_sorted = true;
+    for (int i = lane; i < M; i += 32)
+      if (!(zc[i] <= zc[i + 1])) z_sorted = false;
+    if (!__all_sync(kFullMask, z_sorted)) {
+      for (int r = 0; r <= M; ++r) {
+        for (int i = (r & 1) + 2 * lane; i < M; i += 64) {
+          const float x = zc[i], y = zc[i + 1];
+          if (x > y) { zc[i] = y; zc[i + 1] = x; }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
   // merge: position = own index + rank in the other list (coarse depths first among equals)
   for (int i = lane; i <= M; i += 32) {
     const float v = zc[i];

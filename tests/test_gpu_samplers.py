@@ -114,6 +114,22 @@ def test_hierarchical_live_oracle(cuda, shape):
     assert bit_equal(zz, both)
 
 
+@pytest.mark.parametrize("shape", [(300, 64, 128), (50, 33, 17), (9, 2, 3)])
+def test_hierarchical_unsorted_coarse_depths(cuda, shape):
+    """The reference sorts the concatenation of the coarse depths and the new samples (ray_utils.py:139), so a row of
+    z_vals that is NOT ascending still yields the sorted multiset (and the bins are gathered in the given order).  The
+    kernel merges by rank and therefore sorts such a row first: bit-identical z / pts given the oracle's cdf."""
+    n, m1, ni = shape
+    ro, rd, z, w, u = _hier_inputs(n, m1, ni, seed=n + 3 * ni)
+    g = torch.Generator().manual_seed(5)
+    perm = torch.stack([torch.randperm(m1, generator=g) for _ in range(n)])
+    z_shuffled = torch.gather(z, 1, perm)
+    z_shuffled[::3] = z[::3]                                  # every third ray stays sorted
+    r = O.hierarchical(ro, rd, z_shuffled, w, u)
+    c = dict(rays_o=ro, rays_d=rd, z_vals=z_shuffled, weights=w, u=u, cdf=r["cdf"], idx=r["idx"], z=r["z"], pts=r["pts"])
+    _hier_kernel_level(c, cuda)
+
+
 def test_hierarchical_api(cuda):
     from utils.ray_utils import hierarchical_sampling
     ro, rd, z, w, _ = _hier_inputs(256, 64, 128, seed=3)
