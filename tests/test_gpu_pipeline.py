@@ -208,8 +208,10 @@ def test_conditioned_render_vs_oracle(cuda):
     assert e_rgb <= 1e-2 and e_depth <= 5e-2, (e_rgb, e_depth)
 
 
-@pytest.mark.parametrize("n_rays,n_coarse,n_imp", [(1024, 64, 128), (1000, 33, 20), (77, 64, 0)])
-def test_step_session_matches_per_call_gradients(cuda, monkeypatch, n_rays, n_coarse, n_imp):
+@pytest.mark.parametrize("n_rays,n_coarse,n_imp,kwargs", [(1024, 64, 128, {}), (1000, 33, 20, {}), (77, 64, 0, {}),
+                                                         (600, 64, 128, dict(n_layers=4)), (300, 48, 0, dict(n_layers=2)),
+                                                         (1, 64, 128, {})])
+def test_step_session_matches_per_call_gradients(cuda, monkeypatch, n_rays, n_coarse, n_imp, kwargs):
     """mlp.StepSession (one weight-gradient launch per layer over the coarse + fine points, written straight into
     the optimizer's flat gradient) against the per-call route (autograd accumulation + gather_grads), same draws:
     identical forward, gradients equal up to the fp32 summation order (rel L2 <= 1e-4); ragged point counts put
@@ -229,7 +231,7 @@ def test_step_session_matches_per_call_gradients(cuda, monkeypatch, n_rays, n_co
         # consumer CTAs fed through L2, opt-in)
         monkeypatch.setenv("NFS_BWD_MERGED", "1" if mode == "session_merged" else "0")
         torch.manual_seed(3)
-        model = NeRFMLP().to(cuda).train()
+        model = NeRFMLP(**kwargs).to(cuda).train()
         with torch.no_grad():
             model.sigma_out.bias.fill_(0.3)
         opt = FusedAdam(model.parameters(), lr=5e-4)
@@ -244,7 +246,7 @@ def test_step_session_matches_per_call_gradients(cuda, monkeypatch, n_rays, n_co
     rel = float((g_s - g_p).norm() / g_p.norm())
     rel_x = float((g_x - g_p).norm() / g_p.norm())
     rel_sx = float((g_s - g_x).norm() / g_x.norm())
-    record("step_session_vs_per_call", n_rays=n_rays, n_coarse=n_coarse, n_imp=n_imp, grad_rel_l2=rel,
+    record("step_session_vs_per_call", n_rays=n_rays, n_coarse=n_coarse, n_imp=n_imp, kwargs=str(kwargs), grad_rel_l2=rel,
            merged_grad_rel_l2=rel_x, merged_vs_split_rel_l2=rel_sx)
     assert rel <= 1e-4 and rel_x <= 1e-4 and rel_sx <= 1e-4, (rel, rel_x, rel_sx)
 
