@@ -10,15 +10,20 @@
 // summed over ALL points, wgrad_body.cuh).  As separate launches every dY element is written to HBM by the chain and read
 // back by nine weight-gradient launches that each start only when the chain has finished.  Here the CTA pairs of one
 // grid are split by role:
-//   * producers  (the first `producer_ctas` CTAs, whole pairs): the dgrad chain over quads of four tiles, unchanged,
-//     plus a release: when an epilogue warp's TMA stores of a quad have completed it bumps quad_done[quad];
-//   * consumers  (the remaining CTAs, divided among the jobs by operand bytes): the weight-gradient body; the TMA warp
-//     acquires quad_done[slab / 8] before it loads a slab the chain produces (jobs whose operands exist before the
-//     launch - the head's - do not wait).
-// Producers never wait for consumers, so the kernel cannot deadlock whatever the block scheduler does (all waits are
-// bounded and trap); a consumer that falls behind simply finds its operand in HBM instead of L2.  The dgrad chain is
-// bound by the SM (shared-memory / store bandwidth), the weight gradients by DRAM: run side by side they overlap, and a
-// dY tile is read back while it is still resident in the 126 MB L2.
+//   * producers  (the first `producer_ctas` CTAs, whole pairs; 38 of 74 pairs on B200): the dgrad chain over quads of
+//     four tiles, unchanged, plus a release: when an epilogue warp's TMA stores of a quad have COMPLETED it bumps
+//     quad_done[quad].  The stores carry an L2 evict_last hint;
+//   * consumers  (the remaining pairs, divided among the jobs by measured cost): the weight-gradient body on CTA pairs
+//     (wgrad_pair_body.cuh; the single-CTA body for shapes it does not cover); the TMA thread acquires
+//     quad_done[slab / 8] before it loads a slab the chain produces (jobs whose operands exist before the launch - the
+//     head's - do not wait), loads everything evict_first, and once the slab's MMAs have completed the idle drain warps
+//     discard the dY lines the CTA loaded (discard.global.L2: each plane of dY has exactly one reader), so that dY is
+//     neither read from nor written back to DRAM.
+// Producers never depend on consumers for progress - the back-pressure that keeps them at most 5/4 of a round ahead (so
+// that a quad's dY is still in L2 when it is read) gives up after a bounded spin - so the kernel cannot deadlock whatever
+// the block scheduler does; every other wait is bounded and traps.  Measured on the cfg 3 step (profiles/r02e_*): 2.0 ms
+// against 2.37 ms for the dgrad chains + nine weight-gradient launches, 6.3 GB of DRAM traffic against 13.1 GB; what
+// bounds it is SM time on both sides, not DRAM.
 #include "fused_mlp_body.cuh"
 #include "wgrad_pair_body.cuh"
 
