@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NFS_B200_ABI_VERSION 4
+#define NFS_B200_ABI_VERSION 5
 
 /* negative return codes (argument errors) */
 #define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
@@ -294,6 +294,43 @@ int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int32_t n_laye
                            int64_t bits_rows_per_layer, const int32_t *mask_idx, void *dys_bf16,
                            int64_t save_rows_per_layer, const nfs_wgrad_job *jobs, int32_t n_jobs,
                            const int32_t *job_waits, uint32_t *quad_flags, int32_t producer_pairs, void *stream);
+
+/* nfs_render_fused_bwd: the backward pass of a training step's render path in one call - the counterpart of
+ *   nfs_render_fused_fwd for NeRFDINOTrainer.train_step (train.py:244-292: loss.backward() through render_rays):
+ *   for every compositing pass of the step (coarse, fine) the compositing backward with the MLP head's derivative
+ *   folded in (nfs_composite_bwd_dy) writes columns 0..3 of that pass's rows of the dgrad chain's bf16 operand
+ *   dy_bf16 [n_points, dy_pitch] (rows between a pass's last point and its 128-row boundary are zeroed here), then
+ *   the whole MLP backward runs as ONE persistent launch (nfs_mlp_backward_fused over all n_points rows: dgrad chain +
+ *   every weight / bias gradient).  passes[i].row0: first row of the pass in the step's arenas (multiple of 128; the
+ *   passes must not overlap); mlp: HOST struct, fields as the nfs_mlp_backward_fused arguments of the same name.
+ *   The d(rgb_sigma) tensors, the hidden gradients' round trip to DRAM and every per-layer launch are gone. */
+typedef struct nfs_render_pass {
+  const float *rgb_sigma;   /* [n_rays, n_samples, 4] packed network output of the pass */
+  const float *z_vals;      /* [n_rays, n_samples] */
+  const float *g_rgb;       /* [n_rays, 3] d loss / d rgb_map of the pass */
+  const float *g_depth;     /* [n_rays] d loss / d depth_map | NULL */
+  int32_t n_samples;
+  int64_t row0;
+} nfs_render_pass;
+typedef struct nfs_chain_backward {
+  int32_t n_layers;
+  const int32_t *k_dims, *n_dims, *acts, *row0;
+  const void *wt_stack_bf16;
+  int32_t w_rows;
+  const void *relu_bits_in;
+  int64_t bits_rows_per_layer;
+  const int32_t *mask_idx;
+  void *dys_bf16;
+  int64_t save_rows_per_layer;
+  const nfs_wgrad_job *jobs;
+  int32_t n_jobs;
+  const int32_t *job_waits;
+  uint32_t *quad_flags;
+  int32_t producer_pairs;
+} nfs_chain_backward;
+int nfs_render_fused_bwd(const nfs_render_pass *passes, int32_t n_passes, const float *rays_d, int64_t n_rays,
+                         int32_t white_bkgd, void *dy_bf16, int64_t dy_pitch, int64_t n_points,
+                         const nfs_chain_backward *mlp, void *stream);
 
 /* nfs_mlp_chain: a whole chain of dense layers in ONE launch (fused multi-layer MLP):
  *   h_0 = X;  h_{l+1} = act_l( h_l . W_l^T + b_l ),  l = 0 .. n_layers-1

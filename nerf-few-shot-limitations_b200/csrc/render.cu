@@ -9,6 +9,8 @@
 // input of the compositing and of the resampling), and the network's packed [r,g,b,sigma] rows (P,4): the compositing
 // scan runs over the S samples of a ray, which only coincide with the chain kernel's 128-row tiles when S divides 128 -
 // the fine pass (S = 192) does not - so K1 stays its own (HBM-bound, 2 % of the frame) launch.
+#include <cuda_bf16.h>
+
 #include "nfs_common.cuh"
 
 using namespace nfs;
@@ -51,4 +53,35 @@ extern "C" int nfs_render_fused_fwd(const nfs_chain_model *m, const float *rays_
   if (rc) return rc;
   return nfs_composite_fwd(raw_fine, nullptr, z_fine, rays_d, nullptr, 0.f, n_rays, S, white_bkgd, 1, rgb_fine, depth_fine,
                            weights_fine, stream);
+}
+
+// nfs_render_fused_bwd — the backward of a training step's render path behind ONE C call: autograd's loss.backward()
+// through NeRFDINOTrainer.render_rays (/root/reference/src/training/train.py:188-242, 244-292) for the plain model:
+// compositing backward of every pass (closed form, nothing saved, the head's sigmoid / identity derivative folded in,
+// written as the bf16 operand of the MLP backward), then dgrad chain + all weight gradients in one persistent launch.
+extern "C" int nfs_render_fused_bwd(const nfs_render_pass *passes, int32_t n_passes, const float *rays_d, int64_t n_rays,
+                                    int32_t white_bkgd, void *dy_bf16, int64_t dy_pitch, int64_t n_points,
+                                    const nfs_chain_backward *m, void *stream) {
+  const char *fn = "nfs_render_fused_bwd";
+  if (!passes || n_passes < 1 || !rays_d || !dy_bf16 || !m || n_rays < 0 || n_points < 0 || dy_pitch < 4)
+    return fail_arg(fn, NFS_E_BADARG, "null pointer / bad sizes");
+  if (n_rays == 0 || n_points == 0) return 0;
+  for (int i = 0; i < n_passes; ++i) {
+    const nfs_render_pass &p = passes[i];
+    const long long P = (long long)n_rays * p.n_samples, pad = (P + 127) / 128 * 128;
+    if (!p.rgb_sigma || !p.z_vals || !p.g_rgb || p.n_samples < 2 || p.row0 < 0 || (p.row0 & 127) || p.row0 + pad > (n_points + 127) / 128 * 128)
+      return fail_arg(fn, NFS_E_BADARG, "a pass needs rgb_sigma, z_vals, g_rgb, n_samples >= 2 and a 128-aligned row range inside n_points");
+    __nv_bfloat16 *dy = static_cast<__nv_bfloat16 *>(dy_bf16) + p.row0 * dy_pitch;
+    if (pad > P) {                     // zero-gradient rows up to the pass's 128-row boundary
+      cudaError_t e = cudaMemsetAsync(dy + P * dy_pitch, 0, (size_t)(pad - P) * (size_t)dy_pitch * 2, (cudaStream_t)stream);
+      if (e != cudaSuccess) return fail_cuda(fn, e);
+    }
+    int rc = nfs_composite_bwd_dy(p.rgb_sigma, p.z_vals, rays_d, p.g_rgb, p.g_depth, nullptr, n_rays, p.n_samples, white_bkgd,
+                                  dy, dy_pitch, stream);
+    if (rc) return rc;
+  }
+  return nfs_mlp_backward_fused(dy_bf16, n_points, m->n_layers, m->k_dims, m->n_dims, m->acts, m->row0, m->wt_stack_bf16,
+                                m->w_rows, m->relu_bits_in, m->bits_rows_per_layer, m->mask_idx, m->dys_bf16,
+                                m->save_rows_per_layer, m->jobs, m->n_jobs, m->job_waits, m->quad_flags, m->producer_pairs,
+                                stream);
 }

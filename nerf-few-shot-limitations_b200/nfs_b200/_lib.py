@@ -50,6 +50,7 @@ SIGNATURES = {
                                           _p, _i32, _p]),
     "nfs_render_fused_fwd": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, _p,
                                             _p, _p, _p, _p, _p, _p]),
+    "nfs_render_fused_bwd": (ctypes.c_int, [_p, _i32, _p, _i64, _i32, _p, _i64, _i64, _p, _p]),
     "nfs_posenc_bf16": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p]),
     "nfs_gate_bwd_bf16": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p]),
     "nfs_pack_linear_bf16": (ctypes.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
@@ -82,6 +83,19 @@ class ChainModel(ctypes.Structure):
     """struct nfs_chain_model of include/nfs_b200.h."""
     _fields_ = [("n_layers", _i32), ("k_dims", _p), ("n_dims", _p), ("acts", _p), ("row0", _p), ("w_stack_bf16", _p),
                 ("w_rows", _i32), ("bias_terms_bf16", _p), ("freq0", _f32), ("n_octaves", _i32)]
+
+
+class RenderPass(ctypes.Structure):
+    """struct nfs_render_pass of include/nfs_b200.h."""
+    _fields_ = [("rgb_sigma", _p), ("z_vals", _p), ("g_rgb", _p), ("g_depth", _p), ("n_samples", _i32), ("row0", _i64)]
+
+
+class ChainBackward(ctypes.Structure):
+    """struct nfs_chain_backward of include/nfs_b200.h."""
+    _fields_ = [("n_layers", _i32), ("k_dims", _p), ("n_dims", _p), ("acts", _p), ("row0", _p), ("wt_stack_bf16", _p),
+                ("w_rows", _i32), ("relu_bits_in", _p), ("bits_rows_per_layer", _i64), ("mask_idx", _p), ("dys_bf16", _p),
+                ("save_rows_per_layer", _i64), ("jobs", _p), ("n_jobs", _i32), ("job_waits", _p), ("quad_flags", _p),
+                ("producer_pairs", _i32)]
 
 
 _lib = None

@@ -549,6 +549,8 @@ class StepSession:
             self.quad_flags = torch.zeros(2 * (rows // 512 + 2), device=dev, dtype=torch.int32)
         self.cursor = 0
         self.pending = 0
+        self.n_calls = 0
+        self.k1 = []                  # compositing backwards deferred to flush() (merged route): one C call for the whole backward
         self.dy_written = set()
         # One launch for the whole backward pass (nfs_mlp_backward_fused: dgrad chain on producer CTA pairs, weight
         # gradients on consumer CTA pairs fed through L2) when the step is large enough to fill the persistent grid
@@ -575,13 +577,27 @@ class StepSession:
             raise RuntimeError("StepSession: the step evaluates more points than begin() was told")
         self.cursor += pad
         self.pending += 1
+        self.n_calls += 1
         return r0
+
+    def defer_composite_backward(self, r0, rgb_sigma, z_vals, rays_d, g_rgb, g_depth, n_rays, n_samples, white):
+        """Merged route: the compositing backward of the call at row r0 (it writes the head's dY rows) is not launched
+        now but handed to nfs_render_fused_bwd together with the MLP backward at flush().  Returns False when the
+        session does not run the merged route (the caller launches nfs_composite_bwd_dy itself)."""
+        if not self.merged:
+            return False
+        self.k1.append(dict(r0=r0, rgb_sigma=rgb_sigma, z_vals=z_vals, rays_d=rays_d, g_rgb=g_rgb, g_depth=g_depth,
+                            n_rays=n_rays, n_samples=n_samples, white=white))
+        return True
 
     def backward_call(self, out, g_out, r0):
         """Head gradient + dgrad chain of one call, into the arenas."""
         plan = self.plan
         P = out.shape[0]
         pad = _ceil_to(P, 128)
+        if any(k["r0"] == r0 for k in self.k1):          # deferred: nfs_render_fused_bwd writes (and pads) these rows
+            self.pending -= 1
+            return
         if pad != P:
             self.dy[r0 + P:r0 + pad].zero_()
         if r0 in self.dy_written:
@@ -654,10 +670,42 @@ class StepSession:
         waits.append(1)
         arr, n, dev, kept = ops.wgrad_job_array(jobs, "nfs_mlp_backward_fused")
         c_waits = (ctypes.c_int32 * n)(*[waits[i] for i in kept])
+        k1 = self.k1
+        one_call = (len(k1) == self.n_calls and len(k1) > 0 and os.environ.get("NFS_RENDER_FUSED_BWD", "1") != "0"
+                    and all(k["rays_d"].data_ptr() == k1[0]["rays_d"].data_ptr() and k["n_rays"] == k1[0]["n_rays"]
+                            and k["white"] == k1[0]["white"] for k in k1))
         with torch.cuda.device(dev):
-            _lib.call("nfs_mlp_backward_fused", ptr(self.dy), T, n_layers, plan.cb_k, plan.cb_n, plan.cb_act, plan.cb_row0,
-                      ptr(plan.wt_stack), plan.wt_rows, ptr(self.bits), self.rows_cap, plan.cb_mask, ptr(self.dys),
-                      self.rows_cap, ctypes.byref(arr), n, c_waits, ptr(self.quad_flags), 0, _stream())
+            if one_call:
+                # the whole backward of the step behind ONE C call: compositing backward of every pass (writes the head's dY
+                # rows) + dgrad chain + all weight gradients (nfs_render_fused_bwd)
+                passes = (_lib.RenderPass * len(k1))()
+                for ps, k in zip(passes, k1):
+                    ps.rgb_sigma, ps.z_vals, ps.g_rgb = k["rgb_sigma"].data_ptr(), k["z_vals"].data_ptr(), k["g_rgb"].data_ptr()
+                    ps.g_depth = k["g_depth"].data_ptr() if k["g_depth"] is not None else None
+                    ps.n_samples, ps.row0 = k["n_samples"], k["r0"]
+                cb = _lib.ChainBackward()
+                addr = lambda a: ctypes.cast(a, ctypes.c_void_p).value
+                cb.n_layers, cb.k_dims, cb.n_dims, cb.acts, cb.row0 = n_layers, addr(plan.cb_k), addr(plan.cb_n), addr(plan.cb_act), addr(plan.cb_row0)
+                cb.wt_stack_bf16, cb.w_rows = plan.wt_stack.data_ptr(), plan.wt_rows
+                cb.relu_bits_in, cb.bits_rows_per_layer, cb.mask_idx = self.bits.data_ptr(), self.rows_cap, addr(plan.cb_mask)
+                cb.dys_bf16, cb.save_rows_per_layer = self.dys.data_ptr(), self.rows_cap
+                cb.jobs, cb.n_jobs, cb.job_waits = addr(arr), n, addr(c_waits)
+                cb.quad_flags, cb.producer_pairs = self.quad_flags.data_ptr(), 0
+                _lib.call("nfs_render_fused_bwd", ctypes.byref(passes), len(k1), ptr(k1[0]["rays_d"]), k1[0]["n_rays"],
+                          int(k1[0]["white"]), ptr(self.dy), int(self.dy.stride(0)), T, ctypes.byref(cb), _stream())
+            else:
+                for k in k1:                     # (mixed steps: some calls composited elsewhere) pass by pass
+                    P = k["n_rays"] * k["n_samples"]
+                    pad = _ceil_to(P, 128)
+                    if pad != P:
+                        self.dy[k["r0"] + P:k["r0"] + pad].zero_()
+                    _lib.call("nfs_composite_bwd_dy", ptr(k["rgb_sigma"]), ptr(k["z_vals"]), ptr(k["rays_d"]), ptr(k["g_rgb"]),
+                              ptr(k["g_depth"]), None, k["n_rays"], k["n_samples"], int(k["white"]),
+                              ptr(self.dy[k["r0"]:k["r0"] + P]), int(self.dy.stride(0)), _stream())
+                _lib.call("nfs_mlp_backward_fused", ptr(self.dy), T, n_layers, plan.cb_k, plan.cb_n, plan.cb_act, plan.cb_row0,
+                          ptr(plan.wt_stack), plan.wt_rows, ptr(self.bits), self.rows_cap, plan.cb_mask, ptr(self.dys),
+                          self.rows_cap, ctypes.byref(arr), n, c_waits, ptr(self.quad_flags), 0, _stream())
+        self.k1 = []
         v[2 * n_layers + 0].add_(self.head_w[3:4, :hd])      # sigma_out.weight (head rows 0..2 rgb_out, 3 sigma_out)
         v[2 * n_layers + 1].add_(self.head_b[3:4])
         v[2 * n_layers + 2].add_(self.head_w[0:3, :hd])

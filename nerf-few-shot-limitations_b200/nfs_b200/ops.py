@@ -183,6 +183,11 @@ class _CompositeLossFn(torch.autograd.Function):
             # receives a stride-0 placeholder.
             sess, r0 = ctx.dy_slot
             P = n_rays * n_samples
+            if sess.defer_composite_backward(r0, rgb, z_vals, rays_d, g_rgb, g_depth, n_rays, n_samples, white):
+                # merged route: this launch happens inside nfs_render_fused_bwd at the session's flush, together with
+                # the MLP backward - the step's whole backward is one C call
+                sess.dy_written.add(r0)
+                return (_placeholder(rgb), None) + none
             with torch.cuda.device(z_vals.device):
                 _lib.call("nfs_composite_bwd_dy", ptr(rgb), ptr(z_vals), ptr(rays_d), ptr(g_rgb), ptr(g_depth), None, n_rays,
                           n_samples, white, ptr(sess.dy[r0:r0 + P]), int(sess.dy.stride(0)), _stream())
