@@ -116,6 +116,36 @@ def _train_py_model(pos_freq=10, dir_freq=4, hidden_dim=256, num_density_layers=
                         hidden_dim=hidden_dim, num_density_layers=num_density_layers)
 
 
+def _g1_class():
+    try:
+        from .nerf_model import NeRFMLP as G1
+    except ImportError:
+        from nerf_model import NeRFMLP as G1
+    return G1
+
+
+class NeRFMLP(_g1_class()):
+    """Legacy spelling `from models.nerf_mlp import NeRFMLP` of the reference's older scripts
+    (src/training/train_minimal.py:28 `NeRFMLP(pos_dim=63)`, train_lora.py:57
+    `NeRFMLP(pos_dim=..., dino_dim=768, hidden_dim=256, n_layers=8, lora_rank=4)`).
+    The class body is absent from the reference snapshot, so only the form whose meaning the call sites pin is
+    served: without image features and without LoRA it is the plain 8 x 256 MLP of nerf_model.py:5-24 and returns
+    (P,4) = [rgb | sigma] through the fused tcgen05 chain.  The feature-conditioned / LoRA forms raise - there is
+    nothing to check them against (and no eager fallback to hide behind)."""
+
+    def __init__(self, pos_dim=63, dino_dim=0, hidden_dim=256, n_layers=8, lora_rank=0):
+        if dino_dim or lora_rank:
+            raise NotImplementedError(
+                "nfs_b200: models.nerf_mlp.NeRFMLP with dino_dim / lora_rank: the reference snapshot does not contain "
+                "this class (SURVEY.md section 8f rank 4); use models.nerf_mlp.NeRFWithDINO for feature-conditioned models")
+        super().__init__(pos_dim=pos_dim, hidden_dim=hidden_dim, n_layers=n_layers)
+
+    def forward(self, x, dino_feat=None):
+        if dino_feat is not None and dino_feat.shape[-1] != 0:
+            raise NotImplementedError("nfs_b200: this legacy NeRFMLP was built without image features (dino_dim=0)")
+        return super().forward(x)
+
+
 class VolumeRenderer(nn.Module):
     """Alpha compositing along rays, nerf_mlp.py:160-215, as one CUDA kernel forward
     (nfs_composite_fwd) and one backward (nfs_composite_bwd, recomputing alpha / T)."""

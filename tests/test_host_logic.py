@@ -134,3 +134,17 @@ def test_module_construction_matches_reference_fixture(golden):
     torch.manual_seed(3)
     b = O.PlainNeRF()
     assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+
+
+def test_legacy_nerf_mlp_alias():
+    """`from models.nerf_mlp import NeRFMLP` (train_minimal.py:3,28): the dino_dim=0 / lora_rank=0 form is the plain
+    MLP with the reference's parameter names; the forms whose class body the reference does not contain raise."""
+    import pytest
+    from models.nerf_mlp import NeRFMLP as Legacy
+    from models.nerf_model import NeRFMLP as G1
+    m = Legacy(pos_dim=63)
+    assert isinstance(m, G1)
+    assert sorted(m.state_dict()) == sorted(G1().state_dict())
+    assert sum(p.numel() for p in m.parameters()) == 477956
+    with pytest.raises(NotImplementedError):
+        Legacy(pos_dim=63, dino_dim=768, hidden_dim=256, n_layers=8, lora_rank=4)
