@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NFS_B200_ABI_VERSION 5
+#define NFS_B200_ABI_VERSION 6
 
 /* negative return codes (argument errors) */
 #define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
@@ -294,6 +294,31 @@ int nfs_mlp_backward_fused(const void *dy_bf16, int64_t n_points, int32_t n_laye
                            int64_t bits_rows_per_layer, const int32_t *mask_idx, void *dys_bf16,
                            int64_t save_rows_per_layer, const nfs_wgrad_job *jobs, int32_t n_jobs,
                            const int32_t *job_waits, uint32_t *quad_flags, int32_t producer_pairs, void *stream);
+
+/* nfs_render_fused_fwd_train: nfs_render_fused_fwd for a TRAINING step (train.py:244-292 up to the loss): the same
+ *   path - stratified depths -> sampler + encoding + MLP -> compositing [-> resampling -> MLP -> compositing] - with
+ *   (a) the chain kernel's training form: the encoded first-layer operand, every hidden activation and the ReLU sign
+ *   bits of both passes go to the step's arenas (state: HOST struct; pass i occupies the rows from row0[i], a multiple
+ *   of 128, of arenas with `rows_per_layer` rows per layer plane) for nfs_render_fused_bwd, and (b) the rgb MSE of every
+ *   pass (train.py:36-44) evaluated in the compositing epilogue (nfs_composite_loss_fwd): g_rgb_* (N,3) receive
+ *   d loss / d rgb_map of the pass, loss_out[0] = rgb_weight * (mse_coarse + mse_fine), [1] = mse_coarse, [2] = mse_fine
+ *   (one small kernel sums the 32 fp64 partial slots of each pass; loss_sums: 128 doubles of scratch, zeroed here).
+ *   Other arguments as nfs_render_fused_fwd (no weights_fine: nothing resamples after the fine pass). */
+typedef struct nfs_chain_train {
+  void *x_bf16;              /* [rows, k_dims[0]] bf16: receives the encoded operand of the first layer */
+  void *save_bf16;           /* [n_layers - 1, rows_per_layer, n_dims[0]] bf16: hidden activations */
+  void *relu_bits;           /* [n_layers - 1, rows_per_layer, 8] uint32: ReLU sign bits */
+  int64_t rows_per_layer;
+  int64_t row0[2];           /* first arena row of the coarse / fine pass */
+} nfs_chain_train;
+int nfs_render_fused_fwd_train(const nfs_chain_model *model, const nfs_chain_train *state, const float *rays_o,
+                               const float *rays_d, int64_t n_rays, int32_t n_coarse, const float *z_base,
+                               const float *lower, const float *upper, const float *t_rand, int32_t n_importance,
+                               const float *u, int64_t u_stride, int32_t white_bkgd, const float *target_rgb,
+                               float rgb_weight, float *z_coarse, float *raw_coarse, float *weights_coarse,
+                               float *bin_weights, float *rgb_coarse, float *depth_coarse, float *g_rgb_coarse,
+                               float *z_fine, float *raw_fine, float *rgb_fine, float *depth_fine, float *g_rgb_fine,
+                               double *loss_sums, float *loss_out, void *stream);
 
 /* nfs_render_fused_bwd: the backward pass of a training step's render path in one call - the counterpart of
  *   nfs_render_fused_fwd for NeRFDINOTrainer.train_step (train.py:244-292: loss.backward() through render_rays):

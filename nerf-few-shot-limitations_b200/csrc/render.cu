@@ -85,3 +85,91 @@ extern "C" int nfs_render_fused_bwd(const nfs_render_pass *passes, int32_t n_pas
                                 m->save_rows_per_layer, m->jobs, m->n_jobs, m->job_waits, m->quad_flags, m->producer_pairs,
                                 stream);
 }
+
+// nfs_render_fused_fwd_train — the forward of a training step's render path behind ONE C call
+// (NeRFDINOTrainer.train_step up to the loss, /root/reference/src/training/train.py:244-292 with render_rays :188-242 and
+// the rgb MSE of :36-44 on both passes): what nfs_render_fused_fwd does, with the chain kernel saving what the backward
+// needs into the step's arenas and the loss evaluated in the compositing epilogue.
+namespace nfs {
+namespace {
+// loss_sums: [2 passes][32 slots][2] fp64 partial sums of nfs_composite_loss_fwd -> out = {total, mse_coarse, mse_fine}
+__global__ void loss_finalize_kernel(const double *__restrict__ sums, long long n_rays, int n_passes, float rgb_weight,
+                                     float *__restrict__ out) {
+  const int lane = threadIdx.x;                     // one warp
+  float mse[2] = {0.f, 0.f};
+  for (int p = 0; p < n_passes; ++p) {
+    double v = sums[(p * 32 + lane) * 2];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    mse[p] = (float)(v / (3.0 * (double)n_rays));   // fp64 sum and quotient, rounded once (ops.composite_loss does the same)
+  }
+  if (lane == 0) {
+    out[1] = mse[0];
+    out[2] = mse[1];
+    out[0] = n_passes == 2 ? __fadd_rn(__fmul_rn(rgb_weight, mse[0]), __fmul_rn(rgb_weight, mse[1])) : __fmul_rn(rgb_weight, mse[0]);
+  }
+}
+}  // namespace
+}  // namespace nfs
+
+extern "C" int nfs_render_fused_fwd_train(const nfs_chain_model *m, const nfs_chain_train *st, const float *rays_o,
+                                          const float *rays_d, int64_t n_rays, int32_t n_coarse, const float *z_base,
+                                          const float *lower, const float *upper, const float *t_rand,
+                                          int32_t n_importance, const float *u, int64_t u_stride, int32_t white_bkgd,
+                                          const float *target_rgb, float rgb_weight, float *z_coarse, float *raw_coarse,
+                                          float *weights_coarse, float *bin_weights, float *rgb_coarse,
+                                          float *depth_coarse, float *g_rgb_coarse, float *z_fine, float *raw_fine,
+                                          float *rgb_fine, float *depth_fine, float *g_rgb_fine, double *loss_sums,
+                                          float *loss_out, void *stream) {
+  const char *fn = "nfs_render_fused_fwd_train";
+  if (!m || !st || !rays_o || !rays_d || !z_base || !target_rgb || !z_coarse || !raw_coarse || !rgb_coarse || !g_rgb_coarse ||
+      !loss_sums || !loss_out || n_rays < 0 || n_coarse < 2 || n_importance < 0)
+    return fail_arg(fn, NFS_E_BADARG, "null pointer / bad sizes");
+  if (!st->x_bf16 || !st->save_bf16 || !st->relu_bits || (st->row0[0] & 127) || (st->row0[1] & 127))
+    return fail_arg(fn, NFS_E_BADARG, "the arenas (x_bf16, save_bf16, relu_bits) and 128-aligned pass rows are required");
+  if (n_importance > 0 && (!u || !weights_coarse || !bin_weights || !z_fine || !raw_fine || !rgb_fine || !g_rgb_fine))
+    return fail_arg(fn, NFS_E_BADARG, "the fine pass needs u, weights_coarse, bin_weights, z_fine, raw_fine, rgb_fine, g_rgb_fine");
+  if (n_rays == 0) return 0;
+  const int n_passes = n_importance > 0 ? 2 : 1;
+  cudaError_t e = cudaMemsetAsync(loss_sums, 0, 128 * sizeof(double), (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(fn, e);
+  const size_t k0 = (size_t)m->k_dims[0], hp = (size_t)m->n_dims[0];
+  auto arena = [&](int pass, void **x, void **save, void **bits) {
+    const size_t r0 = (size_t)st->row0[pass];
+    *x = static_cast<uint8_t *>(st->x_bf16) + r0 * k0 * 2;
+    *save = static_cast<uint8_t *>(st->save_bf16) + r0 * hp * 2;
+    *bits = static_cast<uint8_t *>(st->relu_bits) + r0 * 8 * 4;
+  };
+  void *x, *save, *bits;
+  int rc = nfs_sample_stratified(nullptr, nullptr, z_base, lower, upper, t_rand, n_rays, n_coarse, z_coarse, nullptr, stream);
+  if (rc) return rc;
+  arena(0, &x, &save, &bits);
+  rc = nfs_mlp_chain_rays(rays_o, rays_d, z_coarse, n_rays, n_coarse, m->freq0, m->n_octaves, m->n_layers, m->k_dims,
+                          m->n_dims, m->acts, m->row0, m->w_stack_bf16, m->w_rows, m->bias_terms_bf16, x, save, bits,
+                          st->rows_per_layer, raw_coarse, 4, stream);
+  if (rc) return rc;
+  rc = nfs_composite_loss_fwd(raw_coarse, nullptr, z_coarse, rays_d, nullptr, 0.f, target_rgb, nullptr, rgb_weight, 0.f,
+                              n_rays, n_coarse, white_bkgd, 1, rgb_coarse, depth_coarse,
+                              n_importance > 0 ? weights_coarse : nullptr, g_rgb_coarse, nullptr, loss_sums, stream);
+  if (rc) return rc;
+  if (n_importance > 0) {
+    const int M = n_coarse - 1;
+    e = cudaMemcpy2DAsync(bin_weights, (size_t)M * 4, weights_coarse, (size_t)n_coarse * 4, (size_t)M * 4, (size_t)n_rays,
+                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(fn, e);
+    rc = nfs_sample_hierarchical(rays_o, rays_d, z_coarse, bin_weights, u, u_stride, nullptr, n_rays, M, n_importance, z_fine,
+                                 nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    const int S = n_coarse + n_importance;
+    arena(1, &x, &save, &bits);
+    rc = nfs_mlp_chain_rays(rays_o, rays_d, z_fine, n_rays, S, m->freq0, m->n_octaves, m->n_layers, m->k_dims, m->n_dims,
+                            m->acts, m->row0, m->w_stack_bf16, m->w_rows, m->bias_terms_bf16, x, save, bits,
+                            st->rows_per_layer, raw_fine, 4, stream);
+    if (rc) return rc;
+    rc = nfs_composite_loss_fwd(raw_fine, nullptr, z_fine, rays_d, nullptr, 0.f, target_rgb, nullptr, rgb_weight, 0.f, n_rays,
+                                S, white_bkgd, 1, rgb_fine, depth_fine, nullptr, g_rgb_fine, nullptr, loss_sums + 64, stream);
+    if (rc) return rc;
+  }
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_sums, (long long)n_rays, n_passes, rgb_weight, loss_out);
+  return check_launch(fn);
+}

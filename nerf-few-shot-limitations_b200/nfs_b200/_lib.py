@@ -50,6 +50,8 @@ SIGNATURES = {
                                           _p, _i32, _p]),
     "nfs_render_fused_fwd": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p, _p, _p, _p,
                                             _p, _p, _p, _p, _p, _p]),
+    "nfs_render_fused_fwd_train": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _i64, _i32, _p, _f32,
+                                                  _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "nfs_render_fused_bwd": (ctypes.c_int, [_p, _i32, _p, _i64, _i32, _p, _i64, _i64, _p, _p]),
     "nfs_posenc_bf16": (ctypes.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _i32, _p, _p]),
     "nfs_gate_bwd_bf16": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p, _p]),
@@ -83,6 +85,11 @@ class ChainModel(ctypes.Structure):
     """struct nfs_chain_model of include/nfs_b200.h."""
     _fields_ = [("n_layers", _i32), ("k_dims", _p), ("n_dims", _p), ("acts", _p), ("row0", _p), ("w_stack_bf16", _p),
                 ("w_rows", _i32), ("bias_terms_bf16", _p), ("freq0", _f32), ("n_octaves", _i32)]
+
+
+class ChainTrain(ctypes.Structure):
+    """struct nfs_chain_train of include/nfs_b200.h."""
+    _fields_ = [("x_bf16", _p), ("save_bf16", _p), ("relu_bits", _p), ("rows_per_layer", _i64), ("row0", _i64 * 2)]
 
 
 class RenderPass(ctypes.Structure):

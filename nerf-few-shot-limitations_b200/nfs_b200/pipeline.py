@@ -38,6 +38,14 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
             u = torch.rand(N, n_importance, device=dev) if perturb else ops.importance_table(dev, n_importance)
         return ops.render_fused(plan, freq_bands, rays_o, rays_d, near, far, n_coarse, n_importance,
                                 t_rand=t_rand if perturb else None, u=u, white_bkgd=white_bkgd, want_weights=True)
+    sess = _active_session(model) if (in_kernel and target is not None and torch.is_grad_enabled()) else None
+    if sess is not None and sess.merged and os.environ.get("NFS_RENDER_FUSED_TRAIN", "1") != "0":
+        # training step on the merged route: the whole forward behind one C call (nfs_render_fused_fwd_train), the whole
+        # backward behind another (nfs_render_fused_bwd, issued by the session's flush)
+        if n_importance > 0 and u is None:
+            u = torch.rand(N, n_importance, device=dev) if perturb else ops.importance_table(dev, n_importance)
+        return _render_train(sess, plan, freq_bands, rays_o, rays_d, target, near, far, n_coarse, n_importance,
+                             t_rand if perturb else None, u, white_bkgd)
     if in_kernel:
         # sampler fused into the chain kernel: only the depths are sampled here
         _, z = ops.sample_stratified(rays_o, rays_d, near, far, n_coarse, t_rand=t_rand if perturb else None, want_pts=False)
@@ -73,6 +81,88 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
         out.update(rgb=rgb_f, depth=depth_f, weights=w_f, z_vals=z_f)
     if loss is not None:
         out["loss"] = loss
+    return out
+
+
+def _active_session(model):
+    """The mlp.StepSession that pipeline.train_step / GraphedTrainStep opened on the model's plan, or None."""
+    get = getattr(model, "_get_plan", None)
+    return getattr(get(), "_session", None) if get is not None else None
+
+
+class _RenderTrainFn(torch.autograd.Function):
+    """Forward = nfs_render_fused_fwd_train (one C call: sampler + encoding + MLP + compositing + loss for the coarse and
+    the fine pass, activations into the session's arenas); backward hands both compositing backwards to the session,
+    whose flush() issues nfs_render_fused_bwd (one C call: compositing backward + dgrad chain + all weight gradients).
+    The only differentiable output is the loss; parameter gradients go straight into the optimizer's flat buffer."""
+
+    @staticmethod
+    def forward(ctx, sess, plan, freqs, rays_o, rays_d, target, cfg, t_rand, u, *params):
+        import ctypes
+        from . import _lib
+        from ._lib import ptr
+        from .ops import _f32c, _stream, _tables_on
+        near, far, Sc, Ni, white = cfg
+        rays_o, rays_d, target, t_rand = _f32c(rays_o), _f32c(rays_d), _f32c(target), _f32c(t_rand)
+        N, dev, Sf = rays_o.shape[0], rays_o.device, Sc + Ni
+        z_base, lower, upper = _tables_on(dev, near, far, Sc, False)
+        f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        z_c, raw_c, w_c, rgb_c, dep_c, g_c = f(N, Sc), f(N, Sc, 4), f(N, Sc), f(N, 3), f(N), f(N, 3)
+        z_f = raw_f = rgb_f = dep_f = g_f = bins = None
+        u_stride = 0
+        r0 = [sess.take(N * Sc), 0]
+        if Ni > 0:
+            u = _f32c(u)
+            u_stride = 0 if u.dim() == 1 else Ni
+            z_f, raw_f, rgb_f, dep_f, g_f, bins = f(N, Sf), f(N, Sf, 4), f(N, 3), f(N), f(N, 3), f(N, Sc - 1)
+            r0[1] = sess.take(N * Sf)
+        sums = torch.empty(128, device=dev, dtype=torch.float64)
+        loss3 = f(3)
+        st = _lib.ChainTrain(sess.x16.data_ptr(), sess.save.data_ptr(), sess.bits.data_ptr(), sess.rows_cap,
+                             (ctypes.c_int64 * 2)(*r0))
+        model = plan.chain_model(freqs)
+        with torch.cuda.device(dev):
+            _lib.call("nfs_render_fused_fwd_train", ctypes.byref(model), ctypes.byref(st), ptr(rays_o), ptr(rays_d), N, Sc,
+                      ptr(z_base), ptr(lower), ptr(upper), ptr(t_rand), Ni, ptr(u), u_stride, int(bool(white)), ptr(target),
+                      1.0, ptr(z_c), ptr(raw_c), ptr(w_c), ptr(bins), ptr(rgb_c), ptr(dep_c), ptr(g_c), ptr(z_f), ptr(raw_f),
+                      ptr(rgb_f), ptr(dep_f), ptr(g_f), ptr(sums), ptr(loss3), _stream())
+        ctx.sess, ctx.r0, ctx.cfg, ctx.n_params = sess, r0, (N, Sc, Sf, Ni, white), len(params)
+        ctx.save_for_backward(*[t for t in (rays_d, raw_c, z_c, g_c, raw_f, z_f, g_f) if t is not None])
+        outs = (loss3[0], rgb_c, dep_c, w_c, z_c) + ((rgb_f, dep_f, z_f) if Ni > 0 else ())
+        ctx.mark_non_differentiable(*outs[1:])
+        ctx.set_materialize_grads(False)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_loss, *_unused):
+        N, Sc, Sf, Ni, white = ctx.cfg
+        sess = ctx.sess
+        none = (None,) * (9 + ctx.n_params)
+        saved = ctx.saved_tensors
+        rays_d, raw_c, z_c, g_c = saved[:4]
+        passes = [(ctx.r0[0], raw_c, z_c, g_c, Sc)]
+        if Ni > 0:
+            raw_f, z_f, g_f = saved[4:7]
+            passes.append((ctx.r0[1], raw_f, z_f, g_f, Sf))
+        for r0, raw, z, g, S in passes:
+            sess.pending -= 1
+            if g_loss is None:
+                continue
+            if not sess.defer_composite_backward(r0, raw, z, rays_d, g * g_loss, None, N, S, int(bool(white))):
+                raise RuntimeError("nfs_b200: the fused training render needs the session's merged backward route")
+            sess.dy_written.add(r0)
+        return none
+
+
+def _render_train(sess, plan, freqs, rays_o, rays_d, target, near, far, n_coarse, n_importance, t_rand, u, white_bkgd):
+    outs = _RenderTrainFn.apply(sess, plan, freqs, rays_o, rays_d, target, (near, far, int(n_coarse), int(n_importance),
+                                bool(white_bkgd)), t_rand, u, *plan.params())
+    loss, rgb_c, dep_c, w_c, z_c = outs[:5]
+    out = {"rgb": rgb_c, "depth": dep_c, "weights": w_c, "z_vals": z_c, "loss": loss}
+    if n_importance > 0:
+        rgb_f, dep_f, z_f = outs[5:8]
+        out.update(rgb_coarse=rgb_c, depth_coarse=dep_c, weights_coarse=w_c, z_coarse=z_c, rgb=rgb_f, depth=dep_f,
+                   weights=None, z_vals=z_f)
     return out
 
 
