@@ -21,7 +21,7 @@
 //     neither read from nor written back to DRAM.
 // Producers never depend on consumers for progress - the back-pressure that keeps them at most 5/4 of a round ahead (so
 // that a quad's dY is still in L2 when it is read) gives up after a bounded spin - so the kernel cannot deadlock whatever
-// the block scheduler does; every other wait is bounded and traps.  Measured on the cfg 3 step (profiles/r02e_*): 2.0 ms
+// the block scheduler does; every other wait is bounded and traps.  Measured on the cfg 3 step (profiles/r02f_*): 2.0 ms
 // against 2.37 ms for the dgrad chains + nine weight-gradient launches, 6.3 GB of DRAM traffic against 13.1 GB; what
 // bounds it is SM time on both sides, not DRAM.
 #include "fused_mlp_body.cuh"
