@@ -136,8 +136,8 @@ act_grad_kernel(const float *__restrict__ out, const float *__restrict__ g_out, 
 //   dlogit_i = g_i (dg_i - (g0 dg0 + g1 dg1)).
 // enc(x) is recomputed, never stored.  One warp per point, lanes across the columns of the row: the dc' row, the extra
 // features and the output row are read and written coalesced (one thread per point read its own 256-byte row with 2-byte
-// loads, 32 sectors per instruction: 33 us per 32 768 points, all of it L1 wavefronts), each lane evaluates the one or
-// two encoding columns it owns with an accurate sinf / cosf, and two shuffle trees finish the dot products.
+// loads, 32 sectors per instruction: 33 us per 32 768 points, all of it L1 wavefronts), each lane evaluates one
+// (band, coordinate) pair with an accurate sincosf, and two shuffle trees finish the dot products.
 constexpr int kGateBwdWarps = 8;
 __global__ void __launch_bounds__(32 * kGateBwdWarps)
 gate_bwd_kernel(const float *__restrict__ x, const float *__restrict__ freqs, const float *__restrict__ extra,
@@ -147,21 +147,33 @@ gate_bwd_kernel(const float *__restrict__ x, const float *__restrict__ freqs, co
   const long long warp = (long long)blockIdx.x * kGateBwdWarps + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * kGateBwdWarps;
   const int enc_w = D * (2 * L + 1);
+  const int k_first = lane / D, d_first = lane - k_first * D;
   for (long long p = warp; p < n_points; p += n_warps) {
     const __nv_bfloat16 *row = dc + p * dc_pitch;
     float dg0 = 0.f, dg1 = 0.f;
-    for (int c = lane; c < enc_w; c += 32) {
-      float e;
-      if (c < D) {
-        e = __ldg(x + p * D + c);
-      } else {                                   // column D + (2k + s) D + d: s = 0 sin, 1 cos (posenc layout)
-        const int q = (c - D) / D, d = (c - D) - q * D;
-        const float arg = __fmul_rn(__ldg(x + p * D + d), __ldg(freqs + (q >> 1)));
-        e = (q & 1) ? cosf(arg) : sinf(arg);
-      }
-      dg0 += __bfloat162float(row[c]) * e;
+    for (int c = lane; c < D; c += 32) dg0 += __bfloat162float(row[c]) * __ldg(x + p * D + c);
+    // one (band, coordinate) pair per lane: a single sincosf serves the sin and the cos column (posenc layout: columns
+    // D + 2kD + d and D + 2kD + D + d); the pair owned in the first round never changes, so its division is hoisted
+    for (int pair = lane, round = 0; pair < L * D; pair += 32, ++round) {
+      const int k = round == 0 ? k_first : pair / D;
+      const int d = round == 0 ? d_first : pair - k * D;
+      float sn, cs;
+      sincosf(__fmul_rn(__ldg(x + p * D + d), __ldg(freqs + k)), &sn, &cs);
+      const __nv_bfloat16 *e = row + D + 2 * k * D + d;
+      dg0 += __bfloat162float(e[0]) * sn + __bfloat162float(e[D]) * cs;
     }
-    for (int j = lane; j < E; j += 32) dg1 += __bfloat162float(row[enc_w + j]) * __ldg(extra + p * E + j);
+    // image features: up to eight independent loads in flight per lane
+    for (int j0 = lane; j0 < E; j0 += 128) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 32 * u;
+        a[u] = j < E ? __bfloat162float(row[enc_w + j]) : 0.f;
+        b[u] = j < E ? __ldg(extra + p * E + j) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dg1 += a[u] * b[u];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       dg0 += __shfl_xor_sync(0xffffffffu, dg0, o);
