@@ -367,14 +367,16 @@ int nfs_render_fused_bwd(const nfs_render_pass *passes, int32_t n_passes, const 
  *   columns 0..K_l, zero padded); biases stacked the same way as bias_terms_bf16 [w_rows, 8] (row row0[l] + n =
  *   nfs_bias_terms_bf16 of b_l[n]: the bias is added by the tensor core, one K = 16 MMA per tile and layer) or NULL.
  *   K_l, N_l multiples of 64 in [64,256], K_l == N_{l-1}.
- *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 4 ReLU backward: multiply by the sign bit
+ *   acts[l]: 0 none, 1 relu, 2 sigmoid on columns 0..2, 3 sigmoid, 5 softmax over columns 0..1 (output head with
+ *   out_cols == 2 only: the gate of dino_feature_model.py:188), 4 ReLU backward: multiply by the sign bit
  *   relu_bits_in[mask_idx[l]][p][n] (layers >= 128 wide).
  *   ReLU mask bits: uint32 [layers, rows_per_layer, 8] = 256 bits per point (1 = the pre-activation was positive);
  *   in word w bit 15 - j (j < 16) is column 32w + 2j and bit 31 - j is column 32w + 2j + 1.  relu_bits_out (forward chain of a training step, NULL
  *   otherwise) receives the bits of every act-1 layer's output, 32 bytes per point instead of the 512-byte
  *   activation row the backward would otherwise re-read; rows per layer = save_rows_per_layer.
  *   out_f32 != NULL: the LAST layer is an output head whose first out_cols columns are written
- *   as fp32 [P,out_cols].  save_bf16 != NULL: [n_saved, save_rows_per_layer, N_0] bf16 receives
+ *   as fp32 [P,out_cols].  save_bf16 != NULL: [n_saved, save_rows_per_layer, max_l N_l] bf16 (saved layers are
+ *   at least 128 wide; a narrower layer fills the first N_l columns of its rows) receives
  *   every non-head layer's output by TMA store (n_saved = n_layers - 1 with a head, else
  *   n_layers); *_rows_per_layer >= P rounded up to 128. */
 int nfs_mlp_chain(const void *x_bf16, int64_t n_points, int32_t n_layers,

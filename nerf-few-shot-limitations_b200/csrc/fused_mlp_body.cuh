@@ -526,10 +526,11 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
           // steps ahead (same tile, previous layer's step), so their latency never shows
           const bool use_bits = kMasked && act_l == 4 && tile < n_tiles;
           const int words = quarter >> 5;                       // 2 (256-wide layers) or 1 (128-wide)
-          auto load_bits = [&](int layer) -> uint2 {
-            const uint32_t *bp = a.bits_in + ((long long)a.mask_idx[layer] * a.bits_rows + row) * 8 + (c0 >> 5);
+          auto load_bits = [&](int layer) -> uint2 {           // widths may differ from layer to layer: the words this
+            const int lq = a.N[layer] >> 2;                    // thread owns follow the width of the layer they mask
+            const uint32_t *bp = a.bits_in + ((long long)a.mask_idx[layer] * a.bits_rows + row) * 8 + ((cq * lq) >> 5);
             uint2 v = make_uint2(0u, 0u);
-            if (words == 2) v = __ldg(reinterpret_cast<const uint2 *>(bp));
+            if (lq == 64) v = __ldg(reinterpret_cast<const uint2 *>(bp));
             else v.x = __ldg(bp);
             return v;
           };
@@ -552,10 +553,15 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
             const bool do_save = (kTrain || kMasked) && a.save != 0;
             const bool paired = do_save && quarter == 32;
             const uint32_t pair_bar = 1u + (uint32_t)(q * 2 + (cq >> 1));
+            // Width change (256 -> 128 or back): the columns this warp writes now were stored by ANOTHER warp of the
+            // same 32 rows one layer ago - every warp waits for its own store, then the four warps of the row quarter
+            // meet (without this, one tile in a few hundred kept stale columns: scripts/dev/chain_mixed.py).
+            const bool changed = l > 0 && a.N[l - 1] != Nl;
             if (store_pending) {
-              if (lane == 0 && (!paired || (cq & 1) == 0)) bulk_wait_read1();
+              if (lane == 0 && (changed || !paired || (cq & 1) == 0)) bulk_wait_read1();
               __syncwarp();
-              if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+              if (changed) asm volatile("bar.sync %0, 128;" ::"r"(9u + (uint32_t)q) : "memory");
+              else if (paired) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             }
             NFS_TRACE(14, l, t);
             uint8_t *srow = act_t + (c0 >> 6) * kActSlab + r_in * 128;
@@ -638,6 +644,12 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
               float v[16];
               tmem_ld16(taddr, v);
               if (row < a.P) {
+                if (act_l == 5) {                  // 2-way softmax gate (dino_feature_model.py:169,188), as nfs_linear_bf16
+                  const float mx = fmaxf(v[0], v[1]);
+                  const float e0 = expf(v[0] - mx), e1 = expf(v[1] - mx);
+                  const float inv = 1.0f / (e0 + e1);
+                  v[0] = e0 * inv; v[1] = e1 * inv;
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   if (j < a.out_cols) {
@@ -715,7 +727,9 @@ static inline int chain_prepare(const char *fn, const void *x_bf16, const float 
       return fail_arg(fn, NFS_E_BADARG, "act 4 (ReLU backward) needs relu_bits_in and mask_idx");
     if ((a.act[l] == 4 || (a.act[l] == 1 && relu_bits_out)) && a.N[l] < 128 && !(out_f32 && l == n_layers - 1))
       return fail_arg(fn, NFS_E_UNSUPPORTED, "ReLU sign bits need layers at least 128 wide");
-    if (a.act[l] < 0 || a.act[l] > 4) return fail_arg(fn, NFS_E_BADARG, "act must be 0..4");
+    if (a.act[l] < 0 || a.act[l] > 5) return fail_arg(fn, NFS_E_BADARG, "act must be 0..5");
+    if (a.act[l] == 5 && !(out_f32 && l == n_layers - 1 && out_cols == 2))
+      return fail_arg(fn, NFS_E_BADARG, "act 5 (2-way softmax) belongs to an output head with out_cols == 2");
     if (a.K[l] % 64 || a.K[l] <= 0 || a.K[l] > 256 || a.N[l] % 64 || a.N[l] <= 0 || a.N[l] > 256 ||
         a.row0[l] < 0 || a.row0[l] + a.N[l] > w_rows)
       return fail_arg(fn, NFS_E_UNSUPPORTED, "layer dims must be multiples of 64 in [64,256] and fit the weight stack");
@@ -730,9 +744,13 @@ static inline int chain_prepare(const char *fn, const void *x_bf16, const float 
   if (relu_bits_out && (relu_bits_in || save_rows_per_layer < rows128))
     return fail_arg(fn, NFS_E_BADARG, "relu_bits_out belongs to a forward chain (no relu_bits_in) with save_rows_per_layer >= rows");
   const int n_saved = a.head ? n_layers - 1 : n_layers;
+  // saved rows are as wide as the widest saved layer; a narrower layer fills the first N_l columns of its rows
+  int save_w = 0;
   if (a.save)
-    for (int l = 0; l < n_saved; ++l)
-      if (a.N[l] != a.N[0]) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need equal layer widths");
+    for (int l = 0; l < n_saved; ++l) {
+      if (a.N[l] < 128) return fail_arg(fn, NFS_E_UNSUPPORTED, "saved activations need layers at least 128 wide");
+      save_w = a.N[l] > save_w ? a.N[l] : save_w;
+    }
 
   CUtensorMap tx{}, tw{}, ts{}, tb{};
   int rc = 0;
@@ -756,8 +774,8 @@ static inline int chain_prepare(const char *fn, const void *x_bf16, const float 
     if (rc) return rc;
   }
   if (a.save) {
-    rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * n_saved), (uint64_t)a.N[0],
-                            (uint64_t)a.N[0], 32, fn);
+    rc = tc::make_tmap_bf16(&ts, save_bf16, (uint64_t)(save_rows_per_layer * n_saved), (uint64_t)save_w,
+                            (uint64_t)save_w, 32, fn);
     if (rc) return rc;
   }
   *a_out = a; *tx_out = tx; *tw_out = tw; *ts_out = ts; *tb_out = tb;

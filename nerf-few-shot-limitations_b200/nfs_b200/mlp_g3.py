@@ -5,12 +5,13 @@ nerf_mlp.NeRFWithDINO = NeRFDINOFusion -> DensityMLP -> ColorMLP
 The nn.Modules in models/ keep the reference's fp32 parameters; this file owns the launch
 sequence.  Forward, P points:
     c    = [enc(x) | f]                         nfs_posenc_bf16          (dino_feature_model.py:182)
-    h2   = relu(W2 relu(W1 c))                  nfs_mlp_chain (2 layers) (:185)
-    g    = softmax(Wb relu(Wa h2))              nfs_linear_bf16 x2, softmax in the epilogue (:188)
+    h2   = relu(W2 relu(W1 c))                  one nfs_mlp_chain for both lines: three layers and the
+    g    = softmax(Wb relu(Wa h2))              2-way softmax as its fp32 head (:185,188)
     c'   = [enc(x) g0 | f g1]                   nfs_posenc_bf16 with the gate (:191-195)
     h_n  = density layers(Wo relu(W2 relu(W1 c')))   nfs_mlp_chain (3 + n_density layers) (:195-197, nerf_mlp.py:60)
-    dens = relu(w_d h_n), feat = W_f h_n        nfs_linear_bf16 x2 (nerf_mlp.py:61-65)
-    rgb  = sigmoid(Wc3 relu(Wc2 relu(Wc1 [feat | enc(d)])))   nfs_posenc_bf16 + nfs_linear_bf16 x3 (:82-84)
+    dens = relu(w_d h_n), feat = W_f h_n        head of that chain; nfs_linear_bf16 (nerf_mlp.py:61-65)
+    rgb  = sigmoid(Wc3 relu(Wc2 relu(Wc1 [feat | enc(d)])))   nfs_posenc_bf16 + nfs_linear_bf16 (K = 320) +
+                                                nfs_mlp_chain [Wc2, Wc3 as sigmoid head] (:82-84)
 Backward: the same graph in reverse - dgrad GEMMs with the ReLU-backward mask fused in their
 epilogues (nfs_mlp_chain act 4 / nfs_linear_bf16 relu_mask_src), nfs_wgrad_bf16 for every weight
 and bias (the fusion layers W1, W2 receive both of their uses), nfs_gate_bwd_bf16 for the softmax
@@ -245,25 +246,40 @@ class G3Plan:
         self.pc3 = PackedLinear([self.Wc3], self.c2p, 64)
         self.all_packed = [self.p1, self.p2, self.pa, self.pb, self.po] + self.pd + [self.pdh, self.pf, self.pheads,
                                                                                     self.pc1, self.pc2, self.pc3]
-        self.chain_a = _Stack([self.p1, self.p2])
-        self.chain_b = _Stack([self.p1, self.p2, self.po] + self.pd)
+        # chain A: the fusion layers, the first attention layer (its 64 outputs zero-padded to 128 columns) and the gate
+        # logits as a 2-way softmax head; its
+        # dgrad chain runs from d(gate logits) back to d(pre-activation of W1): [Wb^T, Wa^T, W2^T], each masked by the
+        # sign bits chain A saved for the layer's input
+        self.chain_a = _Stack([self.p1, self.p2, self.pa, self.pb])
+        self.chain_a_bwd = _Stack([self.pb, self.pa, self.p2], transposed=True)
+        self.ca_act, self.cab_act, self.cab_mask = _i32arr([1, 1, 1, 5]), _i32arr([4, 4, 4]), _i32arr([2, 1, 0])
+        # chain B: second use of the fusion layers, output_proj, the density layers - and the density head as the
+        # chain's fp32 output head when the layer count allows
+        self.nb = 3 + len(self.Wd)
+        body = [self.p1, self.p2, self.po] + self.pd
+        self.head_in_chain = self.nb + 1 <= 12
+        self.chain_b = _Stack(body + ([self.pdh] if self.head_in_chain else []))
         # dgrad chain of chain B: from d(h_n) down to d(pre-activation of W1's second use); weight of step t =
         # W^T of forward layer nb-1-t, mask = the input of that layer (ReLU output) or none (output_proj is linear)
-        self.nb = 3 + len(self.Wd)
-        back = list(reversed(self.chain_b.layers[1:]))
+        back = list(reversed(body[1:]))
         self.chain_b_bwd = _Stack(back, transposed=True)
+        # chain C: the colour MLP behind its first layer (K = 320 does not fit the chain): [Wc2, Wc3 as sigmoid head]
+        self.chain_c = _Stack([self.pc2, self.pc3])
+        self.cc_act = _i32arr([1, 3])
         acts, midx = [], []
         for t in range(self.nb - 1):
             j_in = self.nb - 2 - t                     # forward layer whose output feeds layer nb-1-t
             acts.append(0 if j_in == 2 else 4)
             midx.append(j_in)
         self.cb_act, self.cb_mask = _i32arr(acts), _i32arr(midx)
-        self.ca_act = _i32arr([1, 1])
-        self.cbf_act = _i32arr([1, 1, 0] + [1] * len(self.Wd))
+        self.cbf_act = _i32arr([1, 1, 0] + [1] * len(self.Wd) + ([1] if self.head_in_chain else []))
 
     # parameters in a fixed order; run_backward returns gradients in this order
     def linears(self):
         return [self.W1, self.W2, self.Wa, self.Wb, self.Wo] + self.Wd + [self.Wdh, self.Wf, self.Wc1, self.Wc2, self.Wc3]
+
+    def stacks(self):
+        return (self.chain_a, self.chain_a_bwd, self.chain_b, self.chain_b_bwd, self.chain_c)
 
     def params(self):
         ps = []
@@ -285,7 +301,7 @@ class G3Plan:
         if not simple or os.environ.get("NFS_PACK_STACK", "1") == "0":       # layer by layer (any dtype / layout)
             for p in self.all_packed:
                 p.refresh()
-            for st in (self.chain_a, self.chain_b, self.chain_b_bwd):
+            for st in self.stacks():
                 st.key = None
                 st.refresh()
             self._key, self._place = key, None
@@ -296,7 +312,7 @@ class G3Plan:
             for p in self.all_packed:
                 p.alloc(dev)
                 rows += p.table_rows()
-            for st in (self.chain_a, self.chain_b, self.chain_b_bwd):
+            for st in self.stacks():
                 st.alloc(dev)
                 rows += st.table_rows()
             self._table = torch.tensor(rows, dtype=torch.int64, device=dev)
@@ -308,41 +324,47 @@ class G3Plan:
             p._key = p.current_key() if hasattr(p, "current_key") and type(p).refresh is PackedLinear.refresh else None
         self._key = key
 
-    def _chain(self, x16, stack, n_layers, acts, P, bits_in=None, mask_idx=None, want_bits=False):
-        """nfs_mlp_chain without an output head: every layer's output is saved -> [n_layers, rows, hp]
-        (+ the ReLU sign bits [n_layers, rows, 8] of a forward chain when want_bits)."""
+    def _chain(self, x16, stack, n_layers, acts, P, bits_in=None, mask_idx=None, want_bits=False, head_cols=0):
+        """nfs_mlp_chain: every non-head layer's output is saved -> [n_saved, rows, widest saved layer]
+        (+ the ReLU sign bits [n_saved, rows, 8] of a forward chain when want_bits; + the fp32 [P, head_cols] output of
+        the last layer when head_cols > 0)."""
         rows = _ceil_to(P, 128)
-        save = torch.empty((n_layers, rows, self.hp), device=x16.device, dtype=torch.bfloat16)
-        bits = torch.empty((n_layers, rows, 8), device=x16.device, dtype=torch.int32) if want_bits else None
+        n_saved = n_layers - 1 if head_cols else n_layers
+        width = max(stack.c_n[l] for l in range(n_saved))
+        save = torch.empty((n_saved, rows, width), device=x16.device, dtype=torch.bfloat16)
+        bits = torch.empty((n_saved, rows, 8), device=x16.device, dtype=torch.int32) if want_bits else None
+        out = torch.empty((P, head_cols), device=x16.device, dtype=torch.float32) if head_cols else None
         with torch.cuda.device(x16.device):
             _lib.call("nfs_mlp_chain", ptr(x16), P, n_layers, stack.c_k, stack.c_n, acts, stack.c_row0, ptr(stack.w),
                       stack.rows, ptr(stack.b), ptr(bits_in), 0 if bits_in is None else bits_in.shape[1], mask_idx,
-                      ptr(save), ptr(bits), rows, None, 0, _stream())
-        return (save, bits) if want_bits else save
+                      ptr(save), ptr(bits), rows, ptr(out), head_cols, _stream())
+        res = (save,) + ((bits,) if want_bits else ()) + ((out,) if head_cols else ())
+        return res if len(res) > 1 else save
 
     def run_forward(self, x, d, f, freqs_pos, freqs_dir):
         P = x.shape[0]
         hp = self.hp
         c16 = encode_operand(x, freqs_pos, self.k0, extra=f)
-        sa = self._chain(c16, self.chain_a, 2, self.ca_act, P)
-        h2 = sa[1, :P]
-        a16, _ = ops.linear_bf16(h2, self.pa.w16, self.pa.bias, act=1)
-        _, gate = ops.linear_bf16(a16, self.pb.w16, self.pb.bias, act=5, out_bf16=False, out_f32_cols=2)
+        sa, sa_bits, gate = self._chain(c16, self.chain_a, 4, self.ca_act, P, want_bits=True, head_cols=2)
         c2 = encode_operand(x, freqs_pos, self.k0, extra=f, gate=gate)
-        sb, sb_bits = self._chain(c2, self.chain_b, self.nb, self.cbf_act, P, want_bits=True)
+        if self.head_in_chain:
+            sb, sb_bits, density = self._chain(c2, self.chain_b, self.nb + 1, self.cbf_act, P, want_bits=True, head_cols=1)
+        else:
+            sb, sb_bits = self._chain(c2, self.chain_b, self.nb, self.cbf_act, P, want_bits=True)
         hn = sb[self.nb - 1, :P]
-        _, density = ops.linear_bf16(hn, self.pdh.w16, self.pdh.bias, act=1, out_bf16=False, out_f32_cols=1)
+        if not self.head_in_chain:
+            _, density = ops.linear_bf16(hn, self.pdh.w16, self.pdh.bias, act=1, out_bf16=False, out_f32_cols=1)
         cat16 = torch.empty((P, self.cat_k), device=x.device, dtype=torch.bfloat16)
         ops.linear_bf16(hn, self.pf.w16, self.pf.bias, act=0, out=cat16[:, :hp])
         encode_operand(d, freqs_dir, self.kd, out=cat16[:, hp:])
         k1, _ = ops.linear_bf16(cat16, self.pc1.w16, self.pc1.bias, act=1)
-        k2, _ = ops.linear_bf16(k1, self.pc2.w16, self.pc2.bias, act=1)
-        _, rgb = ops.linear_bf16(k2, self.pc3.w16, self.pc3.bias, act=3, out_bf16=False, out_f32_cols=3)
-        saved = (c16, sa, a16, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits)
+        sc, rgb = self._chain(k1, self.chain_c, 2, self.cc_act, P, head_cols=3)
+        k2 = sc[0, :P]
+        saved = (c16, sa, sa_bits, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits)
         return rgb, density, saved
 
     def run_backward(self, x, f, freqs_pos, saved, g_rgb, g_density):
-        c16, sa, a16, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits = saved
+        c16, sa, sa_bits, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits = saved
         P = x.shape[0]
         dev = x.device
         hp, H, nb = self.hp, self.H, self.nb
@@ -411,14 +433,13 @@ class G3Plan:
         with torch.cuda.device(dev):
             _lib.call("nfs_gate_bwd_bf16", ptr(x), ptr(fr), ptr(f) if self.D else None, ptr(gate), ptr(dc2), self.k0, P,
                       3, int(fr.numel()), self.D, 64, ptr(dlog), _stream())
+        h1, h2, a16 = sa[0, :P], sa[1, :P], sa[2, :P, :self.ap]
         wg(self.Wb, a16, dlog)
-        da, _ = ops.linear_bf16(dlog, self.pb.w16t, None, act=0, relu_mask_src=a16)
-        h1, h2 = sa[0, :P], sa[1, :P]
-        wg(self.Wa, h2, da)
-        dh2, _ = ops.linear_bf16(da, self.pa.w16t, None, act=0, relu_mask_src=h2)
-        wg(self.W2, h1, dh2)
-        dh1, _ = ops.linear_bf16(dh2, self.p2.w16t, None, act=0, relu_mask_src=h1)
-        wg(self.W1, c16, dh1, blocks=k0_blocks)
+        # d a, d h2, d h1 (pre-activations): one dgrad chain [Wb^T, Wa^T, W2^T] masked by chain A's sign bits
+        dya = self._chain(dlog, self.chain_a_bwd, 3, self.cab_act, P, bits_in=sa_bits, mask_idx=self.cab_mask)
+        wg(self.Wa, h2, dya[0, :P, :self.ap])
+        wg(self.W2, h1, dya[1, :P])
+        wg(self.W1, c16, dya[2, :P], blocks=k0_blocks)
         if jobs:
             ops.wgrad_multi(jobs)
         return views

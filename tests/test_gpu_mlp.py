@@ -337,3 +337,74 @@ def test_chain_stress_repeatable(cuda):
             assert torch.equal(save[0][:, :P], ref_save[0][:, :P]) and torch.equal(save[1][:, :P], ref_save[1][:, :P])
             assert torch.equal(plan.dgrad_chain_fused(dy, save[1], P)[:, :P], ref_dys[:, :P])
             assert torch.equal(plan.run_forward_fused(x16, keep=False)[0], ref_out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [1, 300, 5000, 40001])
+def test_chain_mixed_widths_softmax_head_and_dgrad(cuda, P):
+    """Chains whose layers differ in width (NeRFDINOFusion's attention branch, dino_feature_model.py:165-170,185-188):
+    forward [192 -> 256 -> 256 -> 128 -> 2-way softmax head] with saved activations and sign bits, then its dgrad chain
+    [64 -> 128 -> 256 -> 256] masked by those bits - against bf16-operand / fp32-accumulate torch arithmetic.  The saved
+    tensor is as wide as the widest layer; the 128-wide layer fills the first 128 columns of its rows."""
+    import ctypes
+    from nfs_b200 import _lib
+    from nfs_b200._lib import ptr
+    from nfs_b200.mlp import bias_terms
+    from nfs_b200.ops import _stream
+    from helpers import record
+    g = torch.Generator().manual_seed(P)
+    dims = [(192, 256), (256, 256), (256, 128), (128, 64)]
+    Ws = [(torch.randn(n, k, generator=g) * (2.0 / k) ** 0.5).to(torch.bfloat16) for k, n in dims]
+    bs = [torch.randn(n, generator=g) * 0.1 for k, n in dims]
+    Ws[3][2:] = 0; bs[3][2:] = 0
+    x = torch.randn(P, 192, generator=g).to(torch.bfloat16)
+    i32 = lambda v: (ctypes.c_int32 * len(v))(*v)
+    rows = (P + 127) // 128 * 128
+
+    def stack(mats):
+        w = torch.zeros(sum(m.shape[0] for m in mats), 256, dtype=torch.bfloat16)
+        r, row0 = 0, []
+        for m in mats:
+            w[r:r + m.shape[0], :m.shape[1]] = m
+            row0.append(r); r += m.shape[0]
+        return w.to(cuda), row0
+
+    w, row0 = stack(Ws)
+    bt = bias_terms(torch.cat(bs).to(cuda))
+    save = torch.full((3, rows, 256), float("nan"), device=cuda, dtype=torch.bfloat16)
+    bits = torch.zeros((3, rows, 8), device=cuda, dtype=torch.int32)
+    gate = torch.empty((P, 2), device=cuda, dtype=torch.float32)
+    xc = x.to(cuda)
+    _lib.call("nfs_mlp_chain", ptr(xc), P, 4, i32([k for k, n in dims]), i32([n for k, n in dims]), i32([1, 1, 1, 5]),
+              i32(row0), ptr(w), w.shape[0], ptr(bt), None, 0, None, ptr(save), ptr(bits), rows, ptr(gate), 2, _stream())
+    # reference: bf16 operands, fp32 accumulation, bf16 activations between layers
+    h, acts = x.float(), []
+    for l in range(3):
+        h = torch.relu(h @ Ws[l].float().T + bs[l]).to(torch.bfloat16).float()
+        acts.append(h)
+    ref_gate = torch.softmax((h @ Ws[3].float().T + bs[3])[:, :2], dim=-1)
+    for l, n in enumerate((256, 256, 128)):
+        got = save[l, :P, :n].float().cpu()
+        assert torch.isfinite(got).all()
+        assert (got - acts[l]).abs().max() <= 0.02 * acts[l].abs().max() + 1e-3, l
+    assert torch.isnan(save[2, :P, 128:].float()).all()          # the narrow layer wrote only its own columns
+    assert (gate.cpu() - ref_gate).abs().max() < 5e-3
+    record("chain_mixed_widths", P=P, gate_err=float((gate.cpu() - ref_gate).abs().max()))
+
+    # dgrad chain: dlog [P,64] -> d a (128) -> d h2 (256) -> d h1 (256), each masked by the sign of the saved layer
+    dlog = torch.zeros(P, 64, dtype=torch.bfloat16)
+    dlog[:, :2] = torch.randn(P, 2, generator=g).to(torch.bfloat16)
+    Wt = [Ws[3].T.contiguous(), Ws[2].T.contiguous(), Ws[1].T.contiguous()]        # [128,64], [256,128], [256,256]
+    wt, row0t = stack(Wt)
+    dys = torch.full((3, rows, 256), float("nan"), device=cuda, dtype=torch.bfloat16)
+    dc = dlog.to(cuda)
+    _lib.call("nfs_mlp_chain", ptr(dc), P, 3, i32([64, 128, 256]), i32([128, 256, 256]), i32([4, 4, 4]), i32(row0t),
+              ptr(wt), wt.shape[0], None, ptr(bits), rows, i32([2, 1, 0]), ptr(dys), None, rows, None, 0, _stream())
+    saved_cpu = [save[l, :P].float().cpu() for l in range(3)]
+    d = dlog.float()
+    for t, (wmat, src, n) in enumerate(zip(Wt, (2, 1, 0), (128, 256, 256))):
+        d = ((d @ wmat.float().T) * (saved_cpu[src][:, :n] > 0)).to(torch.bfloat16).float()
+        got = dys[t, :P, :n].float().cpu()
+        assert torch.isfinite(got).all()
+        assert (got - d).abs().max() <= 0.02 * d.abs().max() + 1e-4, t
+        d = got                                                   # follow the kernel's own rounding downstream
