@@ -76,24 +76,36 @@ class _Stack:
         key = tuple(p._key for p in self.layers)
         if key == self.key:
             return self
-        dev = self.layers[0].w16.device
         mats = [(p.w16t if self.transposed else p.w16) for p in self.layers]
-        rows = sum(m.shape[0] for m in mats)
+        dev = mats[0].device
+        shapes = [((p.k_pad, p.n_pad) if self.transposed else (p.n_pad, p.k_pad)) for p in self.layers]
+        rows = sum(sh[0] for sh in shapes)
         w = torch.zeros(rows, 256, device=dev, dtype=torch.bfloat16)
         b = None if self.transposed else torch.zeros(rows, device=dev, dtype=torch.float32)
         r, row0 = 0, []
-        for p, m in zip(self.layers, mats):
+        for p, m, sh in zip(self.layers, mats, shapes):
             w[r:r + m.shape[0], :m.shape[1]].copy_(m)
             if b is not None:
                 b[r:r + m.shape[0]].copy_(p.bias)
             row0.append(r)
-            r += m.shape[0]
+            r += sh[0]
         self.w, self.b, self.rows = w, (None if b is None else bias_terms(b)), rows
         self.c_row0 = _i32arr(row0)
-        self.c_k = _i32arr([m.shape[1] for m in mats])
-        self.c_n = _i32arr([m.shape[0] for m in mats])
+        self.c_k = _i32arr([sh[1] for sh in shapes])
+        self.c_n = _i32arr([sh[0] for sh in shapes])
         self.key = key
         return self
+
+
+class _WiderT:
+    """The W^T copy of a packed layer as a dgrad-chain layer whose output is zero-padded to `rows` columns (the chain
+    kernel saves layers of 128 or 256 columns; the 192-wide d c' of the first fusion layer becomes 256 wide)."""
+
+    def __init__(self, packed, rows):
+        self.packed, self.k_pad, self.n_pad, self.linears = packed, rows, packed.n_pad, packed.linears
+
+    w16t = property(lambda self: self.packed.w16t)
+    _key = property(lambda self: self.packed._key)
 
 
 class _SplitColumns(PackedLinear):
@@ -261,7 +273,8 @@ class G3Plan:
         self.chain_b = _Stack(body + ([self.pdh] if self.head_in_chain else []))
         # dgrad chain of chain B: from d(h_n) down to d(pre-activation of W1's second use); weight of step t =
         # W^T of forward layer nb-1-t, mask = the input of that layer (ReLU output) or none (output_proj is linear)
-        back = list(reversed(body[1:]))
+        # ... and one more step to d c' itself (no mask: c' is the gated input), the operand of the gate's backward
+        back = list(reversed(body[1:])) + [_WiderT(self.p1, pad_hidden(self.k0))]
         self.chain_b_bwd = _Stack(back, transposed=True)
         # chain C: the colour MLP behind its first layer (K = 320 does not fit the chain): [Wc2, Wc3 as sigmoid head]
         self.chain_c = _Stack([self.pc2, self.pc3])
@@ -271,7 +284,7 @@ class G3Plan:
             j_in = self.nb - 2 - t                     # forward layer whose output feeds layer nb-1-t
             acts.append(0 if j_in == 2 else 4)
             midx.append(j_in)
-        self.cb_act, self.cb_mask = _i32arr(acts), _i32arr(midx)
+        self.cb_act, self.cb_mask = _i32arr(acts + [0]), _i32arr(midx + [0])
         self.cbf_act = _i32arr([1, 1, 0] + [1] * len(self.Wd) + ([1] if self.head_in_chain else []))
 
     # parameters in a fixed order; run_backward returns gradients in this order
@@ -415,7 +428,7 @@ class G3Plan:
             dcat[:, hp:].zero_()
         g_top, _ = ops.linear_bf16(dcat, self.pheads.w16t, None, act=0, relu_mask_src=hn)
         # ---- density layers, output_proj, second use of fusion[2] (dgrad chain)
-        dys = self._chain(g_top, self.chain_b_bwd, nb - 1, self.cb_act, P, bits_in=sb_bits, mask_idx=self.cb_mask)
+        dys = self._chain(g_top, self.chain_b_bwd, nb, self.cb_act, P, bits_in=sb_bits, mask_idx=self.cb_mask)
 
         def grad_pre(j):          # dL/d(pre-activation of chain-B layer j)
             return g_top if j == nb - 1 else dys[nb - 2 - j, :P]
@@ -426,12 +439,12 @@ class G3Plan:
         k0_blocks = [(0, self.W1.in_features, 0, self.k0)]
         wg(self.W1, c2, grad_pre(0), blocks=k0_blocks)
         # ---- the gate (dino_feature_model.py:188-195)
-        dc2, _ = ops.linear_bf16(grad_pre(0), self.p1.w16t, None, act=0)
+        dc2 = dys[nb - 1]                              # d c' = d(pre-activation of W1) . W1, last step of the chain
         dlog = torch.empty((P, 64), device=dev, dtype=torch.bfloat16)
         from .mlp import freqs_on
         fr = freqs_on(dev, freqs_pos)
         with torch.cuda.device(dev):
-            _lib.call("nfs_gate_bwd_bf16", ptr(x), ptr(fr), ptr(f) if self.D else None, ptr(gate), ptr(dc2), self.k0, P,
+            _lib.call("nfs_gate_bwd_bf16", ptr(x), ptr(fr), ptr(f) if self.D else None, ptr(gate), ptr(dc2), dc2.shape[1], P,
                       3, int(fr.numel()), self.D, 64, ptr(dlog), _stream())
         h1, h2, a16 = sa[0, :P], sa[1, :P], sa[2, :P, :self.ap]
         wg(self.Wb, a16, dlog)
