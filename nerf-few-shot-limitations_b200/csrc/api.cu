@@ -1,4 +1,5 @@
 // Error plumbing and bookkeeping shared by every entry point of include/nfs_b200.h.
+#include <stdlib.h>
 #include "nfs_common.cuh"
 
 #include <string.h>
@@ -24,6 +25,11 @@ int fail_arg(const char *where, int code, const char *what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char *v = getenv("NFS_PDL"); return !(v != nullptr && v[0] == '0'); }();
+  return on;
+}
 
 }  // namespace nfs
 

@@ -44,13 +44,10 @@ static int launch_prepared(const char *fn, FusedArgs a, const CUtensorMap &tx, c
   const long long n_quads = ((a.P + 127) / 128 + 3) / 4;
   const long long max_pairs = sms / 2;
   const unsigned grid = 2u * (unsigned)(n_quads < max_pairs ? n_quads : max_pairs);   // whole CTA pairs
-  if (dgrad)
-    fused_mlp_kernel<true, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
-  else if (train)
-    fused_mlp_kernel<false, true><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
-  else
-    fused_mlp_kernel<false, false><<<grid, kFmThreads, smem, (cudaStream_t)stream>>>(tx, tw, ts, tb, a);
-  return check_launch(fn);
+  const dim3 g(grid), b(kFmThreads);
+  if (dgrad) return launch_dep(fn, fused_mlp_kernel<true, false>, g, b, smem, (cudaStream_t)stream, tx, tw, ts, tb, a);
+  if (train) return launch_dep(fn, fused_mlp_kernel<false, true>, g, b, smem, (cudaStream_t)stream, tx, tw, ts, tb, a);
+  return launch_dep(fn, fused_mlp_kernel<false, false>, g, b, smem, (cudaStream_t)stream, tx, tw, ts, tb, a);
 }
 
 

@@ -290,6 +290,8 @@ __device__ __forceinline__ void chain_body(const CUtensorMap *tmap_x_p, const CU
   cluster_sync_all();                              // both CTAs' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                                   // (nfs_common.cuh: programmatic dependent launch)
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer

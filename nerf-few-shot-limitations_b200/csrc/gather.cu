@@ -22,6 +22,8 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) project_gather_kernel(const GatherArgs a) {
+  pdl_trigger();
+  pdl_wait();                                  // (nfs_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -98,6 +100,5 @@ extern "C" int nfs_project_gather(const float *points, const float *pose_inv, fl
   a.points_2d = points_2d; a.depths = depths; a.valid = valid; a.sampled = sampled;
   long long blocks = (n_points + 7) / 8;                 // 8 warps per block, one point per warp per pass
   if (blocks > 148 * 16) blocks = 148 * 16;
-  project_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
-  return check_launch(fn);
+  return launch_dep(fn, project_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
 }

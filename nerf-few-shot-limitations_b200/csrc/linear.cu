@@ -75,11 +75,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tmem_relinquish();
   }
+  pdl_wait();                      // everything above is private to the CTA; from here on global memory is touched
   for (int i = threadIdx.x; i < N; i += kLinThreads) s_bias[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                   // TMEM is held: a dependent grid's CTAs may be scheduled behind this one
 
   if (warp == 0) {
     if (lane == 0) {
@@ -269,6 +271,5 @@ extern "C" int nfs_linear_bf16(const void *x_bf16, const void *w_bf16, const flo
   }
   const long long n_tiles = (n_points + kTileM - 1) / kTileM;
   const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
-  linear_kernel<<<grid, kLinThreads, smem, (cudaStream_t)stream>>>(tx, tw, a);
-  return check_launch(fn);
+  return launch_dep(fn, linear_kernel, dim3(grid), dim3(kLinThreads), smem, (cudaStream_t)stream, tx, tw, a);
 }

@@ -30,8 +30,10 @@ posenc_bf16_kernel(const float *__restrict__ x, const float *__restrict__ freqs,
   const int enc_w = D * (2 * L + 1);
 
   // zero the padding columns (and everything else; cheap) so the GEMM sees exact zeros
+  pdl_trigger();
   for (int t = threadIdx.x; t < np * k_pad / 8; t += kEncThreads) reinterpret_cast<uint4 *>(tile)[t] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  pdl_wait();                                  // (nfs_common.cuh) first global access below
 
   const int per_pt = L * D;
   if (pow2_bands) {
@@ -103,6 +105,8 @@ pack_linear_kernel(const float *__restrict__ w, int N, int K, int n_pad, int k_p
 __global__ void __launch_bounds__(256)
 act_grad_kernel(const float *__restrict__ out, const float *__restrict__ g_out, long long n_points, int C, int act,
                 int n_pad, long long dy_pitch, __nv_bfloat16 *__restrict__ dy) {
+  pdl_trigger();
+  pdl_wait();                                  // (nfs_common.cuh)
   const int chunks = n_pad / 8;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_points * chunks) return;
@@ -143,6 +147,8 @@ __global__ void __launch_bounds__(32 * kGateBwdWarps)
 gate_bwd_kernel(const float *__restrict__ x, const float *__restrict__ freqs, const float *__restrict__ extra,
                 const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dc, long long dc_pitch,
                 long long n_points, int D, int L, int E, int n_pad, __nv_bfloat16 *__restrict__ out) {
+  pdl_trigger();
+  pdl_wait();                                  // (nfs_common.cuh)
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kGateBwdWarps + (threadIdx.x >> 5);
   const long long n_warps = (long long)gridDim.x * kGateBwdWarps;
@@ -240,10 +246,9 @@ extern "C" int nfs_posenc_bf16(const float *x, const float *freqs, const float *
   if (smem > 48 * 1024) return fail_arg(fn, NFS_E_TOOLARGE, "k_pad too large");
   const long long blocks = (n_points + kEncTile - 1) / kEncTile;
   if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
-  posenc_bf16_kernel<<<(unsigned)blocks, kEncThreads, smem, (cudaStream_t)stream>>>(
-      x, freqs, extra_dim > 0 ? extra : nullptr, scale_enc, scale_extra, scale_stride, n_points, dim, n_freqs,
-      extra_dim, k_pad, out_pitch, (pow2_bands != 0 && n_freqs > 1) ? 1 : 0, (__nv_bfloat16 *)out_bf16);
-  return check_launch(fn);
+  return launch_dep(fn, posenc_bf16_kernel, dim3((unsigned)blocks), dim3(kEncThreads), smem, (cudaStream_t)stream,
+                    x, freqs, extra_dim > 0 ? extra : nullptr, scale_enc, scale_extra, scale_stride, n_points, dim, n_freqs,
+                    extra_dim, k_pad, out_pitch, (pow2_bands != 0 && n_freqs > 1) ? 1 : 0, (__nv_bfloat16 *)out_bf16);
 }
 
 extern "C" int nfs_pack_linear_bf16(const float *w, int32_t n_dim, int32_t k_dim, int32_t n_pad, int32_t k_pad,
@@ -402,9 +407,8 @@ extern "C" int nfs_act_grad_bf16(const float *out, const float *g_out, int64_t n
   const long long threads = n_points * (n_pad / 8);
   const long long blocks = (threads + 255) / 256;
   if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
-  act_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, g_out, n_points, n_cols, act, n_pad,
-                                                                     dy_pitch, (__nv_bfloat16 *)dy_bf16);
-  return check_launch(fn);
+  return launch_dep(fn, act_grad_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, out, g_out, n_points,
+                    n_cols, act, n_pad, dy_pitch, (__nv_bfloat16 *)dy_bf16);
 }
 
 extern "C" int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float *extra, const float *gate,
@@ -421,10 +425,9 @@ extern "C" int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float
   // grid-stride over points: at most 8 resident blocks per SM worth of warps
   const long long want = (n_points + kGateBwdWarps - 1) / kGateBwdWarps;
   const long long blocks = want < 148 * 8 ? want : 148 * 8;
-  gate_bwd_kernel<<<(unsigned)blocks, 32 * kGateBwdWarps, 0, (cudaStream_t)stream>>>(
-      x, freqs, extra, gate, (const __nv_bfloat16 *)dc_bf16, dc_pitch, n_points, dim, n_freqs, extra_dim, n_pad,
-      (__nv_bfloat16 *)dlogits_bf16);
-  return check_launch(fn);
+  return launch_dep(fn, gate_bwd_kernel, dim3((unsigned)blocks), dim3(32 * kGateBwdWarps), 0, (cudaStream_t)stream,
+                    x, freqs, extra, gate, (const __nv_bfloat16 *)dc_bf16, (long long)dc_pitch, (long long)n_points, dim,
+                    n_freqs, extra_dim, n_pad, (__nv_bfloat16 *)dlogits_bf16);
 }
 
 extern "C" int nfs_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,

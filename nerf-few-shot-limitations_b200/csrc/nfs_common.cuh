@@ -23,6 +23,34 @@ static inline int check_launch(const char *where) {
   return 0;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// A step is a few dozen dependent launches of 5-100 us each; every kernel's set-up (barrier init, TMEM allocation,
+// tensor-map prefetch) and the previous kernel's tail (store drain, TMEM release, CTA exit) are pure latency.  Kernels
+// launched through launch_dep() may start while their predecessor in the stream is still finishing: they run their
+// set-up, then pdl_wait() blocks until the predecessor has completed and its writes are visible.  RULES for such a
+// kernel: every thread executes pdl_wait() before its first access to global memory (reads AND writes - the
+// predecessor may still be reading what this kernel overwrites); pdl_trigger() only after the CTA holds its TMEM
+// allocation (a dependent CTA co-resident on the SM could otherwise take the columns and wait for this grid forever).
+// Without the launch attribute both instructions do nothing.  NFS_PDL=0 launches everything the classic way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline int launch_dep(const char *where, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail_cuda(where, e); }
+  return check_launch(where);
+}
+
 // cudaFuncSetAttribute is per device: remember per (call site, device) whether the opt-in shared-memory size has
 // been set, so that a process driving several GPUs configures the kernel on each of them.
 struct PerDeviceOnce {

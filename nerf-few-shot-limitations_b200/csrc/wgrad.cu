@@ -95,8 +95,7 @@ extern "C" int nfs_wgrad_bf16(const void *u_bf16, int64_t u_pitch, const void *v
     wgrad_pair_kernel<<<(unsigned)(2 * gp), kWgThreads, kWpSmemBytes, (cudaStream_t)stream>>>(tu, tv, a);
     return check_launch(fn);
   }
-  wgrad_kernel<<<(unsigned)g, kWgThreads, smem, (cudaStream_t)stream>>>(tu, tv, a);
-  return check_launch(fn);
+  return launch_dep(fn, wgrad_kernel, dim3((unsigned)g), dim3(kWgThreads), smem, (cudaStream_t)stream, tu, tv, a);
 }
 
 extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, void *stream) {
@@ -167,8 +166,7 @@ extern "C" int nfs_wgrad_multi_bf16(const nfs_wgrad_job *jobs, int32_t n_jobs, v
     m.cta0[k] = used;
     m.n_jobs = k;
     m.print_times = getenv("NFS_WGRAD_TIMES") != nullptr;
-    wgrad_multi_kernel<<<used, kWgThreads, smem, (cudaStream_t)stream>>>(m);
-    rc = check_launch(fn);
+    rc = launch_dep(fn, wgrad_multi_kernel, dim3(used), dim3(kWgThreads), smem, (cudaStream_t)stream, m);
     if (rc) return rc;
   }
   return 0;

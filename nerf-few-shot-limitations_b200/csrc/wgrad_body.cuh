@@ -97,6 +97,8 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap *tmap_u_p, const CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                                   // (nfs_common.cuh: programmatic dependent launch)
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {

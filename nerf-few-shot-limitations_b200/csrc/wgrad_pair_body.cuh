@@ -82,6 +82,8 @@ __device__ __forceinline__ void wgrad_pair_body(const CUtensorMap *tmap_u_p, con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                                   // (nfs_common.cuh: programmatic dependent launch)
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
