@@ -63,6 +63,12 @@ def test_g3_forward_backward_vs_oracle(cuda, kwargs, P):
            grad_rel_l2_small=max(small.values()) if small else 0.0, worst=max(rels, key=rels.get))
     assert e_rgb <= 2e-2 and e_den <= 1.0, (e_rgb, e_den)
     assert max(big.values()) <= 1e-1, big
+    # direction of every weight gradient, however small its norm: the gate branch (attention.*, the first use of
+    # fusion.*) carries ~1e-7 of the largest gradient, far below the absolute floor used for the small tensors below,
+    # so a wrong ReLU mask in its dgrad chain only shows here (measured >= 0.989; scripts/dev/g3_rels.py)
+    cos = {k: float((a.flatten() @ b.flatten()) / (a.norm() * b.norm()).clamp_min(1e-30))
+           for k, a, b in zip(names, grads, g_ref) if k.endswith("weight")}
+    assert min(cos.values()) >= 0.97, {k: v for k, v in cos.items() if v < 0.97}
     for k, a, b in zip(names, grads, g_ref):
         if k in small:
             assert float((a - b).norm()) <= 1e-1 * float(b.norm()) + 2e-4 * gmax, (k, rels[k])
