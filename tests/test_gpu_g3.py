@@ -67,7 +67,9 @@ def test_g3_forward_backward_vs_oracle(cuda, kwargs, P):
     # fusion.*) carries ~1e-7 of the largest gradient, far below the absolute floor used for the small tensors below,
     # so a wrong ReLU mask in its dgrad chain only shows here (measured >= 0.989; scripts/dev/g3_rels.py)
     cos = {k: float((a.flatten() @ b.flatten()) / (a.norm() * b.norm()).clamp_min(1e-30))
-           for k, a, b in zip(names, grads, g_ref) if k.endswith("weight")}
+           for k, a, b in zip(names, grads, g_ref) if k.endswith("weight") and float(b.norm()) > 0}
+    for k, a, b in zip(names, grads, g_ref):               # a dead head (all pre-activations <= 0) has a zero gradient
+        assert float(b.norm()) > 0 or float(a.norm()) == 0, k
     assert min(cos.values()) >= 0.97, {k: v for k, v in cos.items() if v < 0.97}
     for k, a, b in zip(names, grads, g_ref):
         if k in small:
