@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NFS_B200_ABI_VERSION 6
+#define NFS_B200_ABI_VERSION 7
 
 /* negative return codes (argument errors) */
 #define NFS_E_BADARG   (-1)  /* null pointer / non-positive size            */
@@ -457,6 +457,14 @@ int nfs_pack_stack(const void *table, int32_t n_entries, int32_t max_elems, void
  *           dst[(row0+k)*dst_pitch + col0+n];   mode 2: fp32 dst[row0+n] = src[n];   mode 3: bias terms
  *           (nfs_bias_terms_bf16) dst[row0+n].  max_elems = the largest n_dim*max(k_dim,1). */
 int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_elems, void *stream);
+
+/* nfs_scatter_add_table: several strided fp32 block adds in ONE launch.  table: device int64 [n_entries, 8], row =
+ *   [src, dst, rows, cols, src_ld_r, src_ld_c, dst_ld, clear]:  dst[r*dst_ld + c] += src[r*src_ld_r + c*src_ld_c];
+ *   clear != 0 zeroes the source entries afterwards (an accumulator that is reused every step needs no fill).
+ * Moves the lane-contiguous accumulators of the weight-gradient kernels (the output head's rows stacked in one
+ * operand, the first layer's gradient transposed) into the parameter gradients' own layout (autograd of
+ * nerf_model.py:16-24); max_elems = the largest rows*cols.  Blocks must not overlap. */
+int nfs_scatter_add_table(const void *table, int32_t n_entries, int64_t max_elems, void *stream);
 
 /* fp32 bias[n] -> terms_bf16 [n, 8] bf16, row i = [hi, mid, lo, 0, 0, 0, 0, 0] with hi + mid + lo = bias[i] to
  * ~2^-24 relative: the bias operand of nfs_mlp_chain (nn.Linear's "+ b", nerf_model.py:16-24, added on the

@@ -222,6 +222,26 @@ __global__ void adam_tick_kernel(int *step, float b1, float b2, float *state) {
   state[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
 }
 
+// Several strided fp32 block adds in one launch: dst[r*dst_ld + c] += src[r*src_ld_r + c*src_ld_c] per table row
+// [src, dst, rows, cols, src_ld_r, src_ld_c, dst_ld, clear] (clear != 0: the source entries are zeroed after they have been
+// read).  The weight-gradient kernels write lane-contiguous
+// accumulators (the head's rows stacked, the first layer transposed); this moves them into the parameters' own layout
+// (five torch adds per training step before).
+__global__ void __launch_bounds__(256) scatter_add_table_kernel(const long long *__restrict__ table) {
+  pdl_trigger();
+  pdl_wait();                                  // (nfs_common.cuh)
+  const long long *e = table + 8 * blockIdx.y;
+  const float *src = reinterpret_cast<const float *>(e[0]);
+  float *dst = reinterpret_cast<float *>(e[1]);
+  const long long rows = e[2], cols = e[3], n = rows * cols;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols, c = idx - r * cols;
+    float *sp = const_cast<float *>(src) + r * e[4] + c * e[5];
+    dst[r * e[6] + c] += *sp;
+    if (e[7]) *sp = 0.f;                       // leave the accumulator clean for the next step (no fill launch)
+  }
+}
+
 }  // namespace
 }  // namespace nfs
 
@@ -382,6 +402,16 @@ extern "C" int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_
   dim3 grid((unsigned)(bx < 16 ? bx : 16), (unsigned)n_entries);
   pack_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)table);
   return check_launch(fn);
+}
+
+extern "C" int nfs_scatter_add_table(const void *table, int32_t n_entries, int64_t max_elems, void *stream) {
+  const char *fn = "nfs_scatter_add_table";
+  if (n_entries < 0 || max_elems < 0) return fail_arg(fn, NFS_E_BADARG, "negative size");
+  if (n_entries == 0 || max_elems == 0) return 0;
+  if (!table) return fail_arg(fn, NFS_E_BADARG, "null table");
+  const long long bx = (max_elems + 255) / 256;
+  dim3 grid((unsigned)(bx < 64 ? bx : 64), (unsigned)n_entries);
+  return launch_dep(fn, scatter_add_table_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const long long *)table);
 }
 
 extern "C" int nfs_bias_terms_bf16(const float *bias, int32_t n, void *terms_bf16, void *stream) {

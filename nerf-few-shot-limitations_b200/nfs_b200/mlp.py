@@ -543,10 +543,24 @@ class StepSession:
             self.bits = torch.zeros((n_hidden, rows, 8), device=dev, dtype=torch.int32)
             self.dy = torch.zeros((rows, 64), device=dev, dtype=torch.bfloat16)
             self.dys = torch.zeros((n_hidden, rows, plan.h_pad), device=dev, dtype=torch.bfloat16)
-            self.head_w = torch.zeros((64, plan.h_pad), device=dev, dtype=torch.float32)
-            self.head_b = torch.zeros(64, device=dev, dtype=torch.float32)
-            self.w0_t = torch.zeros((plan.k0, plan.h_pad), device=dev, dtype=torch.float32)
             self.quad_flags = torch.zeros(2 * (rows // 512 + 2), device=dev, dtype=torch.int32)
+        if getattr(self, "tmp", None) is None:
+            # lane-contiguous accumulators of the head's and the first layer's weight gradients: one buffer (one fill per
+            # step) and one table-driven launch that adds them into the parameters' own layout (_scatter_head)
+            hp, k0, hd, L = plan.h_pad, plan.k0, plan.hidden, len(plan.packed)
+            self.tmp = torch.zeros(64 * hp + 64 + k0 * hp, device=dev, dtype=torch.float32)
+            self.head_w = self.tmp[:64 * hp].view(64, hp)
+            self.head_b = self.tmp[64 * hp:64 * hp + 64]
+            self.w0_t = self.tmp[64 * hp + 64:].view(k0, hp)
+            v, hw, hb = self.views, self.head_w.data_ptr(), self.head_b.data_ptr()
+            table = [[hw + 3 * hp * 4, v[2 * L + 0].data_ptr(), 1, hd, hp, 1, hd, 1],      # sigma_out.weight (head row 3)
+                     [hb + 3 * 4, v[2 * L + 1].data_ptr(), 1, 1, 1, 1, 1, 1],
+                     [hw, v[2 * L + 2].data_ptr(), 3, hd, hp, 1, hd, 1],                   # rgb_out.weight (head rows 0..2)
+                     [hb, v[2 * L + 3].data_ptr(), 1, 3, 3, 1, 3, 1],
+                     [self.w0_t.data_ptr(), v[0].data_ptr(), hd, plan.in_dim, 1, hp, plan.in_dim, 1]]   # first layer, transposed back
+            self.tmp_clean = True               # every entry the weight gradients touch is cleared by the scatter launch
+            self.scatter = torch.tensor(table, dtype=torch.int64, device=dev)
+            self.scatter_max = max(r[2] * r[3] for r in table)
         self.cursor = 0
         self.pending = 0
         self.n_calls = 0
@@ -559,9 +573,9 @@ class StepSession:
         force = os.environ.get("NFS_BWD_MERGED", "")
         self.merged = plan.h_pad == 256 and (force not in ("", "0") if force != "" else rows >= 65536)
         self.opt.grad.zero_()
-        self.head_w.zero_()
-        self.head_b.zero_()
-        self.w0_t.zero_()
+        if not self.tmp_clean:                  # only after a step that never reached flush()
+            self.tmp.zero_()
+        self.tmp_clean = False
         plan._session = self
         return self
 
@@ -631,10 +645,7 @@ class StepSession:
         with torch.cuda.stream(side):
             ops.wgrad_bf16(self.save[n_layers - 1, :T], self.dy[:T], self.head_w, 1, plan.h_pad, colsum=self.head_b,
                            colsum_of_v=True)
-            v[2 * n_layers + 0].add_(self.head_w[3:4, :hd])      # sigma_out.weight (head rows 0..2 rgb_out, 3 sigma_out)
-            v[2 * n_layers + 1].add_(self.head_b[3:4])
-            v[2 * n_layers + 2].add_(self.head_w[0:3, :hd])
-            v[2 * n_layers + 3].add_(self.head_b[0:3])
+            self._scatter_head(4)
         for n, i in enumerate(range(n_layers - 1, 0, -1)):
             with torch.cuda.stream(side if n & 1 else main):
                 ops.wgrad_bf16(self.save[i - 1, :T], self.dys[n_layers - 1 - i, :T], v[2 * i], 1, hd, colsum=v[2 * i + 1],
@@ -649,7 +660,9 @@ class StepSession:
             else:
                 ops.wgrad_bf16(self.dys[n_layers - 1, :T], self.x16[:T], self.w0_t, 1, plan.h_pad, colsum=v[1],
                                colsum_of_v=False, m_valid=hd, n_valid=plan.in_dim)
-                v[0].add_(self.w0_t[:plan.in_dim, :hd].t())
+                with torch.cuda.device(dev):
+                    _lib.call("nfs_scatter_add_table", ptr(self.scatter[4:]), 1, self.scatter_max, _stream())
+            self.tmp_clean = True
         main.wait_stream(side)
 
 
@@ -706,11 +719,13 @@ class StepSession:
                           ptr(plan.wt_stack), plan.wt_rows, ptr(self.bits), self.rows_cap, plan.cb_mask, ptr(self.dys),
                           self.rows_cap, ctypes.byref(arr), n, c_waits, ptr(self.quad_flags), 0, _stream())
         self.k1 = []
-        v[2 * n_layers + 0].add_(self.head_w[3:4, :hd])      # sigma_out.weight (head rows 0..2 rgb_out, 3 sigma_out)
-        v[2 * n_layers + 1].add_(self.head_b[3:4])
-        v[2 * n_layers + 2].add_(self.head_w[0:3, :hd])
-        v[2 * n_layers + 3].add_(self.head_b[0:3])
-        v[0].add_(self.w0_t[:plan.in_dim, :hd].t())
+        self._scatter_head()
+
+    def _scatter_head(self, entries=5):
+        """head_w / head_b / w0_t -> sigma_out, rgb_out and the first layer's gradient views (one launch)."""
+        with torch.cuda.device(self.tmp.device):
+            _lib.call("nfs_scatter_add_table", ptr(self.scatter), entries, self.scatter_max, _stream())
+        self.tmp_clean = entries == 5
 
 
 class _G1Fn(torch.autograd.Function):

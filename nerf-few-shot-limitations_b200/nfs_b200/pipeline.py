@@ -27,7 +27,11 @@ def render_rays(model, freq_bands, rays_o, rays_d, near, far, n_coarse=64, n_imp
     renderings are detached."""
     N = rays_o.shape[0]
     dev = rays_o.device
-    if perturb and t_rand is None:
+    if perturb and t_rand is None and u is None and n_importance > 0 and (N * n_coarse) % 4 == 0:
+        # both draws of the step from one generator launch (the coarse jitter first, as the reference draws them)
+        r = torch.rand(N * (n_coarse + n_importance), device=dev)
+        t_rand, u = r[:N * n_coarse].view(N, n_coarse), r[N * n_coarse:].view(N, n_importance)
+    elif perturb and t_rand is None:
         t_rand = torch.rand(N, n_coarse, device=dev)
     plan = model._get_plan() if hasattr(model, "_get_plan") else None
     in_kernel = plan is not None and hasattr(model, "forward_rays") and (plan.refresh() or True) \
@@ -370,7 +374,7 @@ class GraphedTrainStep(GraphedStep):
         sess = _session_for(model, optimizer)
         plan = model._get_plan() if hasattr(model, "_get_plan") else None
         self._captured = [getattr(o, k, None) for o, keys in (
-            (sess, ("x16", "save", "bits", "dy", "dys", "head_w", "head_b", "w0_t", "quad_flags")),
+            (sess, ("x16", "save", "bits", "dy", "dys", "head_w", "head_b", "w0_t", "quad_flags", "scatter")),
             (plan, ("w_stack", "wt_stack", "b_stack", "_table"))) if o is not None for k in keys]
 
     def _forward_backward(self):

@@ -26,7 +26,7 @@ def test_library_is_built_and_exports_header_symbols():
 def test_abi_version_and_error_string():
     from nfs_b200 import _lib
     lib = _lib.load()
-    assert lib.nfs_abi_version() == 6
+    assert lib.nfs_abi_version() == 7
     assert isinstance(_lib.last_error(), str)
     assert _lib.launch_count() >= 0
 
