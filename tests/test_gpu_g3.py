@@ -38,6 +38,7 @@ def _inputs(P, D, seed):
     (dict(pos_freq=12, dino_dim=64), 1000),                # BASELINE cfg 4 (dino_nerf.yaml): K0 = 139 -> 192
     (dict(dino_dim=0), 777),                               # feature-less variant (train.py use_dino=False)
     (dict(pos_freq=6, dir_freq=2, dino_dim=16, hidden_dim=128, num_density_layers=2), 130),
+    (dict(num_density_layers=9), 300),                     # 12-layer chains: the density head no longer fits its chain
 ])
 def test_g3_forward_backward_vs_oracle(cuda, kwargs, P):
     from helpers import record
