@@ -458,6 +458,26 @@ int nfs_pack_stack(const void *table, int32_t n_entries, int32_t max_elems, void
  *           (nfs_bias_terms_bf16) dst[row0+n].  max_elems = the largest n_dim*max(k_dim,1). */
 int nfs_pack_table(const void *table, int32_t n_entries, int32_t max_elems, void *stream);
 
+/* nfs_g3_operand: K5 + K2 as the PRODUCER of the conditioned model's first operand: row p of
+ *   out_bf16 [P,k_pad] = [x, sin(x f_0), cos(x f_0), ..., cos(x f_{L-1}) | bilinear features of the projected point | 0]
+ *   (dino_feature_model.py:182 on top of ray_utils.py:176-210 + dino_feature_model.py:114-148 + nerf_mlp.py:24-33), i.e.
+ *   nfs_project_gather followed by nfs_posenc_bf16 without the (P,C) fp32 features in between.  Arguments as the
+ *   arguments of the same name of those two entries; k_pad % 8 == 0, 3 (2 n_freqs + 1) + C <= k_pad <= 320. */
+int nfs_g3_operand(const float *points, const float *pose_inv, float focal, int32_t H, int32_t W,
+                   const float *features, int32_t Hp, int32_t Wp, int32_t C, const float *freqs, int32_t n_freqs,
+                   int32_t pow2_bands, int64_t n_points, int32_t k_pad, int64_t out_pitch, void *out_bf16, void *stream);
+
+/* nfs_gate_scale_bf16 / nfs_gate_bwd_operand: the softmax gate of NeRFDINOFusion (dino_feature_model.py:188-195) and
+ *   its backward, on the bf16 operand c = [enc(x) | f | 0] [P,k_pad] that the first fusion layer consumed:
+ *     out[p,j] = c[p,j] * (j < enc_w ? gate[p,0] : gate[p,1])
+ *     dlogits[p,0:2] = g_i (dg_i - (g0 dg0 + g1 dg1)),  dg0 = <dc[p,0:enc_w], c[p,0:enc_w]>,  dg1 = <dc[p,enc_w:width], c[p,enc_w:width]>
+ *   (bf16 [P,n_pad], zero padded).  The fp32 variants that recompute enc(x) are nfs_posenc_bf16 (with its scale
+ *   arguments) and nfs_gate_bwd_bf16. */
+int nfs_gate_scale_bf16(const void *c_bf16, int64_t c_pitch, const float *gate, int64_t n_points, int32_t enc_w,
+                        int32_t k_pad, void *out_bf16, int64_t out_pitch, void *stream);
+int nfs_gate_bwd_operand(const void *c_bf16, int64_t c_pitch, const float *gate, const void *dc_bf16, int64_t dc_pitch,
+                         int64_t n_points, int32_t enc_w, int32_t width, int32_t n_pad, void *dlogits_bf16, void *stream);
+
 /* nfs_scatter_add_table: several strided fp32 block adds in ONE launch.  table: device int64 [n_entries, 8], row =
  *   [src, dst, rows, cols, src_ld_r, src_ld_c, dst_ld, clear]:  dst[r*dst_ld + c] += src[r*src_ld_r + c*src_ld_c];
  *   clear != 0 zeroes the source entries afterwards (an accumulator that is reused every step needs no fill).

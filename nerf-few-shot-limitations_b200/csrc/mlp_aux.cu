@@ -193,6 +193,70 @@ gate_bwd_kernel(const float *__restrict__ x, const float *__restrict__ freqs, co
   }
 }
 
+// The same two operations on the bf16 operand c = [enc(x) | f] the first fusion layer consumed, instead of on x and f:
+//   gate_scale:       c'[p,j] = c[p,j] * (j < enc_w ? g0 : g1)           (dino_feature_model.py:191-195)
+//   gate_bwd_operand: dg0 = <dc'[0:enc_w], c[0:enc_w]>, dg1 = <dc'[enc_w:width], c[enc_w:width]>, dlogits as above
+// - no trigonometry, no fp32 feature tensor: both read 2 bytes per element that the forward pass wrote anyway.
+__global__ void __launch_bounds__(256)
+gate_scale_kernel(const __nv_bfloat16 *__restrict__ c, long long c_pitch, const float *__restrict__ gate, long long n_points,
+                  int enc_w, int k_pad, long long out_pitch, __nv_bfloat16 *__restrict__ out) {
+  pdl_trigger();
+  pdl_wait();                                  // (nfs_common.cuh)
+  const int chunks = k_pad >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_points * chunks) return;
+  const long long p = t / chunks;
+  const int c0 = (int)(t - p * chunks) * 8;
+  const float g0 = __ldg(gate + 2 * p), g1 = __ldg(gate + 2 * p + 1);
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(c + p * c_pitch + c0));
+  const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float lo = __uint_as_float(in[j] << 16), hi = __uint_as_float(in[j] & 0xffff0000u);
+    o[j] = tc::pack_bf16x2(lo * (c0 + 2 * j < enc_w ? g0 : g1), hi * (c0 + 2 * j + 1 < enc_w ? g0 : g1));
+  }
+  *reinterpret_cast<uint4 *>(out + p * out_pitch + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(32 * kGateBwdWarps)
+gate_bwd_operand_kernel(const __nv_bfloat16 *__restrict__ c, long long c_pitch, const float *__restrict__ gate,
+                        const __nv_bfloat16 *__restrict__ dc, long long dc_pitch, long long n_points, int enc_w, int width,
+                        int n_pad, __nv_bfloat16 *__restrict__ out) {
+  pdl_trigger();
+  pdl_wait();                                  // (nfs_common.cuh)
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * kGateBwdWarps + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * kGateBwdWarps;
+  const int chunks = (width + 7) >> 3;                     // both rows are zero beyond `width` up to a multiple of 8
+  for (long long p = warp; p < n_points; p += n_warps) {
+    float dg0 = 0.f, dg1 = 0.f;
+    for (int ch = lane; ch < chunks; ch += 32) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4 *>(c + p * c_pitch) + ch);
+      const uint4 b = __ldg(reinterpret_cast<const uint4 *>(dc + p * dc_pitch) + ch);
+      const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t0 = __uint_as_float(av[j] << 16) * __uint_as_float(bv[j] << 16);
+        const float t1 = __uint_as_float(av[j] & 0xffff0000u) * __uint_as_float(bv[j] & 0xffff0000u);
+        const int col = ch * 8 + 2 * j;
+        if (col < enc_w) dg0 += t0; else if (col < width) dg1 += t0;
+        if (col + 1 < enc_w) dg0 += t1; else if (col + 1 < width) dg1 += t1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dg0 += __shfl_xor_sync(0xffffffffu, dg0, o);
+      dg1 += __shfl_xor_sync(0xffffffffu, dg1, o);
+    }
+    const float g0 = __ldg(gate + 2 * p), g1 = __ldg(gate + 2 * p + 1);
+    const float mean = g0 * dg0 + g1 * dg1;
+    uint4 *o = reinterpret_cast<uint4 *>(out + p * n_pad);
+    for (int ch = lane; ch < n_pad / 8; ch += 32)
+      o[ch] = ch == 0 ? make_uint4(tc::pack_bf16x2(g0 * (dg0 - mean), g1 * (dg1 - mean)), 0, 0, 0) : make_uint4(0, 0, 0, 0);
+  }
+}
+
 // ------------------------------------------------------------------ Adam / AdamW over a flat buffer
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
@@ -458,6 +522,41 @@ extern "C" int nfs_gate_bwd_bf16(const float *x, const float *freqs, const float
   return launch_dep(fn, gate_bwd_kernel, dim3((unsigned)blocks), dim3(32 * kGateBwdWarps), 0, (cudaStream_t)stream,
                     x, freqs, extra, gate, (const __nv_bfloat16 *)dc_bf16, (long long)dc_pitch, (long long)n_points, dim,
                     n_freqs, extra_dim, n_pad, (__nv_bfloat16 *)dlogits_bf16);
+}
+
+extern "C" int nfs_gate_scale_bf16(const void *c_bf16, int64_t c_pitch, const float *gate, int64_t n_points, int32_t enc_w,
+                                   int32_t k_pad, void *out_bf16, int64_t out_pitch, void *stream) {
+  const char *fn = "nfs_gate_scale_bf16";
+  if (n_points < 0 || enc_w < 0 || k_pad <= 0 || (k_pad & 7)) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
+  if (n_points == 0) return 0;
+  if (!c_bf16 || !gate || !out_bf16) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  if (c_pitch == 0) c_pitch = k_pad;
+  if (out_pitch == 0) out_pitch = k_pad;
+  if (c_pitch < k_pad || out_pitch < k_pad || ((c_pitch | out_pitch) & 7) || !aligned16(c_bf16) || !aligned16(out_bf16))
+    return fail_arg(fn, NFS_E_ALIGN, "pitches must be >= k_pad and multiples of 8, tensors 16-byte aligned");
+  const long long blocks = (n_points * (k_pad / 8) + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail_arg(fn, NFS_E_TOOLARGE, "too many points for one launch");
+  return launch_dep(fn, gate_scale_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                    (const __nv_bfloat16 *)c_bf16, (long long)c_pitch, gate, (long long)n_points, enc_w, k_pad,
+                    (long long)out_pitch, (__nv_bfloat16 *)out_bf16);
+}
+
+extern "C" int nfs_gate_bwd_operand(const void *c_bf16, int64_t c_pitch, const float *gate, const void *dc_bf16,
+                                    int64_t dc_pitch, int64_t n_points, int32_t enc_w, int32_t width, int32_t n_pad,
+                                    void *dlogits_bf16, void *stream) {
+  const char *fn = "nfs_gate_bwd_operand";
+  if (n_points < 0 || enc_w < 0 || width < enc_w || n_pad < 8 || (n_pad & 7)) return fail_arg(fn, NFS_E_BADARG, "bad sizes");
+  if (n_points == 0) return 0;
+  if (!c_bf16 || !gate || !dc_bf16 || !dlogits_bf16) return fail_arg(fn, NFS_E_BADARG, "null tensor pointer");
+  const long long w8 = (width + 7) / 8 * 8;
+  if (c_pitch < w8 || dc_pitch < w8 || ((c_pitch | dc_pitch) & 7) || !aligned16(c_bf16) || !aligned16(dc_bf16) ||
+      !aligned16(dlogits_bf16))
+    return fail_arg(fn, NFS_E_ALIGN, "row pitches must cover the width rounded up to 8 and be multiples of 8; 16-byte aligned tensors");
+  const long long want = (n_points + kGateBwdWarps - 1) / kGateBwdWarps;
+  const long long blocks = want < 148 * 8 ? want : 148 * 8;
+  return launch_dep(fn, gate_bwd_operand_kernel, dim3((unsigned)blocks), dim3(32 * kGateBwdWarps), 0, (cudaStream_t)stream,
+                    (const __nv_bfloat16 *)c_bf16, (long long)c_pitch, gate, (const __nv_bfloat16 *)dc_bf16,
+                    (long long)dc_pitch, (long long)n_points, enc_w, width, n_pad, (__nv_bfloat16 *)dlogits_bf16);
 }
 
 extern "C" int nfs_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,

@@ -43,6 +43,10 @@ SIGNATURES = {
     "nfs_pack_stack": (ctypes.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
     "nfs_pack_table": (ctypes.c_int, [_p, _i32, _i32, _p]),
     "nfs_scatter_add_table": (ctypes.c_int, [_p, _i32, _i64, _p]),
+    "nfs_g3_operand": (ctypes.c_int, [_p, _p, ctypes.c_float, _i32, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _i64, _i32,
+                                      _i64, _p, _p]),
+    "nfs_gate_scale_bf16": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _i32, _p, _i64, _p]),
+    "nfs_gate_bwd_operand": (ctypes.c_int, [_p, _i64, _p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p]),
     "nfs_bias_terms_bf16": (ctypes.c_int, [_p, _i32, _p, _p]),
     "nfs_mlp_chain_points": (ctypes.c_int, [_p, _f32, _i32, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _i32, _p]),
     "nfs_mlp_chain_points_train": (ctypes.c_int, [_p, _f32, _i32, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p,

@@ -180,8 +180,9 @@ def encode_operand(x, freqs, k_pad, extra=None, gate=None, out=None):
         if gate is not None:
             gate = ops._f32c(gate)
             g0, g1 = ptr(gate), ctypes.c_void_p(gate.data_ptr() + 4)
+        extra = ops._f32c(extra) if E else None          # a converted copy must outlive the launch: hold it in a name
         with torch.cuda.device(x.device):
-            _lib.call("nfs_posenc_bf16", ptr(x), ptr(fr), ptr(ops._f32c(extra)) if E else None, g0, g1, 2, P, D, L, E,
+            _lib.call("nfs_posenc_bf16", ptr(x), ptr(fr), ptr(extra), g0, g1, 2, P, D, L, E,
                       k_pad, int(pitch), int(octaves), ptr(out), _stream())
     return out
 

@@ -4,17 +4,18 @@ nerf_mlp.NeRFWithDINO = NeRFDINOFusion -> DensityMLP -> ColorMLP
 
 The nn.Modules in models/ keep the reference's fp32 parameters; this file owns the launch
 sequence.  Forward, P points:
-    c    = [enc(x) | f]                         nfs_posenc_bf16          (dino_feature_model.py:182)
+    c    = [enc(x) | f]                         nfs_posenc_bf16, or nfs_g3_operand when f is looked up in a feature map
+                                                (projection + lookup + encoding in one kernel) (dino_feature_model.py:182)
     h2   = relu(W2 relu(W1 c))                  one nfs_mlp_chain for both lines: three layers and the
     g    = softmax(Wb relu(Wa h2))              2-way softmax as its fp32 head (:185,188)
-    c'   = [enc(x) g0 | f g1]                   nfs_posenc_bf16 with the gate (:191-195)
+    c'   = [enc(x) g0 | f g1]                   nfs_gate_scale_bf16 on the operand c (:191-195)
     h_n  = density layers(Wo relu(W2 relu(W1 c')))   nfs_mlp_chain (3 + n_density layers) (:195-197, nerf_mlp.py:60)
     dens = relu(w_d h_n), feat = W_f h_n        head of that chain; nfs_linear_bf16 (nerf_mlp.py:61-65)
     rgb  = sigmoid(Wc3 relu(Wc2 relu(Wc1 [feat | enc(d)])))   nfs_posenc_bf16 + nfs_linear_bf16 (K = 320) +
                                                 nfs_mlp_chain [Wc2, Wc3 as sigmoid head] (:82-84)
 Backward: the same graph in reverse - dgrad GEMMs with the ReLU-backward mask fused in their
 epilogues (nfs_mlp_chain act 4 / nfs_linear_bf16 relu_mask_src), nfs_wgrad_bf16 for every weight
-and bias (the fusion layers W1, W2 receive both of their uses), nfs_gate_bwd_bf16 for the softmax
+and bias (the fusion layers W1, W2 receive both of their uses), nfs_gate_bwd_operand for the softmax
 gate.  Nothing here computes on the CPU or in eager PyTorch.
 """
 import ctypes
@@ -354,12 +355,23 @@ class G3Plan:
         res = (save,) + ((bits,) if want_bits else ()) + ((out,) if head_cols else ())
         return res if len(res) > 1 else save
 
-    def run_forward(self, x, d, f, freqs_pos, freqs_dir):
-        P = x.shape[0]
+    def gate_scale(self, c16, gate):
+        """c' = [enc(x) g0 | f g1] from the operand the first pass consumed (nfs_gate_scale_bf16)."""
+        out = torch.empty_like(c16)
+        with torch.cuda.device(c16.device):
+            _lib.call("nfs_gate_scale_bf16", ptr(c16), c16.stride(0), ptr(gate), c16.shape[0], self.pos_w, self.k0,
+                      ptr(out), out.stride(0), _stream())
+        return out
+
+    def run_forward(self, x, d, f, freqs_pos, freqs_dir, c16=None):
+        """c16: the first operand [enc(x) | f | 0] bf16 [P,k0] when the caller has built it already (nfs_g3_operand:
+        projection + feature lookup + encoding in one kernel); x / f are not read then."""
+        P = d.shape[0]
         hp = self.hp
-        c16 = encode_operand(x, freqs_pos, self.k0, extra=f)
+        if c16 is None:
+            c16 = encode_operand(x, freqs_pos, self.k0, extra=f)
         sa, sa_bits, gate = self._chain(c16, self.chain_a, 4, self.ca_act, P, want_bits=True, head_cols=2)
-        c2 = encode_operand(x, freqs_pos, self.k0, extra=f, gate=gate)
+        c2 = self.gate_scale(c16, gate)
         if self.head_in_chain:
             sb, sb_bits, density = self._chain(c2, self.chain_b, self.nb + 1, self.cbf_act, P, want_bits=True, head_cols=1)
         else:
@@ -367,7 +379,7 @@ class G3Plan:
         hn = sb[self.nb - 1, :P]
         if not self.head_in_chain:
             _, density = ops.linear_bf16(hn, self.pdh.w16, self.pdh.bias, act=1, out_bf16=False, out_f32_cols=1)
-        cat16 = torch.empty((P, self.cat_k), device=x.device, dtype=torch.bfloat16)
+        cat16 = torch.empty((P, self.cat_k), device=d.device, dtype=torch.bfloat16)
         ops.linear_bf16(hn, self.pf.w16, self.pf.bias, act=0, out=cat16[:, :hp])
         encode_operand(d, freqs_dir, self.kd, out=cat16[:, hp:])
         k1, _ = ops.linear_bf16(cat16, self.pc1.w16, self.pc1.bias, act=1)
@@ -376,10 +388,10 @@ class G3Plan:
         saved = (c16, sa, sa_bits, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits)
         return rgb, density, saved
 
-    def run_backward(self, x, f, freqs_pos, saved, g_rgb, g_density):
+    def run_backward(self, saved, g_rgb, g_density):
         c16, sa, sa_bits, gate, c2, sb, density, cat16, k1, k2, rgb, sb_bits = saved
-        P = x.shape[0]
-        dev = x.device
+        P = c16.shape[0]
+        dev = c16.device
         hp, H, nb = self.hp, self.H, self.nb
         lins = self.linears()
         ps = self.params()
@@ -441,11 +453,9 @@ class G3Plan:
         # ---- the gate (dino_feature_model.py:188-195)
         dc2 = dys[nb - 1]                              # d c' = d(pre-activation of W1) . W1, last step of the chain
         dlog = torch.empty((P, 64), device=dev, dtype=torch.bfloat16)
-        from .mlp import freqs_on
-        fr = freqs_on(dev, freqs_pos)
         with torch.cuda.device(dev):
-            _lib.call("nfs_gate_bwd_bf16", ptr(x), ptr(fr), ptr(f) if self.D else None, ptr(gate), ptr(dc2), dc2.shape[1], P,
-                      3, int(fr.numel()), self.D, 64, ptr(dlog), _stream())
+            _lib.call("nfs_gate_bwd_operand", ptr(c16), c16.stride(0), ptr(gate), ptr(dc2), dc2.shape[1], P, self.pos_w,
+                      self.pos_w + self.D, 64, ptr(dlog), _stream())
         h1, h2, a16 = sa[0, :P], sa[1, :P], sa[2, :P, :self.ap]
         wg(self.Wb, a16, dlog)
         # d a, d h2, d h1 (pre-activations): one dgrad chain [Wb^T, Wa^T, W2^T] masked by chain A's sign bits
@@ -460,24 +470,54 @@ class G3Plan:
 
 class _G3Fn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, keep, x, d, f, freqs_pos, freqs_dir, *params):
-        rgb, density, saved = plan.run_forward(x, d, f, freqs_pos, freqs_dir)
+    def forward(ctx, plan, keep, x, d, f, c16, freqs_pos, freqs_dir, *params):
+        rgb, density, saved = plan.run_forward(x, d, f, freqs_pos, freqs_dir, c16=c16)
         if keep:
             ctx.plan = plan
-            ctx.has_f = f is not None
-            ctx.save_for_backward(x, f if f is not None else x.new_empty(0), freqs_pos, *saved)
+            ctx.save_for_backward(*saved)
         ctx.set_materialize_grads(False)
         return rgb, density
 
     @staticmethod
     def backward(ctx, g_rgb, g_density):
-        x, f, freqs_pos, *saved = ctx.saved_tensors
         if g_rgb is None and g_density is None:
-            return (None,) * (7 + len(ctx.plan.params()))
-        grads = ctx.plan.run_backward(x, f if ctx.has_f else None, freqs_pos, tuple(saved),
-                                      None if g_rgb is None else g_rgb.contiguous(),
+            return (None,) * (8 + len(ctx.plan.params()))
+        grads = ctx.plan.run_backward(tuple(ctx.saved_tensors), None if g_rgb is None else g_rgb.contiguous(),
                                       None if g_density is None else g_density.contiguous())
-        return (None,) * 7 + tuple(grads)
+        return (None,) * 8 + tuple(grads)
+
+
+def _g3_apply(plan, x, d, f, c16):
+    m = plan.module
+    params = plan.params()
+    keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _G3Fn.apply(plan, keep, x, d, f, c16, m.pos_encoder.freq_bands, m.dir_encoder.freq_bands, *params)
+
+
+def g3_forward_from_map(plan, positions, directions, feature_map, pose_inv, focal, H, W):
+    """NeRFWithDINO on points whose image features come from ONE source view (train.py:209-231): projection,
+    bilinear lookup and positional encoding run as the producer of the first layer's bf16 operand (nfs_g3_operand),
+    the (P,C) fp32 features never exist.  feature_map (1,Hp,Wp,C) | (Hp,Wp,C) fp32; pose_inv (4,4) = inverse pose."""
+    from .mlp import bands_are_octaves, freqs_on
+    m = plan.module
+    ops._need_cuda("NeRFWithDINO", positions, directions, feature_map, pose_inv)
+    fm = ops._f32c(feature_map if feature_map.dim() == 3 else feature_map[0])
+    Hp, Wp, C = fm.shape
+    if C != plan.D or plan.D == 0:
+        raise RuntimeError("NeRFWithDINO: the feature map has %d channels, the model expects %d" % (C, plan.D))
+    plan.refresh()
+    x, d = ops._f32c(positions), ops._f32c(directions)
+    P = x.shape[0]
+    if P == 0:
+        return x.new_zeros((0, 3)), x.new_zeros((0, 1))
+    bands = m.pos_encoder.freq_bands
+    fr = freqs_on(x.device, bands)
+    c16 = torch.empty((P, plan.k0), device=x.device, dtype=torch.bfloat16)
+    pinv = ops._f32c(pose_inv)               # (torch.inverse returns a column-major tensor: this is a copy, kept alive here)
+    with torch.cuda.device(x.device):
+        _lib.call("nfs_g3_operand", ptr(x), ptr(pinv), float(focal), int(H), int(W), ptr(fm), Hp, Wp, C,
+                  ptr(fr), int(fr.numel()), int(bands_are_octaves(bands)), P, plan.k0, c16.stride(0), ptr(c16), _stream())
+    return _g3_apply(plan, None, d, None, c16)
 
 
 def g3_forward(plan, positions, directions, dino_features):
@@ -504,9 +544,7 @@ def g3_forward(plan, positions, directions, dino_features):
     if P == 0:
         z = x.new_zeros((0, 3))
         return z, x.new_zeros((0, 1))
-    params = plan.params()
-    keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    return _G3Fn.apply(plan, keep, x, d, f, m.pos_encoder.freq_bands, m.dir_encoder.freq_bands, *params)
+    return _g3_apply(plan, x, d, f, None)
 
 
 # --------------------------------------------------------------------------------- single layers

@@ -265,10 +265,18 @@ def render_rays_conditioned(model, rays_o, rays_d, near, far, n_samples, pose, f
         t_rand = torch.rand(N, n_samples, device=rays_o.device)
     pts, z = ops.sample_stratified(rays_o, rays_d, near, far, n_samples, t_rand=t_rand if perturb else None)
     pts_flat = pts.reshape(-1, 3)
-    _, _, _, feats = ops.project_gather(pts_flat, pose, focal, H, W, features=feature_map, want_projection=False,
-                                        pose_inv=pose_inv)
     dirs = rays_d.unsqueeze(1).expand(-1, n_samples, -1).reshape(-1, 3)          # train.py:225
-    rgb, density = model(pts_flat, dirs, feats)
+    plan = model._get_plan() if hasattr(model, "_get_plan") else None
+    if hasattr(plan, "chain_a_bwd") and plan.D > 0 and os.environ.get("NFS_G3_OPERAND", "1") != "0":
+        # projection + feature lookup + encoding as the producer of the first layer's operand (nfs_g3_operand)
+        from . import mlp_g3
+        if pose_inv is None:
+            pose_inv = torch.inverse(pose)                                         # ray_utils.py:192
+        rgb, density = mlp_g3.g3_forward_from_map(plan, pts_flat, dirs, feature_map, pose_inv, focal, H, W)
+    else:
+        _, _, _, feats = ops.project_gather(pts_flat, pose, focal, H, W, features=feature_map, want_projection=False,
+                                            pose_inv=pose_inv)
+        rgb, density = model(pts_flat, dirs, feats)
     rgb_map, depth, weights = ops.composite(rgb.reshape(N, n_samples, 3), density.reshape(N, n_samples, 1), z, rays_d,
                                             white_bkgd=white_bkgd)
     return {"rgb": rgb_map, "depth": depth, "weights": weights, "z_vals": z}

@@ -167,3 +167,97 @@ def test_submodules_standalone(cuda):
         gc = torch.autograd.grad(loss_c, ins_c + list(mod.parameters()))
         for a, b in zip(gc, gr):
             assert float((a.cpu() - b).norm()) <= 1e-1 * float(b.norm()) + 1e-7, type(mod).__name__
+
+
+@pytest.mark.parametrize("P,pos_freq,C", [(1, 12, 64), (1000, 12, 64), (4097, 10, 64), (333, 6, 16)])
+def test_g3_operand_kernel_matches_two_kernel_route(cuda, P, pos_freq, C):
+    """nfs_g3_operand (projection + bilinear lookup + encoding -> the bf16 operand [enc(x) | f | 0]) against
+    nfs_project_gather followed by nfs_posenc_bf16: the same arithmetic, so the rows are bit-identical - including
+    points behind the camera / outside the map (zero features) and non-octave bands."""
+    import math
+    from helpers import bit_equal
+    from nfs_b200 import _lib, ops
+    from nfs_b200._lib import ptr
+    from nfs_b200.mlp import encode_operand, pad_in
+    from nfs_b200.ops import _stream
+    g = torch.Generator().manual_seed(P)
+    x = ((torch.rand(P, 3, generator=g) - 0.5) * 8).to(cuda)
+    fmap = torch.randn(1, 9, 9, C, generator=g).to(cuda)
+    pose = torch.eye(4); pose[2, 3] = 4.0; pose[0, 3] = 0.3
+    pose_inv = torch.inverse(pose).contiguous().to(cuda)      # (torch.inverse returns a column-major tensor)
+    focal = 0.5 * 128 / math.tan(0.5 * 0.6911112)
+    for octaves in (True, False):
+        freqs = 2.0 ** torch.arange(pos_freq, dtype=torch.float32) if octaves else torch.linspace(1.0, 2.0 ** (pos_freq - 1), pos_freq)
+        k0 = pad_in(3 * (2 * pos_freq + 1) + C)
+        _, _, _, feats = ops.project_gather(x, pose.to(cuda), focal, 128, 128, features=fmap, want_projection=False,
+                                            pose_inv=pose_inv)
+        ref = encode_operand(x, freqs, k0, extra=feats)
+        out = torch.full((P, k0), float("nan"), device=cuda, dtype=torch.bfloat16)
+        fr = freqs.to(cuda)
+        _lib.call("nfs_g3_operand", ptr(x), ptr(pose_inv), float(focal), 128, 128, ptr(fmap), 9, 9, C, ptr(fr), pos_freq,
+                  int(octaves), P, k0, k0, ptr(out), _stream())
+        assert bit_equal(out, ref), (octaves, float((out.float() - ref.float()).abs().max()))
+        if P >= 1000:                                      # both kinds of points occur: inside the map and outside it
+            assert float(feats.abs().max()) > 0 and bool((feats.abs().sum(1) == 0).any())
+
+
+def test_gate_kernels_on_the_operand_vs_torch(cuda):
+    """nfs_gate_scale_bf16 / nfs_gate_bwd_operand (dino_feature_model.py:188-195 and its backward, evaluated on the bf16
+    operand the first fusion layer consumed) against fp32 torch on the same bf16 values."""
+    from nfs_b200 import _lib
+    from nfs_b200._lib import ptr
+    from nfs_b200.ops import _stream
+    g = torch.Generator().manual_seed(7)
+    for P, enc_w, width, k_pad, dc_pitch in [(1, 75, 139, 192, 256), (1000, 63, 127, 128, 128), (513, 39, 39, 64, 256)]:
+        c = torch.zeros(P, k_pad, dtype=torch.bfloat16)
+        c[:, :width] = torch.randn(P, width, generator=g).to(torch.bfloat16)
+        gate = torch.softmax(torch.randn(P, 2, generator=g), dim=-1)
+        dc = torch.zeros(P, dc_pitch, dtype=torch.bfloat16)
+        dc[:, :width] = torch.randn(P, width, generator=g).to(torch.bfloat16)
+        cc, gc, dcc = c.to(cuda), gate.to(cuda), dc.to(cuda)
+        out = torch.empty_like(cc)
+        _lib.call("nfs_gate_scale_bf16", ptr(cc), k_pad, ptr(gc), P, enc_w, k_pad, ptr(out), k_pad, _stream())
+        scale = torch.cat([gate[:, :1].expand(-1, enc_w), gate[:, 1:].expand(-1, k_pad - enc_w)], dim=1)
+        assert torch.equal(out.cpu(), (c.float() * scale).to(torch.bfloat16))
+        dlog = torch.full((P, 64), float("nan"), device=cuda, dtype=torch.bfloat16)
+        _lib.call("nfs_gate_bwd_operand", ptr(cc), k_pad, ptr(gc), ptr(dcc), dc_pitch, P, enc_w, width, 64, ptr(dlog), _stream())
+        prod = c[:, :width].double() * dc[:, :width].double()
+        dg = torch.stack([prod[:, :enc_w].sum(1), prod[:, enc_w:].sum(1)], dim=1)
+        ref = gate.double() * (dg - (gate.double() * dg).sum(1, keepdim=True))
+        got = dlog.float().cpu()
+        assert torch.equal(got[:, 2:], torch.zeros(P, 62))
+        assert float((got[:, :2].double() - ref).abs().max()) <= 1e-2 * float(ref.abs().max()) + 1e-3
+
+
+def test_conditioned_render_operand_route_matches_gather_route(cuda, monkeypatch):
+    """pipeline.render_rays_conditioned with the fused operand producer (default) against the kernel-by-kernel route
+    (NFS_G3_OPERAND=0: nfs_project_gather -> NeRFWithDINO(points, dirs, features)): identical operands, so identical
+    renderings and parameter gradients."""
+    import math
+    from models.nerf_mlp import NeRFWithDINO
+    from nfs_b200 import pipeline
+    from oracle import nerf_oracle as O
+    N, S = 300, 48
+    ro, rd = O.lego_rays(N, H=128, W=128, seed=3)
+    ro, rd = ro.to(cuda), rd.to(cuda)
+    torch.manual_seed(8)
+    mod = NeRFWithDINO(pos_freq=12, dino_dim=64)
+    with torch.no_grad():
+        mod.density_mlp.density_head.bias.fill_(0.3)
+    mod = mod.to(cuda)
+    fmap = torch.randn(1, 9, 9, 64, generator=torch.Generator().manual_seed(1)).to(cuda)
+    pose = torch.eye(4); pose[2, 3] = 4.0
+    pose = pose.to(cuda)
+    focal = 0.5 * 128 / math.tan(0.5 * 0.6911112)
+    t_rand = torch.rand(N, S, generator=torch.Generator().manual_seed(2)).to(cuda)
+    tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(4)).to(cuda)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NFS_G3_OPERAND", mode)
+        mod.zero_grad()
+        out = pipeline.render_rays_conditioned(mod, ro, rd, 2.0, 6.0, S, pose, focal, 128, 128, fmap, perturb=True, t_rand=t_rand)
+        ((out["rgb"] - tgt) ** 2).mean().backward()
+        res[mode] = (out["rgb"].detach().clone(), [p.grad.clone() for p in mod.parameters()])
+    assert torch.equal(res["1"][0], res["0"][0])
+    for a, b in zip(res["1"][1], res["0"][1]):
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12
