@@ -32,3 +32,19 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _warm_cpu_oracle():
+    """ATen's FIRST multi-threaded evaluation of the compositing arithmetic in a process is occasionally (~1 in 12
+    processes on the 16-core GPU boxes) off by ~6e-5 in one host thread's share of the rays; every later evaluation is
+    bit-stable (scripts/dev/smoke_dbg2.py, __graft_entry__.smoke).  The parity tests hold the CUDA kernels to 1e-5
+    against that oracle, so the checker is warmed once per session on throw-away inputs."""
+    import torch
+    from oracle import nerf_oracle as O
+    g = torch.Generator().manual_seed(123)
+    n, S = 2048, 64
+    z = torch.sort(torch.rand(n, S, generator=g) * 4 + 2, dim=-1).values
+    for _ in range(2):
+        O.render(torch.rand(n, S, 3, generator=g), torch.randn(n, S, 1, generator=g) * 10, z, torch.randn(n, 3, generator=g))
+    yield
