@@ -178,7 +178,7 @@ class NeRFDINOTrainer:
             self.H, self.W, self.focal = hwf
             self.images = [img.permute(1, 2, 0).float().to(self.device) for img in images]
             self.poses = [p.float().to(self.device) for p in poses]
-            self.pose_invs = [torch.inverse(p) for p in self.poses]
+            self.pose_invs = [torch.inverse(p).contiguous() for p in self.poses]
         else:
             self.test_images = [img.permute(1, 2, 0).float().to(self.device) for img in images]
             self.test_poses = [p.float().to(self.device) for p in poses]
@@ -204,15 +204,24 @@ class NeRFDINOTrainer:
         n_rays = rays_o.shape[0]
         pts_flat = pts.reshape(-1, 3)
         feats = None
+        dirs = rays_d.unsqueeze(1).expand(-1, N_samples, -1).reshape(-1, 3)
+        plan = self.nerf_model._get_plan() if hasattr(self.nerf_model, "_get_plan") else None
         if self.use_dino:
             if self.dino_features_precomputed is None:
                 raise RuntimeError("use_dino: call set_feature_maps() with the per-view (1,Hp,Wp,C) feature maps")
             idx = view_idx if self.nerf_model.training else 0
-            _, _, _, feats = _ops.project_gather(pts_flat, self.poses[idx], self.focal, self.H, self.W,
-                                                 features=self.dino_features_precomputed[idx], want_projection=False,
-                                                 pose_inv=self.pose_invs[idx])
-        dirs = rays_d.unsqueeze(1).expand(-1, N_samples, -1).reshape(-1, 3)
-        rgb, density = self.nerf_model(pts_flat, dirs, feats)
+            if hasattr(plan, "chain_a_bwd") and plan.D > 0 and os.environ.get("NFS_G3_OPERAND", "1") != "0":
+                # projection + feature lookup + encoding as the producer of the model's first operand (nfs_g3_operand)
+                from nfs_b200 import mlp_g3
+                rgb, density = mlp_g3.g3_forward_from_map(plan, pts_flat, dirs, self.dino_features_precomputed[idx],
+                                                          self.pose_invs[idx], self.focal, self.H, self.W)
+                feats = False
+            else:
+                _, _, _, feats = _ops.project_gather(pts_flat, self.poses[idx], self.focal, self.H, self.W,
+                                                     features=self.dino_features_precomputed[idx], want_projection=False,
+                                                     pose_inv=self.pose_invs[idx])
+        if feats is not False:
+            rgb, density = self.nerf_model(pts_flat, dirs, feats)
         rgb_r, depth_r, weights = self.volume_renderer(rgb.reshape(n_rays, N_samples, 3),
                                                        density.reshape(n_rays, N_samples, 1), z_vals, rays_d)
         return {"rgb": rgb_r, "depth": depth_r, "weights": weights}

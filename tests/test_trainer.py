@@ -103,6 +103,7 @@ def test_trainer_with_feature_maps(cuda, tmp_path):
     cfg["nerf_model"]["pos_freq"] = 12
     cfg["training"]["batch_size"] = 256
     cfg["output"] = {"save_dir": str(tmp_path), "val_freq": 100, "save_freq": 100}
+    torch.manual_seed(0)                     # (initialisation and the per-step draws come from the global generators)
     tr = NeRFDINOTrainer(cfg, device=cuda)
     tr.load_synthetic(n_test=1)
     with pytest.raises(RuntimeError):
