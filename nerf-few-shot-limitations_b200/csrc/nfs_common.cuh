@@ -31,7 +31,7 @@ static inline int check_launch(const char *where) {
 // kernel: every thread executes pdl_wait() before its first access to global memory (reads AND writes - the
 // predecessor may still be reading what this kernel overwrites); pdl_trigger() only after the CTA holds its TMEM
 // allocation (a dependent CTA co-resident on the SM could otherwise take the columns and wait for this grid forever).
-// Without the launch attribute both instructions do nothing.  NFS_PDL=0 launches everything the classic way.
+// Without the launch attribute both instructions do nothing.  Opt-in: NFS_PDL=1 (default: classic stream order).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
